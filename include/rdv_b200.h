@@ -1,0 +1,188 @@
+/* rdv_b200.h -- C ABI of librdv_b200.so: the B200 (sm_100a) batched replacement for the
+ * RendezvousEnv step()/reset() hot path of cfdeinza/reinforcement-learning-rendezvous.
+ *
+ * Boundary rules
+ *   - extern "C", plain pointers and sizes only; no C++/torch types cross this line.
+ *   - Every buffer is owned by the caller (PyTorch CUDA tensors in the Python host);
+ *     the library never allocates, frees or keeps device memory after a call returns.
+ *   - All entry points enqueue work on the caller's stream and return immediately
+ *     (no device synchronisation inside); 0 = success, negative = RdvStatus error.
+ *   - Results are a pure function of (params, state, actions, seed, env_offset,
+ *     episode index): independent of grid shape and of how envs are sharded over GPUs.
+ *   - There is no CPU fallback: on a machine without a usable GPU the calls return
+ *     RDV_ERR_CUDA.
+ *
+ * Each entry point cites the reference interface (file:line under /root/reference)
+ * it replaces.
+ */
+#ifndef RDV_B200_H
+#define RDV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDV_ABI_VERSION 3
+#define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
+#define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
+#define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
+
+/* Rows of RdvState.f64 ([RDV_NF64][ld], structure-of-arrays, one column per env). */
+enum {
+    RDV_RCX = 0, RDV_RCY, RDV_RCZ,            /* rc: chaser position, LVLH [m]            */
+    RDV_VCX, RDV_VCY, RDV_VCZ,                /* vc: chaser velocity, LVLH [m/s]          */
+    RDV_QCW, RDV_QCX, RDV_QCY, RDV_QCZ,       /* qc: chaser attitude (scalar first)       */
+    RDV_WCX, RDV_WCY, RDV_WCZ,                /* wc: chaser rate, chaser body frame       */
+    RDV_QTW, RDV_QTX, RDV_QTY, RDV_QTZ,       /* qt: target attitude                      */
+    RDV_WTX, RDV_WTY, RDV_WTZ,                /* wt: target rate, target body frame       */
+    RDV_TDV, RDV_TDW,                         /* total_delta_v / total_delta_w (:201-202) */
+    RDV_EPRET,                                /* return of the running episode (Monitor 'r') */
+    RDV_NF64
+};
+/* Rows of RdvState.i32 ([RDV_NI32][ld]). t = round(step*dt, 3) and the bubble radius
+ * max(bubble0 - step*rate, bubble_min) are derived from RDV_I_STEP (:193-198). */
+enum { RDV_I_STEP = 0, RDV_I_SUCCESS, RDV_I_COLLIDED, RDV_I_EPISODE, RDV_NI32 };
+
+/* Slots of the device statistics vector (double[RDV_NSTATS], accumulated with atomics). */
+enum {
+    RDV_S_STEPS = 0, RDV_S_EPISODES, RDV_S_RETURN, RDV_S_LENGTH, RDV_S_SUCCEEDED, RDV_S_COLLIDED,
+    RDV_S_DELTA_V, RDV_S_DELTA_W,
+    RDV_S_END_OBS, RDV_S_END_TIME, RDV_S_END_BUBBLE, RDV_S_END_ATTITUDE,   /* :377 end reasons */
+    RDV_S_REWARD, RDV_S_RK_ACCEPTED, RDV_S_RK_REJECTED, RDV_S_FAILURES,
+    RDV_NSTATS
+};
+
+/* Columns of the per-episode record written for envs whose episode just ended. */
+enum { RDV_EP_RETURN = 0, RDV_EP_LENGTH, RDV_EP_SUCCESS, RDV_EP_COLLIDED, RDV_EP_DELTA_V, RDV_EP_DELTA_W,
+       RDV_EP_NCOL };
+
+typedef enum RdvStatus {
+    RDV_OK = 0,
+    RDV_ERR_NULL = -1,        /* a required pointer is NULL                          */
+    RDV_ERR_SIZE = -2,        /* n < 0, ld < n, or a bad enum value                  */
+    RDV_ERR_ALIGN = -3,       /* a pointer is not aligned for its vector access      */
+    RDV_ERR_PARAMS = -4,      /* rdv_params_derive rejected the configuration        */
+    RDV_ERR_CUDA = -5,        /* kernel launch / CUDA runtime failure                */
+    RDV_ERR_UNSUPPORTED = -6
+} RdvStatus;
+
+/* Integrator used for the two attitude propagations (rendezvous_env.py:552-604). */
+enum {
+    RDV_INTEGRATOR_RK45 = 0,       /* adaptive Dormand-Prince replica of scipy solve_ivp(RK45) */
+    RDV_INTEGRATOR_CLOSED_FORM = 1 /* exact torque-free isotropic rotation; opt-in, gated      */
+};
+
+/* Environment constants.  The first block mirrors the RendezvousEnv constructor
+ * (rendezvous_env.py:17-70) and reward_kwargs (:313); fill it (or start from
+ * rdv_params_default) and call rdv_params_derive, which fills the second block
+ * exactly as the constructor does (:75-126).  Passed BY VALUE to the kernels. */
+typedef struct RdvParams {
+    /* ---- inputs ---- */
+    double rc0[3], vc0[3], qc0[4], wc0[3], qt0[4], wt0[3];      /* nominal initial state        */
+    double rc0_range, vc0_range, qc0_range, wc0_range, qt0_range, wt0_range;
+    double koz_radius, corridor_half_angle, h, dt, t_max;
+    double collision_coef, bonus_coef, fuel_coef, att_coef;     /* get_bubble_reward kwargs     */
+    double inertia_c[9], inertia_t[9];                          /* row-major 3x3 (:75-79,:96-100) */
+    double torque_c[3];                                         /* held chaser torque (env: 0)  */
+    int32_t integrator;                                         /* RDV_INTEGRATOR_*             */
+    int32_t reserved0;
+    /* ---- derived by rdv_params_derive ---- */
+    double inv_inertia_c[9], inv_inertia_t[9];
+    double max_delta_v, max_delta_w, max_axial_distance, max_axial_speed, max_wc;
+    double max_attitude_error, max_rd_error, max_vd_error, max_qd_error, max_wd_error;
+    double rd[3], capture_axis[3], corridor_axis[3];
+    double bubble0, bubble_rate, bubble_min, n;
+    double cw[17];                 /* non-zero entries of the CW transition matrix (dynamics.py:40-47) */
+    float max_delta_v_f32;         /* fp32 constants used when actions are float32 (NumPy-2 promotion) */
+    float fuel_num_f32;            /* (float)(dt*fuel_coef)                                            */
+    float fuel_den_f32;            /* (float)(3*max_delta_v)                                           */
+    int32_t iso_c, iso_t;          /* 1: inertia = c*Identity and zero torque -> rate is constant      */
+    int32_t reserved1;
+} RdvParams;
+
+/* Environment state: device pointers into caller-owned buffers. */
+typedef struct RdvState {
+    double  *f64;     /* [RDV_NF64][ld] */
+    int32_t *i32;     /* [RDV_NI32][ld] */
+    int64_t  ld;      /* leading dimension (>= n), in elements */
+} RdvState;
+
+/* Inputs/outputs of one batched step.  Nullable members are marked. */
+typedef struct RdvStepIO {
+    const void *actions;     /* [n][6] row-major, float32 (act_f64 = 0) or float64 (act_f64 = 1)  */
+    int32_t  act_f64;
+    int32_t  auto_reset;     /* 1: envs that finish are reset in the same launch (VecEnv semantics) */
+    float   *obs;            /* [n][17] observation after the step (after the reset if auto-reset) */
+    double  *reward;         /* [n]                                                                */
+    uint8_t *done;           /* [n]                                                                */
+    float   *terminal_obs;   /* nullable [n][17]: last observation of finished episodes only       */
+    int8_t  *end_reason;     /* nullable [n]: -1 running, 0 obs, 1 time, 2 bubble, 3 attitude      */
+    double  *episode_record; /* nullable [n][RDV_EP_NCOL]: written for finished episodes only      */
+    double  *stats;          /* nullable [RDV_NSTATS] device accumulator                           */
+    int32_t *reset_scratch;  /* [n+2] int32, zeroed ONCE by the caller; required when auto_reset   */
+} RdvStepIO;
+
+/* -- constants ------------------------------------------------------------------------------ */
+int  rdv_abi_version(void);
+int  rdv_sizeof_params(void);
+const char *rdv_strerror(int status);
+
+/* Defaults of RendezvousEnv.__init__ (rendezvous_env.py:17-70). */
+void rdv_params_default(RdvParams *p);
+/* Derived constants of RendezvousEnv.__init__ (rendezvous_env.py:75-126) and the CW matrix of
+ * clohessy_wiltshire_solution (utils/dynamics.py:40-47).  Returns RDV_ERR_PARAMS when the
+ * constructor's assertions (:155-156) would fail or a matrix is singular. */
+int  rdv_params_derive(RdvParams *p);
+
+/* -- the hot path ------------------------------------------------------------------------------ */
+/* RendezvousEnv.step (rendezvous_env.py:160-221) for n envs, plus the auto-reset that SB3's
+ * DummyVecEnv.step_wait performs around it (main.py:33-34).  env_offset is the global index
+ * of env 0 of this shard (Philox key for resets). */
+int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t n,
+             uint64_t seed, int64_t env_offset, void *cuda_stream);
+
+/* RendezvousEnv.reset (rendezvous_env.py:223-270) for the envs selected by mask (NULL = all).
+ * The 24 uniform draws come from Philox4x32-10 keyed by (seed; env_offset+i, episode index),
+ * or from `uniforms` ([n][24], in [0,1)) when it is not NULL (test hook that pins the
+ * draw order against the reference).  bump_episode: 1 increments the episode index first. */
+int rdv_reset(const RdvParams *p, const RdvState *s, const uint8_t *mask, const double *uniforms,
+              float *obs, int64_t n, uint64_t seed, int64_t env_offset, int bump_episode,
+              void *cuda_stream);
+
+/* RendezvousEnv.get_observation (rendezvous_env.py:294-311). */
+int rdv_observe(const RdvParams *p, const RdvState *s, float *obs, int64_t n, void *cuda_stream);
+
+/* get_errors / check_collision / check_success / dist_from_koz (rendezvous_env.py:388-468,
+ * :510-537) -- what monte_carlo.evaluate and the callbacks read after every step.
+ * errors [n][4]; collision, success [n] (success honours the sticky collided flag); koz [n]. */
+int rdv_errors(const RdvParams *p, const RdvState *s, double *errors, uint8_t *collision,
+               uint8_t *success, double *koz, int64_t n, void *cuda_stream);
+
+/* After a caller overwrote the state (monte_carlo.py:106-112 does), optionally recompute the
+ * sticky collided / success flags the way reset() does (:260-261).  The reference evaluator
+ * does NOT do this; it is provided for callers that want consistent flags. */
+int rdv_refresh_flags(const RdvParams *p, const RdvState *s, int64_t n, void *cuda_stream);
+
+/* -- fused policy (model.predict of an SB3 MlpPolicy, monte_carlo.py:128-133) ------------------- */
+/* fp32 tanh MLP obs[17] -> hidden -> hidden -> action[6], deterministic mean clipped to [-1,1].
+ * Weights are row-major [out][in] as in torch.nn.Linear. */
+typedef struct RdvPolicy {
+    const float *w0, *b0;    /* [H][17], [H] */
+    const float *w1, *b1;    /* [H][H],  [H] */
+    const float *w2, *b2;    /* [6][H],  [6] */
+    int32_t hidden;          /* H, must be 64 */
+    int32_t reserved;
+} RdvPolicy;
+int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
+
+/* Measured-peak helper for the roofline: runs `iters` dependent-chain-free DFMA per thread on
+ * every SM and writes one double per thread to `sink` ([blocks*threads]).  flops = 2*iters*16*
+ * blocks*threads. */
+int rdv_fp64_peak_probe(double *sink, int blocks, int threads, int iters, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDV_B200_H */

@@ -1,0 +1,360 @@
+// rdv_math.cuh -- device-side fp64 math of the RendezvousEnv hot path for sm_100a.
+//
+// One thread owns one environment; everything here works on registers.  The
+// functions restate reference behaviour (file:line under /root/reference) but are
+// written for the B200 fp64 pipe: divisions by run-time values use MUFU seeds +
+// FMA refinement (<= 1 ulp), divisions by constants use host-precomputed
+// reciprocals, the quaternion normalisation inside the ODE right-hand side is done
+// once with an rsqrt, and err**-0.2 of the step-size controller is a MUFU seed +
+// two Newton steps instead of a generic pow().  The deviations from the reference's
+// operation order are at the 1e-16 level; the parity bar is 1e-9 (BASELINE.json).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rdv_b200.h"
+
+#define RDV_DEV __device__ __forceinline__
+
+namespace rdv {
+
+// ---------------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------------
+// 1/x for normal positive/negative x: MUFU.RCP64H seed (>= 20 good bits) + 2 Newton steps.
+RDV_DEV double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed + one cubic (Halley-type) step + one
+// Newton clean-up.  <= 1 ulp.
+RDV_DEV double fast_rsqrt(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double m = x * r;
+    double e = fma(-m, r, 1.0);                 // 1 - x r^2
+    double p = fma(0.375, e, 0.5);
+    r = fma(r * e, p, r);                       // r (1 + e/2 + 3e^2/8)
+    m = x * r;
+    e = fma(-m, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    return r;
+}
+
+// x**(-0.1) for x in [1e-30, 1e30]: fp32 MUFU.LG2/EX2 seed (rel. err ~1e-6) and two Newton
+// steps on y -> y (1 + (1 - x y^10)/10), which converge quadratically (11/2 e^2).
+// Used for err_norm**-0.2 with x = err_norm^2 (scipy rk.py:160,170) and for
+// (0.01/max(d1,d2))**0.2 (scipy common.py:131) with x = max(d1,d2)^2 / 1e-4.
+RDV_DEV double pow_neg_tenth(double x)
+{
+    if (!(x >= 1e-30 && x <= 1e30)) return pow(x, -0.1);     // cold path, keeps exact semantics
+    float lf = __log2f((float)x);
+    double y = (double)exp2f(-0.1f * lf);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4, y10 = y8 * y2;
+        double res = fma(-x, y10, 1.0);
+        y = fma(y * 0.1, res, y);
+    }
+    return y;
+}
+
+RDV_DEV double dot3(const double a[3], const double b[3]) { return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])); }
+RDV_DEV double dot4(const double a[4], const double b[4])
+{
+    return fma(a[3], b[3], fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])));
+}
+RDV_DEV void cross3(const double a[3], const double b[3], double o[3])
+{
+    o[0] = fma(a[1], b[2], -(a[2] * b[1]));
+    o[1] = fma(a[2], b[0], -(a[0] * b[2]));
+    o[2] = fma(a[0], b[1], -(a[1] * b[0]));
+}
+
+// Rotation matrix of quat2mat (utils/quaternions.py:48-68), including its re-normalisation.
+struct Rot { double m[9]; };
+RDV_DEV Rot rot_from_quat(const double q_in[4])
+{
+    double r = fast_rsqrt(dot4(q_in, q_in));
+    double w = q_in[0] * r, x = q_in[1] * r, y = q_in[2] * r, z = q_in[3] * r;
+    double ww = w * w;
+    Rot R;
+    R.m[0] = fma(2.0, fma(x, x, ww), -1.0); R.m[1] = 2.0 * fma(x, y, -(w * z)); R.m[2] = 2.0 * fma(x, z, w * y);
+    R.m[3] = 2.0 * fma(x, y, w * z); R.m[4] = fma(2.0, fma(y, y, ww), -1.0); R.m[5] = 2.0 * fma(y, z, -(w * x));
+    R.m[6] = 2.0 * fma(x, z, -(w * y)); R.m[7] = 2.0 * fma(y, z, w * x); R.m[8] = fma(2.0, fma(z, z, ww), -1.0);
+    return R;
+}
+RDV_DEV void rot_apply(const Rot &R, const double v[3], double o[3])            // body -> LVLH (:490-508)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = fma(R.m[3 * i + 2], v[2], fma(R.m[3 * i + 1], v[1], R.m[3 * i] * v[0]));
+}
+RDV_DEV void rot_apply_T(const Rot &R, const double v[3], double o[3])          // LVLH -> body (:470-488)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = fma(R.m[6 + i], v[2], fma(R.m[3 + i], v[1], R.m[i] * v[0]));
+}
+
+// angle_between_vectors (utils/general.py:163-181): acos(round(cos, 5)), with numpy's
+// round == rint(x*1e5)/1e5.  The final division is IEEE so that +-1 stay exactly +-1.
+RDV_DEV double rounded_angle_from(double dot, double n1sq, double n2sq)
+{
+    double c = dot * fast_rsqrt(n1sq * n2sq);
+    return acos(__ddiv_rn(rint(c * 1e5), 1e5));
+}
+
+// ---------------------------------------------------------------------------------
+// Attitude ODE right-hand side (utils/dynamics.py:93-175).
+//   ISO = true : inertia is c*Identity and the torque is zero, so w_dot == 0 exactly and
+//                only the four quaternion derivatives are live (hw = 0.5*w is constant).
+//   ISO = false: full 3x3 inertia, held torque.
+// ---------------------------------------------------------------------------------
+struct BodyConst { const double *I, *Iinv, *tau; };
+
+template <bool ISO>
+RDV_DEV void attitude_rhs(const double *y, const double *hw_iso, const BodyConst &b, double *f)
+{
+    double r = fast_rsqrt(dot4(y, y));             // q/|q| (dynamics.py:108, :134 -- applied once)
+    double h1, h2, h3;
+    if (ISO) { h1 = hw_iso[0]; h2 = hw_iso[1]; h3 = hw_iso[2]; }
+    else     { h1 = 0.5 * y[4]; h2 = 0.5 * y[5]; h3 = 0.5 * y[6]; }
+    // 0.5 * Omega(w) q  (dynamics.py:137-150), scaled by 1/|q| afterwards
+    double g0 = -fma(h3, y[3], fma(h2, y[2], h1 * y[1]));
+    double g1 = fma(-h2, y[3], fma(h3, y[2], h1 * y[0]));
+    double g2 = fma(h1, y[3], fma(-h3, y[1], h2 * y[0]));
+    double g3 = fma(-h1, y[2], fma(h2, y[1], h3 * y[0]));
+    f[0] = g0 * r; f[1] = g1 * r; f[2] = g2 * r; f[3] = g3 * r;
+    if (!ISO) {
+        const double *w = y + 4;
+        double L[3], c[3], t[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) L[i] = fma(b.I[3 * i + 2], w[2], fma(b.I[3 * i + 1], w[1], b.I[3 * i] * w[0]));
+        cross3(w, L, c);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) t[i] = b.tau[i] - c[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            f[4 + i] = fma(b.Iinv[3 * i + 2], t[2], fma(b.Iinv[3 * i + 1], t[1], b.Iinv[3 * i] * t[0]));
+    }
+}
+
+// Dormand-Prince tableau (scipy rk.py, class RK45)
+#define RK_A21 (1.0 / 5)
+#define RK_A31 (3.0 / 40)
+#define RK_A32 (9.0 / 40)
+#define RK_A41 (44.0 / 45)
+#define RK_A42 (-56.0 / 15)
+#define RK_A43 (32.0 / 9)
+#define RK_A51 (19372.0 / 6561)
+#define RK_A52 (-25360.0 / 2187)
+#define RK_A53 (64448.0 / 6561)
+#define RK_A54 (-212.0 / 729)
+#define RK_A61 (9017.0 / 3168)
+#define RK_A62 (-355.0 / 33)
+#define RK_A63 (46732.0 / 5247)
+#define RK_A64 (49.0 / 176)
+#define RK_A65 (-5103.0 / 18656)
+#define RK_B1 (35.0 / 384)
+#define RK_B3 (500.0 / 1113)
+#define RK_B4 (125.0 / 192)
+#define RK_B5 (-2187.0 / 6784)
+#define RK_B6 (11.0 / 84)
+#define RK_E1 (-71.0 / 57600)
+#define RK_E3 (71.0 / 16695)
+#define RK_E4 (-71.0 / 1920)
+#define RK_E5 (17253.0 / 339200)
+#define RK_E6 (-22.0 / 525)
+#define RK_E7 (1.0 / 40)
+#define RK_RTOL 1e-7     /* rendezvous_env.py:567, :594 */
+#define RK_ATOL 1e-6     /* rendezvous_env.py:568, :595 */
+
+// solve_ivp(fun, (0, dt), y, method='RK45', t_eval=[dt], rtol=1e-7, atol=1e-6) -- the adaptive
+// controller of scipy (RungeKutta.__init__ rk.py:85-103, select_initial_step common.py:68-134,
+// _step_impl rk.py:111-179, rk_step rk.py:14-69).  On the step that reaches dt the t_eval
+// branch (ivp.py:710-728) evaluates the dense-output polynomial at x == 1, which equals y_new
+// up to ~1 ulp; y_new is used.  Returns accepted steps, or -1 on TOO_SMALL_STEP / non-finite
+// error norm (the reference raises there); y is left at the last accepted state.
+template <bool ISO>
+RDV_DEV int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b, int &n_rejected)
+{
+    constexpr int NA = ISO ? 4 : 7;         // components with a non-zero derivative
+    double hw[3] = {0.5 * y[4], 0.5 * y[5], 0.5 * y[6]};
+    double K[7][NA];
+    attitude_rhs<ISO>(y, hw, b, K[0]);
+
+    // ---- select_initial_step (order 4) ----
+    double h_abs;
+    {
+        double inv_sc[7], d0s = 0.0, d1s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            inv_sc[i] = fast_rcp(fma(fabs(y[i]), RK_RTOL, RK_ATOL));
+            double a = y[i] * inv_sc[i];
+            d0s = fma(a, a, d0s);
+        }
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            double a = K[0][i] * inv_sc[i];
+            d1s = fma(a, a, d1s);
+        }
+        d0s *= (1.0 / 7.0);
+        d1s *= (1.0 / 7.0);                                  // squares of the rms norms d0, d1
+        double h0;
+        if (d0s < 1e-10 || d1s < 1e-10) h0 = 1e-6;
+        else h0 = 0.01 * sqrt(d0s * fast_rcp(d1s));
+        h0 = fmin(h0, dt);
+        double y1[7], f1[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) y1[i] = fma(h0, K[0][i], y[i]);
+#pragma unroll
+        for (int i = NA; i < 7; ++i) y1[i] = y[i];
+        attitude_rhs<ISO>(y1, hw, b, f1);
+        double d2s = 0.0;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            double a = (f1[i] - K[0][i]) * inv_sc[i];
+            d2s = fma(a, a, d2s);
+        }
+        double inv_h0 = fast_rcp(h0);
+        d2s = d2s * (1.0 / 7.0) * inv_h0 * inv_h0;
+        double h1;
+        if (d1s <= 1e-30 && d2s <= 1e-30) h1 = fmax(1e-6, h0 * 1e-3);
+        else h1 = pow_neg_tenth(fmax(d1s, d2s) * 1e4);        // (0.01/max(d1,d2))**(1/5)
+        h_abs = fmin(fmin(100.0 * h0, h1), dt);
+    }
+
+    double t = 0.0;
+    int accepted = 0;
+    for (;;) {
+        // ---- one solver.step(): _step_impl ----
+        const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        double t_new, h;
+        double y_new[NA];
+        for (;;) {
+            if (h_abs < min_step) return -1;
+            t_new = t + h_abs;
+            if (t_new - dt > 0.0) t_new = dt;
+            h = t_new - t;
+            h_abs = fabs(h);
+            // ---- rk_step: six stages, FSAL row K[6] ----
+            double ys[7];
+            if (ISO) { ys[4] = y[4]; ys[5] = y[5]; ys[6] = y[6]; }
+#pragma unroll
+            for (int i = 0; i < NA; ++i) ys[i] = fma(K[0][i] * RK_A21, h, y[i]);
+            attitude_rhs<ISO>(ys, hw, b, K[1]);
+#pragma unroll
+            for (int i = 0; i < NA; ++i) ys[i] = fma(fma(K[1][i], RK_A32, K[0][i] * RK_A31), h, y[i]);
+            attitude_rhs<ISO>(ys, hw, b, K[2]);
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+                ys[i] = fma(fma(K[2][i], RK_A43, fma(K[1][i], RK_A42, K[0][i] * RK_A41)), h, y[i]);
+            attitude_rhs<ISO>(ys, hw, b, K[3]);
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+                ys[i] = fma(fma(K[3][i], RK_A54, fma(K[2][i], RK_A53, fma(K[1][i], RK_A52, K[0][i] * RK_A51))), h,
+                            y[i]);
+            attitude_rhs<ISO>(ys, hw, b, K[4]);
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+                ys[i] = fma(fma(K[4][i], RK_A65,
+                                fma(K[3][i], RK_A64, fma(K[2][i], RK_A63, fma(K[1][i], RK_A62, K[0][i] * RK_A61)))),
+                            h, y[i]);
+            attitude_rhs<ISO>(ys, hw, b, K[5]);
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+                ys[i] = fma(h,
+                            fma(K[5][i], RK_B6,
+                                fma(K[4][i], RK_B5, fma(K[3][i], RK_B4, fma(K[2][i], RK_B3, K[0][i] * RK_B1)))),
+                            y[i]);
+            attitude_rhs<ISO>(ys, hw, b, K[6]);
+#pragma unroll
+            for (int i = 0; i < NA; ++i) y_new[i] = ys[i];
+            // ---- error norm: rms((K^T E) h / scale), scale = atol + max(|y|,|y_new|) rtol ----
+            double es = 0.0;
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                double e = fma(K[6][i], RK_E7,
+                               fma(K[5][i], RK_E6,
+                                   fma(K[4][i], RK_E5, fma(K[3][i], RK_E4, fma(K[2][i], RK_E3, K[0][i] * RK_E1)))));
+                double sc = fma(fmax(fabs(y[i]), fabs(y_new[i])), RK_RTOL, RK_ATOL);
+                e = e * h * fast_rcp(sc);
+                es = fma(e, e, es);
+            }
+            es *= (1.0 / 7.0);                         // err_norm^2
+            if (!(es < 1.0e300)) return -1;            // NaN / inf: the reference shrinks h to failure
+            if (es < 1.0) {
+                // factor = min(10, 0.9 err^-0.2); err^-0.2 >= 10/0.9 whenever err^2 <= 3.5e-11
+                double factor = (es < 3.0e-11) ? 10.0 : fmin(10.0, 0.9 * pow_neg_tenth(es));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                break;
+            }
+            h_abs *= (es > 1.0e7) ? 0.2 : fmax(0.2, 0.9 * pow_neg_tenth(es));
+            rejected = true;
+            ++n_rejected;
+        }
+        ++accepted;
+        t = t_new;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) { y[i] = y_new[i]; K[0][i] = K[6][i]; }
+        if (t - dt >= 0.0) return accepted;
+    }
+}
+
+// Closed-form alternative (opt-in, RDV_INTEGRATOR_CLOSED_FORM; only valid for ISO bodies):
+// with w constant, q' = 0.5 Omega(w) q/|q| has the exact solution
+// q(dt) = q cos(a) + (Omega(w) q) sin(a)/|w|, a = |w| dt / (2|q|).  The RK45 replica itself
+// is only accurate to ~1e-10..1e-8 per step, so this differs from the reference by the
+// reference's own truncation error (SURVEY.md section 7 hard part 7); callers gate it.
+RDV_DEV void closed_form_attitude(double (&y)[7], const double dt)
+{
+    double wsq = fma(y[6], y[6], fma(y[5], y[5], y[4] * y[4]));
+    if (wsq == 0.0) return;
+    double rq = fast_rsqrt(dot4(y, y));
+    double wn = sqrt(wsq);
+    double s, c;
+    sincos(0.5 * wn * dt * rq, &s, &c);
+    double k = s / wn;
+    double g0 = -fma(y[6], y[3], fma(y[5], y[2], y[4] * y[1]));
+    double g1 = fma(-y[5], y[3], fma(y[6], y[2], y[4] * y[0]));
+    double g2 = fma(y[4], y[3], fma(-y[6], y[1], y[5] * y[0]));
+    double g3 = fma(-y[4], y[2], fma(y[5], y[1], y[6] * y[0]));
+    y[0] = fma(g0, k, y[0] * c); y[1] = fma(g1, k, y[1] * c);
+    y[2] = fma(g2, k, y[2] * c); y[3] = fma(g3, k, y[3] * c);
+}
+
+// ---------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) -- counter-based generator for reset().
+// counter = (env_id lo, env_id hi, episode index, block), key = seed.
+// ---------------------------------------------------------------------------------
+RDV_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// uniforms 2*blk, 2*blk+1 in [0,1) with 53 random bits each (numpy's random_sample recipe)
+RDV_DEV void philox_uniform_pair(uint64_t seed, int64_t env_id, int32_t episode, uint32_t blk, double &u0,
+                                 double &u1)
+{
+    uint32_t c[4] = {(uint32_t)env_id, (uint32_t)((uint64_t)env_id >> 32), (uint32_t)episode, blk};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    u0 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6)) * (1.0 / 9007199254740992.0);
+    u1 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace rdv
