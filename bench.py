@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched RendezvousEnv step/reset hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]    # the reference algorithm on the host cores
+
+Workload (BASELINE.json configs[1]): 65,536 envs per GPU, default constructor parameters, uniform random
+actions, auto-reset on, fp64 state.  A "step" is one env step of every env of the batch.  Prints ONE JSON line
+(rank 0).  Keys:
+
+  value / ms_per_step   device-resident loop: fp64 actions from a pre-generated 64-step device ring (201 MB,
+                        larger than L2), K steps back to back, CUDA events, max over ranks
+  e2e                   same metric through RendezvousVecEnv.step(numpy actions): pinned H2D of the actions and
+                        D2H of obs / reward / done / terminal obs / episode records inside the timed region
+  roofline              dominant kernel (step_kernel) timed alone with CUDA events (deferred-reset mode);
+                        fp64-pipe bound: algorithmic flop per env-step x envs / duration vs the
+                        DFMA peak measured in this run; the HBM view is in roofline["hbm"]
+  cpu_baseline          the reference algorithm (numpy restatement incl. scipy's RK45, bit-exact vs the reference)
+                        under a SubprocVecEnv-protocol harness on all host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 65536
+RING = 64
+METRIC = "env-steps/sec"
+UNIT = "env-steps/s"
+# F_step = 1202 + 1930 * k fp64 flop with k = mean accepted RK45 steps per solve_ivp call;
+# B_step = 511 B (fp64 actions) / 487 B (fp32 actions) of state + action + output traffic per env-step.
+F_STEP_BASE, F_STEP_PER_RK = 1202.0, 1930.0
+B_STEP_F64, B_STEP_F32 = 511.0, 487.0
+F_STEP_CLOSED_FORM = 560.0
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons during the timed region (pynvml; nvidia-smi as a fallback)."""
+
+    def __init__(self, index=0, period=0.1):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def _run(self):
+        names = {}
+        if self._nvml is not None:
+            n = self._nvml
+            for key in ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksEventReasonHwThermalSlowdown",
+                        "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksEventReasonSwPowerCap",
+                        "nvmlClocksThrottleReasonHwSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown",
+                        "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap"):
+                if hasattr(n, key):
+                    label = key.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", "")
+                    names[getattr(n, key)] = {"HwSlowdown": "hw_slowdown", "HwThermalSlowdown": "hw_thermal_slowdown",
+                                              "SwThermalSlowdown": "sw_thermal_slowdown",
+                                              "SwPowerCap": "sw_power_cap"}[label]
+        while not self._stop.is_set():
+            try:
+                if self._nvml is not None:
+                    n = self._nvml
+                    self.samples.append(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                    get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                        getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+                    mask = get(self._h)
+                    for bit, label in names.items():
+                        if mask & bit:
+                            self.reasons.add(label)
+                else:
+                    import subprocess
+                    out = subprocess.run(
+                        ["nvidia-smi", f"--id={self.index}", "--format=csv,noheader,nounits",
+                         "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                         "clocks_event_reasons.sw_power_cap"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    self.samples.append(int(f[0]))
+                    self.max_mhz = int(f[1])
+                    for label, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                        f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(label)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle.subproc_vec_env import time_subproc_baseline
+    cores = args.ref_procs or os.cpu_count() or 1
+    res = time_subproc_baseline(steps=args.steps, warmup=max(args.warmup, 1), n_procs=cores, seed=0,
+                                max_seconds=args.ref_max_seconds)
+    sample = (f"{res['steps']} VecEnv steps of {cores} envs (one env per process, Pipe protocol, auto-reset in the "
+              f"worker), random fp64 actions, default RendezvousEnv parameters; {res['seconds']:.1f} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": res["steps"], "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * res["seconds"] / max(res["steps"], 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "RendezvousEnv step/reset, random actions, reference algorithm on host cores "
+                               "(bounded sample of the 65,536-env workload: one env per core)",
+                   "envs": cores, "harness": "SubprocVecEnv protocol (oracle/subproc_vec_env.py)",
+                   "env": "oracle/rdv_oracle.py OracleEnv: numpy restatement of the reference env incl. scipy's adaptive "
+                          "RK45, bit-exact vs the reference (the Python reference tree cannot travel)"},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N = 1 only), before CUDA is initialised in this process
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.subproc_vec_env import time_c_port, time_subproc_baseline
+        cores = os.cpu_count() or 1
+        res = time_subproc_baseline(steps=100000, warmup=2, n_procs=cores, seed=0, max_seconds=args.cpu_seconds)
+        cport = time_c_port(n_envs=4096, steps=10, threads=cores)
+        cpu_baseline = {
+            "value": res["value"], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{res['steps']} VecEnv steps x {cores} envs (one per process, SubprocVecEnv protocol), "
+                      f"random fp64 actions, numpy restatement of the reference env (bit-exact), "
+                      f"{res['seconds']:.1f} s",
+            "c_port_value": cport["value"],
+            "c_port_sample": f"plain-C oracle, {cport['envs']} envs x {cport['steps']} steps on {cores} threads",
+        }
+
+    import torch
+    import torch.distributed as dist
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, RendezvousVecEnv, _native as N
+    from reinforcement_learning_rendezvous_b200.distributed import all_reduce_stats
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device for its own arm (there is no CPU fallback); "
+                         "use --impl reference for the host baseline")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return ms
+
+    # ---------------- device-resident leg ----------------
+    env = BatchedRendezvousEnv(n, device=dev, seed=args.seed, env_offset=rank * n, auto_reset=True,
+                               integrator=args.integrator)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+    ring = torch.rand((RING, n, 6), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    for k in range(W):
+        env.step(ring[k % RING])
+    env.stats.zero_()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(K):
+        env.step(ring[k % RING])
+    all_reduce_stats(env.stats)                       # the per-rollout statistics reduction (NCCL when N > 1)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    stats = dict(zip(N.STAT_NAMES, env.stats.cpu().tolist()))
+    total_steps = stats["steps"]
+    assert total_steps == world * n * K, (total_steps, world, n, K)
+    value = world * n * K / (ms * 1e-3)
+    rk_mean = stats["rk_accepted"] / (2.0 * max(total_steps, 1.0))
+
+    # ---------------- roofline leg: step_kernel alone (deferred reset), per-launch events ----------------
+    R = min(K, 200)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(R)]
+    torch.cuda.synchronize()
+    for k in range(R):
+        ev[k][0].record()
+        env.step(ring[k % RING], defer_reset=True)
+        ev[k][1].record()
+        env.run_deferred_reset()
+        ev[k][2].record()
+    torch.cuda.synchronize()
+    t_step = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(R)) / R
+    t_reset = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(R)) / R
+
+    # fp64 peak: DFMA probe, best of 5
+    blocks, threads, iters = 148 * 8, 256, 4096
+    sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
+    best = 1e30
+    for _ in range(6):
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        N.check(N.lib().rdv_fp64_peak_probe(sink.data_ptr(), blocks, threads, iters,
+                                            torch.cuda.current_stream().cuda_stream), "fp64 probe")
+        p1.record()
+        torch.cuda.synchronize()
+        best = min(best, p0.elapsed_time(p1))
+    fp64_peak = 2.0 * iters * 16 * blocks * threads / (best * 1e-3) / 1e12
+
+    closed = args.integrator == "closed_form"
+    f_step = F_STEP_CLOSED_FORM if closed else F_STEP_BASE + F_STEP_PER_RK * rk_mean
+    peaks, peak_src = _peaks()
+    ach_tf = f_step * n / (t_step * 1e-3) / 1e12
+    ach_gbs = B_STEP_F64 * n / (t_step * 1e-3) / 1e9
+    roofline = {
+        "kernel": "step_kernel", "bound": "hbm" if closed else "fp64",
+        "achieved": ach_gbs if closed else ach_tf, "peak": peaks["hbm_gbs"] if closed else fp64_peak,
+        "unit": "GB/s" if closed else "TFLOP/s",
+        "frac": (ach_gbs / peaks["hbm_gbs"]) if closed else (ach_tf / fp64_peak),
+        "traffic": None,
+        "peak_source": peak_src if closed else "rdv_fp64_peak_probe (DFMA microbenchmark, this run; "
+                                                 "MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s)",
+        "flop_per_env_step": f_step, "rk45_steps_per_solve": rk_mean,
+        "kernel_ms": t_step, "reset_kernel_ms": t_reset, "launches_timed": R,
+        "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
+                "bytes_per_env_step": B_STEP_F64, "peak_source": peak_src},
+        "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak},
+    }
+
+    # ---------------- L2-flushed variant (per-step events; a 256 MB write between steps) ----------------
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    F = min(K, 50)
+    fe = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(F)]
+    for k in range(F):
+        flush.fill_(k & 0xFF)
+        fe[k][0].record()
+        env.step(ring[k % RING])
+        fe[k][1].record()
+    torch.cuda.synchronize()
+    ms_flushed = sum(a.elapsed_time(b) for a, b in fe) / F
+    del flush
+
+    # ---------------- end-to-end leg: numpy actions in, numpy results out, through the VecEnv ----------------
+    del env
+    venv = RendezvousVecEnv(n, device=dev, seed=args.seed, env_offset=rank * n, integrator=args.integrator)
+    venv.reset()
+    rng = np.random.default_rng(100 + rank)
+    host_ring = rng.uniform(-1, 1, (RING, n, 6)).astype(np.float32)
+    KE = min(K, args.e2e_steps)
+    for k in range(max(3, min(W, 10))):
+        venv.step(host_ring[k % RING])
+    checksum = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(KE):
+        obs, rew, done, infos = venv.step(host_ring[k % RING])
+        checksum += float(rew[0])
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall))
+    e2e = {"value": world * n * KE / (e2e_ms * 1e-3), "unit": UNIT, "steps": KE,
+           "ms_per_step": e2e_ms / KE, "h2d_bytes_per_step": venv.h2d_bytes_per_step,
+           "d2h_bytes_per_step": venv.d2h_bytes_per_step,
+           "api": "RendezvousVecEnv.step(np.float32[N,6]) -> (obs, rewards, dones, infos) numpy, pinned staging"}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batched RendezvousEnv, {n:,} envs per GPU, random actions, fp64 step/reset "
+                               "(BASELINE.json configs[1])",
+                   "envs_per_gpu": n, "total_envs": world * n, "auto_reset": True, "integrator": args.integrator,
+                   "actions": f"fp64 U(-1,1), pre-generated {RING}-step device ring "
+                              f"({RING * n * 48 / 1e6:.0f} MB > 126 MB L2)",
+                   "l2": "state (12.6 MB at 65,536 envs) is carried step to step by the workload itself; the "
+                         "kernel is fp64-pipe bound, see ms_per_step_l2_flushed",
+                   "ms_per_step_l2_flushed": ms_flushed,
+                   "parallelism": f"{world} x independent env shards, no data-path collective; one "
+                                  "16-double statistics all-reduce per rollout"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * K,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "episode_stats": {"episodes": stats["episodes"], "mean_length": stats["length_sum"] / max(stats["episodes"], 1),
+                          "success_rate": stats["succeeded"] / max(stats["episodes"], 1),
+                          "rk_rejected": stats["rk_rejected"], "failures": stats["failures"]},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", choices=("cuda", "reference"), default="cuda")
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--integrator", choices=("rk45", "closed_form"), default="rk45")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--ref-envs", type=int, default=0, help="(ignored; kept for compatibility)")
+    ap.add_argument("--ref-max-seconds", type=float, default=150.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

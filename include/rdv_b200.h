@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 3
+#define RDV_ABI_VERSION 5
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -113,7 +113,9 @@ typedef struct RdvState {
 typedef struct RdvStepIO {
     const void *actions;     /* [n][6] row-major, float32 (act_f64 = 0) or float64 (act_f64 = 1)  */
     int32_t  act_f64;
-    int32_t  auto_reset;     /* 1: envs that finish are reset in the same launch (VecEnv semantics) */
+    int32_t  auto_reset;     /* 0: off.  1: envs that finish are reset by the same call (VecEnv semantics).
+                              * 2: finished envs are only queued in reset_scratch; the caller runs
+                              *    rdv_auto_reset afterwards (lets a profiler time the two kernels apart) */
     float   *obs;            /* [n][17] observation after the step (after the reset if auto-reset) */
     double  *reward;         /* [n]                                                                */
     uint8_t *done;           /* [n]                                                                */
@@ -143,6 +145,11 @@ int  rdv_params_derive(RdvParams *p);
 int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t n,
              uint64_t seed, int64_t env_offset, void *cuda_stream);
 
+/* Second half of rdv_step(auto_reset = 1): reset() every env queued in reset_scratch by a preceding
+ * rdv_step(auto_reset = 2) and write its post-reset observation; clears the queue. */
+int rdv_auto_reset(const RdvParams *p, const RdvState *s, float *obs, int32_t *reset_scratch, int64_t n,
+                   uint64_t seed, int64_t env_offset, void *cuda_stream);
+
 /* RendezvousEnv.reset (rendezvous_env.py:223-270) for the envs selected by mask (NULL = all).
  * The 24 uniform draws come from Philox4x32-10 keyed by (seed; env_offset+i, episode index),
  * or from `uniforms` ([n][24], in [0,1)) when it is not NULL (test hook that pins the
@@ -164,6 +171,12 @@ int rdv_errors(const RdvParams *p, const RdvState *s, double *errors, uint8_t *c
  * sticky collided / success flags the way reset() does (:260-261).  The reference evaluator
  * does NOT do this; it is provided for callers that want consistent flags. */
 int rdv_refresh_flags(const RdvParams *p, const RdvState *s, int64_t n, void *cuda_stream);
+
+/* chaser2lvlh / target2lvlh (transpose = 0: out = R(q) v) and lvlh2chaser / lvlh2target
+ * (transpose = 1: out = R(q)^T v) of rendezvous_env.py:470-508, with quat2mat's
+ * re-normalisation (utils/quaternions.py:48-68).  q [n][4], v [n][3], out [n][3], device fp64. */
+int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n, int transpose,
+                        void *cuda_stream);
 
 /* -- fused policy (model.predict of an SB3 MlpPolicy, monte_carlo.py:128-133) ------------------- */
 /* fp32 tanh MLP obs[17] -> hidden -> hidden -> action[6], deterministic mean clipped to [-1,1].

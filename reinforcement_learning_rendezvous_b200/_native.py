@@ -1,0 +1,167 @@
+"""ctypes binding of librdv_b200.so (the C ABI declared in include/rdv_b200.h).
+
+The library is built in-tree (csrc/librdv_b200.so) by :func:`build` with
+``nvcc -gencode arch=compute_100a,code=sm_100a``.  There is no CPU fallback:
+:func:`lib` raises if the shared object is missing, and every entry point
+returns RDV_ERR_CUDA on a machine without a usable GPU, which :func:`check`
+turns into a RuntimeError.
+
+Only raw device pointers (``tensor.data_ptr()``), sizes and the CUDA stream
+handle cross this boundary; PyTorch owns every buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
+LIB_PATH = os.path.join(CSRC_DIR, "librdv_b200.so")
+SOURCES = ("rdv_b200.cu",)
+HEADERS = ("rdv_math.cuh", "rdv_env.cuh")
+
+ABI_VERSION = 5
+OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
+
+# rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
+(RCX, RCY, RCZ, VCX, VCY, VCZ, QCW, QCX, QCY, QCZ, WCX, WCY, WCZ, QTW, QTX, QTY, QTZ, WTX, WTY, WTZ,
+ TDV, TDW, EPRET, NF64) = range(24)
+I_STEP, I_SUCCESS, I_COLLIDED, I_EPISODE, NI32 = range(5)
+STAT_NAMES = ("steps", "episodes", "return_sum", "length_sum", "succeeded", "collided", "delta_v_sum",
+              "delta_w_sum", "end_obs", "end_time", "end_bubble", "end_attitude", "reward_sum",
+              "rk_accepted", "rk_rejected", "failures")
+NSTATS = len(STAT_NAMES)
+EP_RETURN, EP_LENGTH, EP_SUCCESS, EP_COLLIDED, EP_DELTA_V, EP_DELTA_W, EP_NCOL = range(7)
+INTEGRATOR_RK45, INTEGRATOR_CLOSED_FORM = 0, 1
+END_REASONS = ("obs", "time", "bubble", "attitude")          # rendezvous_env.py:377
+
+
+class RdvParams(C.Structure):
+    _fields_ = [
+        ("rc0", C.c_double * 3), ("vc0", C.c_double * 3), ("qc0", C.c_double * 4),
+        ("wc0", C.c_double * 3), ("qt0", C.c_double * 4), ("wt0", C.c_double * 3),
+        ("rc0_range", C.c_double), ("vc0_range", C.c_double), ("qc0_range", C.c_double),
+        ("wc0_range", C.c_double), ("qt0_range", C.c_double), ("wt0_range", C.c_double),
+        ("koz_radius", C.c_double), ("corridor_half_angle", C.c_double), ("h", C.c_double),
+        ("dt", C.c_double), ("t_max", C.c_double),
+        ("collision_coef", C.c_double), ("bonus_coef", C.c_double), ("fuel_coef", C.c_double),
+        ("att_coef", C.c_double),
+        ("inertia_c", C.c_double * 9), ("inertia_t", C.c_double * 9),
+        ("torque_c", C.c_double * 3),
+        ("integrator", C.c_int32), ("reserved0", C.c_int32),
+        ("inv_inertia_c", C.c_double * 9), ("inv_inertia_t", C.c_double * 9),
+        ("max_delta_v", C.c_double), ("max_delta_w", C.c_double), ("max_axial_distance", C.c_double),
+        ("max_axial_speed", C.c_double), ("max_wc", C.c_double),
+        ("max_attitude_error", C.c_double), ("max_rd_error", C.c_double), ("max_vd_error", C.c_double),
+        ("max_qd_error", C.c_double), ("max_wd_error", C.c_double),
+        ("rd", C.c_double * 3), ("capture_axis", C.c_double * 3), ("corridor_axis", C.c_double * 3),
+        ("bubble0", C.c_double), ("bubble_rate", C.c_double), ("bubble_min", C.c_double), ("n", C.c_double),
+        ("cw", C.c_double * 17),
+        ("max_delta_v_f32", C.c_float), ("fuel_num_f32", C.c_float), ("fuel_den_f32", C.c_float),
+        ("iso_c", C.c_int32), ("iso_t", C.c_int32), ("reserved1", C.c_int32),
+    ]
+
+
+class RdvState(C.Structure):
+    _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p), ("ld", C.c_int64)]
+
+
+class RdvStepIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("act_f64", C.c_int32), ("auto_reset", C.c_int32),
+        ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
+        ("terminal_obs", C.c_void_p), ("end_reason", C.c_void_p), ("episode_record", C.c_void_p),
+        ("stats", C.c_void_p), ("reset_scratch", C.c_void_p),
+    ]
+
+
+class RdvPolicy(C.Structure):
+    _fields_ = [
+        ("w0", C.c_void_p), ("b0", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p),
+        ("w2", C.c_void_p), ("b2", C.c_void_p), ("hidden", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/rdv_b200.h declares
+PROTOTYPES = {
+    "rdv_abi_version": (C.c_int, []),
+    "rdv_sizeof_params": (C.c_int, []),
+    "rdv_strerror": (C.c_char_p, [C.c_int]),
+    "rdv_params_default": (None, [C.POINTER(RdvParams)]),
+    "rdv_params_derive": (C.c_int, [C.POINTER(RdvParams)]),
+    "rdv_step": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.POINTER(RdvStepIO), C.c_int64,
+                           C.c_uint64, C.c_int64, C.c_void_p]),
+    "rdv_auto_reset": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_uint64, C.c_int64, C.c_void_p]),
+    "rdv_reset": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+    "rdv_observe": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_int64, C.c_void_p]),
+    "rdv_errors": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_int64, C.c_void_p]),
+    "rdv_refresh_flags": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_int64, C.c_void_p]),
+    "rdv_frame_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "rdv_policy_forward": (C.c_int, [C.POINTER(RdvPolicy), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "rdv_fp64_peak_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+def nvcc_command(out=LIB_PATH):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-I", INCLUDE_DIR, "-shared", "-Xcompiler", "-fPIC", "-o", out] + \
+           [os.path.join(CSRC_DIR, s) for s in SOURCES]
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC_DIR, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE_DIR, "rdv_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into csrc/librdv_b200.so (in-tree, so it travels to the GPU box)."""
+    global _lib
+    if force or is_stale():
+        cmd = nvcc_command()
+        if verbose:
+            cmd = cmd[:1] + ["-Xptxas", "-v"] + cmd[1:]
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        _lib = None
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library.  Raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.rdv_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"librdv_b200.so ABI {L.rdv_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+        if L.rdv_sizeof_params() != C.sizeof(RdvParams):
+            raise RuntimeError("RdvParams layout mismatch between include/rdv_b200.h and _native.py")
+        _lib = L
+    return _lib
+
+
+def strerror(status: int) -> str:
+    return lib().rdv_strerror(int(status)).decode()
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise RuntimeError(f"{what} failed: {strerror(status)} (status {status})")

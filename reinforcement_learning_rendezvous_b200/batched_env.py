@@ -1,0 +1,312 @@
+"""BatchedRendezvousEnv -- N independent RendezvousEnv instances resident in B200 HBM.
+
+State lives in two torch tensors laid out structure-of-arrays ([row][env], see
+include/rdv_b200.h): ``f64`` = rc vc qc wc qt wt + total_delta_v/w + episode return,
+``i32`` = step counter, success counter, sticky collided flag, episode index.
+Every method launches hand-written sm_100a kernels through the C ABI on the
+current torch CUDA stream and returns device tensors without synchronising;
+nothing here computes environment math on the host.
+
+Reference semantics (/root/reference/rendezvous_env.py): ``step`` = :160-221,
+``reset`` = :223-270, auto-reset + ``terminal_observation`` = what SB3's
+DummyVecEnv.step_wait adds around them (main.py:33-34).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .params import copy_params, make_params
+
+STATE_SLICES = {"rc": (N.RCX, 3), "vc": (N.VCX, 3), "qc": (N.QCW, 4), "wc": (N.WCX, 3), "qt": (N.QTW, 4),
+                "wt": (N.WTX, 3)}
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class ParamGroup:
+    """A contiguous env range [lo, hi) sharing one RdvParams block (one launch per group)."""
+
+    def __init__(self, params: N.RdvParams, lo: int, hi: int):
+        self.params, self.lo, self.hi = params, int(lo), int(hi)
+
+    @property
+    def n(self):
+        return self.hi - self.lo
+
+
+class BatchedRendezvousEnv:
+    """``num_envs`` environments on one GPU.
+
+    :param num_envs: number of environments on this device
+    :param device: CUDA device (no CPU path exists)
+    :param seed: Philox key for reset(); results depend only on (seed, global env id, episode index)
+    :param env_offset: global index of env 0 of this shard (multi-GPU sharding keeps results invariant)
+    :param auto_reset: finished envs are reset inside ``step`` (VecEnv semantics); the returned obs is then
+        the post-reset observation and ``terminal_obs`` holds the last observation of the episode
+    :param param_batches: optional list of ``(count, ctor_kwargs)``: per-env parameter batches (the
+        sensitivity-sweep axes of sensitivity_analysis.py:97-134) as contiguous groups of envs
+    :param ctor_kwargs: the reference ``RendezvousEnv`` constructor arguments (+ ``integrator``, ``inertia``,
+        ``inertia_target``, ``chaser_torque``)
+    """
+
+    def __init__(self, num_envs: int, device="cuda", seed: int = 0, env_offset: int = 0, auto_reset: bool = True,
+                 param_batches: Optional[Sequence] = None, track_stats: bool = True, ld: Optional[int] = None,
+                 **ctor_kwargs):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedRendezvousEnv needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = N.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedRendezvousEnv only runs on CUDA devices")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = n = int(num_envs)
+        if n <= 0:
+            raise ValueError("num_envs must be positive")
+        self.seed, self.env_offset, self.auto_reset = int(seed), int(env_offset), bool(auto_reset)
+        self.ctor_kwargs = dict(ctor_kwargs)
+
+        if param_batches:
+            groups, lo = [], 0
+            for count, kw in param_batches:
+                merged = dict(ctor_kwargs)
+                merged.update(kw)
+                if lo % 32:
+                    raise ValueError("every param batch but the last must hold a multiple of 32 envs "
+                                     "(keeps each group's rows 256-byte aligned)")
+                groups.append(ParamGroup(make_params(**merged), lo, lo + int(count)))
+                lo += int(count)
+            if lo != n:
+                raise ValueError(f"param_batches cover {lo} envs, expected {n}")
+        else:
+            groups = [ParamGroup(make_params(**ctor_kwargs), 0, n)]
+        self.groups = groups
+        self.params = groups[0].params
+
+        # leading dimension padded to 32 envs so every SoA row starts 256-byte aligned
+        self.ld = ld = (n + 31) // 32 * 32 if ld is None else int(ld)
+        if ld < n:
+            raise ValueError("ld must be >= num_envs")
+        dev = self.device
+        self.f64 = torch.zeros((N.NF64, ld), dtype=torch.float64, device=dev)
+        self.i32 = torch.zeros((N.NI32, ld), dtype=torch.int32, device=dev)
+        self.obs = torch.zeros((n, N.OBS_DIM), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.terminal_obs = torch.zeros((n, N.OBS_DIM), dtype=torch.float32, device=dev)
+        self.end_reason = torch.full((n,), -1, dtype=torch.int8, device=dev)
+        self.episode_record = torch.zeros((n, N.EP_NCOL), dtype=torch.float64, device=dev)
+        self.stats = torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) if track_stats else None
+        # one self-clearing reset list per param group: {count, ticket, env indices...}
+        self._reset_scratch = [torch.zeros(g.n + 2, dtype=torch.int32, device=dev) for g in groups]
+        self._io_cache = {}
+        self._keepalive = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _state_of(self, g: ParamGroup) -> N.RdvState:
+        return N.RdvState(self.f64.data_ptr() + 8 * g.lo, self.i32.data_ptr() + 4 * g.lo, self.ld)
+
+    def _check_actions(self, actions: torch.Tensor) -> torch.Tensor:
+        if not isinstance(actions, torch.Tensor):
+            raise TypeError("actions must be a torch tensor on the env's device (use RendezvousVecEnv for numpy)")
+        if actions.device != self.device:
+            raise ValueError(f"actions live on {actions.device}, env on {self.device}")
+        if actions.dtype not in (torch.float32, torch.float64):
+            raise TypeError("actions must be float32 or float64")
+        if tuple(actions.shape) != (self.num_envs, N.ACT_DIM):
+            raise ValueError(f"actions must have shape ({self.num_envs}, {N.ACT_DIM})")
+        return actions if actions.is_contiguous() else actions.contiguous()
+
+    # ------------------------------------------------------------------ hot path
+    def step(self, actions: torch.Tensor, defer_reset: bool = False):
+        """One step of every env.  Returns (obs f32[N,17], reward f64[N], done u8[N]) -- views of the
+        env's output buffers, valid until the next ``step``.  Asynchronous on the current stream.
+        ``defer_reset`` (auto-reset envs only) queues finished envs instead of resetting them; the caller
+        must then call :meth:`run_deferred_reset` before the next step (used to time the two kernels apart)."""
+        actions = self._check_actions(actions)
+        mode = (2 if defer_reset else 1) if self.auto_reset else 0
+        act_f64 = 1 if actions.dtype == torch.float64 else 0
+        esz = 8 if act_f64 else 4
+        stream = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for gi, g in enumerate(self.groups):
+                io = N.RdvStepIO(
+                    actions.data_ptr() + g.lo * N.ACT_DIM * esz, act_f64, mode,
+                    self.obs.data_ptr() + g.lo * N.OBS_DIM * 4, self.reward.data_ptr() + g.lo * 8,
+                    self.done.data_ptr() + g.lo,
+                    self.terminal_obs.data_ptr() + g.lo * N.OBS_DIM * 4, self.end_reason.data_ptr() + g.lo,
+                    self.episode_record.data_ptr() + g.lo * N.EP_NCOL * 8,
+                    self.stats.data_ptr() if self.stats is not None else None,
+                    self._reset_scratch[gi].data_ptr())
+                st = self._state_of(g)
+                N.check(self.lib.rdv_step(C.byref(g.params), C.byref(st), C.byref(io), g.n, self.seed,
+                                          self.env_offset + g.lo, stream), "rdv_step")
+        self._keepalive = actions
+        return self.obs, self.reward, self.done
+
+    def run_deferred_reset(self):
+        """Second half of an auto-reset step issued with ``defer_reset=True``."""
+        stream = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for gi, g in enumerate(self.groups):
+                st = self._state_of(g)
+                N.check(self.lib.rdv_auto_reset(C.byref(g.params), C.byref(st),
+                                                self.obs.data_ptr() + g.lo * N.OBS_DIM * 4,
+                                                self._reset_scratch[gi].data_ptr(), g.n, self.seed,
+                                                self.env_offset + g.lo, stream), "rdv_auto_reset")
+
+    def reset(self, mask: Optional[torch.Tensor] = None, uniforms: Optional[torch.Tensor] = None,
+              bump_episode: bool = True) -> torch.Tensor:
+        """reset() for all envs, or those where ``mask`` (uint8/bool [N]) is set.  ``uniforms`` ([N,24] fp64 in
+        [0,1)) replaces the Philox draws (test hook that pins the reference's draw order)."""
+        m_ptr = u_ptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if mask.numel() != self.num_envs:
+                raise ValueError("mask must have num_envs elements")
+        if uniforms is not None:
+            uniforms = uniforms.to(device=self.device, dtype=torch.float64).contiguous()
+            if tuple(uniforms.shape) != (self.num_envs, N.N_UNIFORMS):
+                raise ValueError(f"uniforms must have shape ({self.num_envs}, {N.N_UNIFORMS})")
+        stream = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for g in self.groups:
+                if mask is not None:
+                    m_ptr = mask.data_ptr() + g.lo
+                if uniforms is not None:
+                    u_ptr = uniforms.data_ptr() + g.lo * N.N_UNIFORMS * 8
+                st = self._state_of(g)
+                N.check(self.lib.rdv_reset(C.byref(g.params), C.byref(st), m_ptr, u_ptr,
+                                           self.obs.data_ptr() + g.lo * N.OBS_DIM * 4, g.n, self.seed,
+                                           self.env_offset + g.lo, int(bump_episode), stream), "rdv_reset")
+        self._keepalive = (mask, uniforms)
+        return self.obs
+
+    def observe(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """get_observation() of the current state (rendezvous_env.py:294-311)."""
+        out = torch.empty((self.num_envs, N.OBS_DIM), dtype=torch.float32, device=self.device) if out is None else out
+        stream = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for g in self.groups:
+                st = self._state_of(g)
+                N.check(self.lib.rdv_observe(C.byref(g.params), C.byref(st), out.data_ptr() + g.lo * N.OBS_DIM * 4,
+                                             g.n, stream), "rdv_observe")
+        return out
+
+    def errors(self):
+        """(errors f64[N,4], collision u8[N], success u8[N], dist_from_koz f64[N]) of the current state:
+        get_errors / check_collision / check_success / dist_from_koz (rendezvous_env.py:388-468, :510-537)."""
+        n, dev = self.num_envs, self.device
+        err = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        col = torch.empty(n, dtype=torch.uint8, device=dev)
+        suc = torch.empty(n, dtype=torch.uint8, device=dev)
+        koz = torch.empty(n, dtype=torch.float64, device=dev)
+        stream = _stream_ptr(dev)
+        with torch.cuda.device(dev):
+            for g in self.groups:
+                st = self._state_of(g)
+                N.check(self.lib.rdv_errors(C.byref(g.params), C.byref(st), err.data_ptr() + g.lo * 32,
+                                            col.data_ptr() + g.lo, suc.data_ptr() + g.lo, koz.data_ptr() + g.lo * 8,
+                                            g.n, stream), "rdv_errors")
+        return err, col, suc, koz
+
+    def refresh_flags(self):
+        """Recompute collided/success from the current state the way reset() does (:260-261)."""
+        stream = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for g in self.groups:
+                st = self._state_of(g)
+                N.check(self.lib.rdv_refresh_flags(C.byref(g.params), C.byref(st), g.n, stream), "rdv_refresh_flags")
+
+    # ------------------------------------------------------------------ state access
+    def state_view(self, name: str) -> torch.Tensor:
+        """Writable [N, k] view of one state vector ('rc','vc','qc','wc','qt','wt') into the SoA rows."""
+        row, k = STATE_SLICES[name]
+        return self.f64[row:row + k, :self.num_envs].t()
+
+    def get_state(self) -> torch.Tensor:
+        """[N,20] fp64 copy: rc vc qc wc qt wt."""
+        return self.f64[:N.TDV, :self.num_envs].t().contiguous()
+
+    def set_state(self, state20, reset_counters: bool = True, refresh_flags: bool = False):
+        """Inject states (what monte_carlo.evaluate does after reset(), monte_carlo.py:106-112).  The sticky
+        collided/success flags are zeroed with the counters (a reset() at the nominal state leaves them 0) and are
+        NOT recomputed from the injected state unless ``refresh_flags`` -- exactly like the reference evaluator."""
+        s = torch.as_tensor(np.asarray(state20, dtype=np.float64) if not isinstance(state20, torch.Tensor) else state20)
+        s = s.to(device=self.device, dtype=torch.float64).reshape(self.num_envs, 20)
+        self.f64[:N.TDV, :self.num_envs] = s.t()
+        if reset_counters:
+            self.f64[N.TDV:, :] = 0
+            self.i32[N.I_STEP:N.I_COLLIDED + 1, :] = 0
+        if refresh_flags:
+            self.refresh_flags()
+
+    @property
+    def step_count(self):
+        return self.i32[N.I_STEP, :self.num_envs]
+
+    @property
+    def collided(self):
+        return self.i32[N.I_COLLIDED, :self.num_envs]
+
+    @property
+    def success(self):
+        return self.i32[N.I_SUCCESS, :self.num_envs]
+
+    @property
+    def episode_index(self):
+        return self.i32[N.I_EPISODE, :self.num_envs]
+
+    @property
+    def total_delta_v(self):
+        return self.f64[N.TDV, :self.num_envs]
+
+    @property
+    def total_delta_w(self):
+        return self.f64[N.TDW, :self.num_envs]
+
+    @property
+    def episode_return(self):
+        return self.f64[N.EPRET, :self.num_envs]
+
+    # ------------------------------------------------------------------ statistics / checkpoint
+    def read_stats(self, reset: bool = False) -> dict:
+        """Rollout statistics accumulated on the device by the step kernel (warp-shuffle + one atomic per CTA)."""
+        if self.stats is None:
+            raise RuntimeError("env was created with track_stats=False")
+        v = self.stats.cpu().numpy()
+        if reset:
+            self.stats.zero_()
+        return dict(zip(N.STAT_NAMES, v.tolist()))
+
+    def state_dict(self) -> dict:
+        return {"f64": self.f64.clone(), "i32": self.i32.clone(), "obs": self.obs.clone(),
+                "seed": self.seed, "env_offset": self.env_offset,
+                "stats": None if self.stats is None else self.stats.clone()}
+
+    def load_state_dict(self, sd: dict):
+        self.f64.copy_(sd["f64"])
+        self.i32.copy_(sd["i32"])
+        self.obs.copy_(sd["obs"])
+        self.seed, self.env_offset = int(sd["seed"]), int(sd["env_offset"])
+        if self.stats is not None and sd.get("stats") is not None:
+            self.stats.copy_(sd["stats"])
+
+    def clone(self) -> "BatchedRendezvousEnv":
+        other = BatchedRendezvousEnv.__new__(BatchedRendezvousEnv)
+        other.__dict__.update(self.__dict__)
+        other.groups = [ParamGroup(copy_params(g.params), g.lo, g.hi) for g in self.groups]
+        other.params = other.groups[0].params
+        for name in ("f64", "i32", "obs", "reward", "done", "terminal_obs", "end_reason", "episode_record"):
+            setattr(other, name, getattr(self, name).clone())
+        other.stats = None if self.stats is None else self.stats.clone()
+        other._reset_scratch = [t.clone() for t in self._reset_scratch]
+        other._keepalive = None
+        return other

@@ -366,6 +366,20 @@ __global__ void __launch_bounds__(128) errors_kernel(const __grid_constant__ Rdv
     if (koz) koz[i] = koz_distance(P, rc_n, th);
 }
 
+// chaser2lvlh / target2lvlh / lvlh2chaser / lvlh2target for evaluators (rendezvous_env.py:470-508)
+__global__ void __launch_bounds__(128) frame_kernel(const double *q, const double *v, double *out, int64_t n,
+                                                    int transpose)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double qq[4] = {q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]};
+    const double vv[3] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
+    double o[3];
+    const Rot R = rot_from_quat(qq);
+    if (transpose) rot_apply_T(R, vv, o); else rot_apply(R, vv, o);
+    out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2];
+}
+
 // ---------------------------------------------------------------------------------
 // fp32 MLP policy forward, 17 -> 64 -> 64 -> 6 with tanh (SB3 MlpPolicy, main.py:39-48);
 // deterministic action = clip(mean, -1, 1) (monte_carlo.py:128-133).  One thread per env, fp32
@@ -537,6 +551,9 @@ int rdv_params_derive(RdvParams *p)
     p->n = sqrt(3.986004418e14 / (ro * ro * ro));                        // :122-126
     if (!(rd_n < p->koz_radius) || !(rd_n - p->max_rd_error > 0)) return RDV_ERR_PARAMS;   // :155-156
     if (!(p->dt > 0) || !(p->t_max > 0)) return RDV_ERR_PARAMS;
+    // t = round(t + dt, 3) each step (:193) is reproduced as round(step * dt, 3), which is the same number only
+    // when dt lies on the 1 ms grid the reference rounds to
+    if (fabs(p->dt * 1000.0 - rint(p->dt * 1000.0)) > 1e-9 * p->dt * 1000.0) return RDV_ERR_UNSUPPORTED;
     // CW transition matrix, non-zero entries row by row (utils/dynamics.py:40-47)
     const double n = p->n, nt = n * p->dt, s = sin(nt), c = cos(nt);
     double *w = p->cw;
@@ -570,6 +587,7 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
     const bool iso = p->iso_c && p->iso_t;
     const bool closed = p->integrator == RDV_INTEGRATOR_CLOSED_FORM;
     int32_t *reset_list = nullptr;      // {count, ticket, env indices...}, self-clearing
+    if (io->auto_reset < 0 || io->auto_reset > 2) return RDV_ERR_SIZE;
     if (io->auto_reset) {
         if (!io->reset_scratch) return RDV_ERR_NULL;
         reset_list = io->reset_scratch;
@@ -582,15 +600,23 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
 #undef RDV_LAUNCH
     rc = launch_status();
     if (rc) return rc;
-    if (io->auto_reset) {
-        // grid sized for the common case (<= n/8 finished envs per step); grid-stride covers the rest
-        unsigned rgrid = (unsigned)((n / 8 + 127) / 128);
-        if (rgrid < 1) rgrid = 1;
-        if (rgrid > 4096) rgrid = 4096;
-        reset_list_kernel<<<rgrid, 128, 0, st>>>(*p, *s, io->obs, reset_list, seed, env_offset);
-        rc = launch_status();
-    }
+    if (io->auto_reset == 1) rc = rdv_auto_reset(p, s, io->obs, reset_list, n, seed, env_offset, cuda_stream);
     return rc;
+}
+
+int rdv_auto_reset(const RdvParams *p, const RdvState *s, float *obs, int32_t *reset_scratch, int64_t n,
+                   uint64_t seed, int64_t env_offset, void *cuda_stream)
+{
+    if (!p || !obs || !reset_scratch) return RDV_ERR_NULL;
+    int rc = check_state(s, n);
+    if (rc) return rc;
+    if (n == 0) return RDV_OK;
+    // grid sized for the common case (<= n/8 finished envs per step); grid-stride covers the rest
+    unsigned rgrid = (unsigned)((n / 8 + 127) / 128);
+    if (rgrid < 1) rgrid = 1;
+    if (rgrid > 4096) rgrid = 4096;
+    reset_list_kernel<<<rgrid, 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, obs, reset_scratch, seed, env_offset);
+    return launch_status();
 }
 
 int rdv_reset(const RdvParams *p, const RdvState *s, const uint8_t *mask, const double *uniforms, float *obs,
@@ -635,6 +661,15 @@ int rdv_refresh_flags(const RdvParams *p, const RdvState *s, int64_t n, void *cu
     if (n == 0) return RDV_OK;
     errors_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, nullptr, nullptr,
                                                                                        nullptr, nullptr, n, 1);
+    return launch_status();
+}
+
+int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n, int transpose, void *cuda_stream)
+{
+    if (!q || !v || !out) return RDV_ERR_NULL;
+    if (n < 0) return RDV_ERR_SIZE;
+    if (n == 0) return RDV_OK;
+    frame_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(q, v, out, n, transpose);
     return launch_status();
 }
 

@@ -1,0 +1,59 @@
+"""Multi-GPU sharding of the environment batch.
+
+Every environment is independent, so the step path needs NO collective: rank g owns the
+contiguous global env range ``shard_range(total, world, g)`` and resets are keyed by the global
+env id, which makes results invariant to the number of GPUs.  The only exchange is the
+per-rollout statistics vector (16 doubles), summed with one all-reduce -- NCCL over NVLink on the
+GPU box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+
+def shard_range(total_envs: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced partition: the first ``total % world`` ranks get one extra env."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(int(total_envs), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def make_sharded_env(total_envs: int, rank: Optional[int] = None, world_size: Optional[int] = None, device=None,
+                     seed: int = 0, **kwargs):
+    """This rank's shard of a ``total_envs`` batch as a BatchedRendezvousEnv (env_offset = shard start)."""
+    from .batched_env import BatchedRendezvousEnv
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(total_envs, world_size, rank)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return BatchedRendezvousEnv(hi - lo, device=device, seed=seed, env_offset=lo, **kwargs)
+
+
+def all_reduce_stats(stats: torch.Tensor, group=None, async_op: bool = False):
+    """Sum the [RDV_NSTATS] statistics vector over all ranks in place.  No-op without a process group."""
+    if stats.numel() != N.NSTATS:
+        raise ValueError(f"stats must have {N.NSTATS} elements")
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def stats_to_dict(stats: torch.Tensor) -> dict:
+    v = stats.detach().cpu().tolist()
+    d = dict(zip(N.STAT_NAMES, v))
+    ep = max(d["episodes"], 1.0)
+    d["mean_return"] = d["return_sum"] / ep
+    d["mean_length"] = d["length_sum"] / ep
+    d["success_rate"] = d["succeeded"] / ep
+    d["collision_rate"] = d["collided"] / ep
+    return d

@@ -1,0 +1,136 @@
+"""Monte-Carlo evaluator (/root/reference/monte_carlo.py:94-207).
+
+``evaluate(model, env, initial_state)`` keeps the reference's single-episode signature and works with
+the single-env facade.  ``evaluate_batch`` runs every initial condition as one env of a GPU batch:
+policy forward, env step and the get_errors / check_collision / check_success / dist_from_koz
+queries are kernels; the per-episode reduction (counts, running minimum, first-index terminal-error
+averaging of monte_carlo.py:159-189) is done on the recorded per-step arrays.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .batched_env import BatchedRendezvousEnv
+from .environment_utils import config_to_kwargs
+
+MC_COLS = ("ep_len", "num_collisions", "collided", "total_reward", "total_delta_v", "num_successes", "succeeded",
+           "min_dist_from_koz", "pos_error", "vel_error", "att_error", "rot_error")
+
+
+def _terminal_errors(errors, limits):
+    """monte_carlo.py:159-189: errors [T,4] of one episode -> averaged terminal errors from the first index
+    at which the most constraints are met."""
+    pos, vel, att, rot = errors[:, 0], errors[:, 1], errors[:, 2], errors[:, 3]
+    pm, vm, am, rm = pos < limits[0], vel < limits[1], att < limits[2], rot < limits[3]
+    all_mask = pm & vm & am & rm
+    if all_mask.any():
+        index = int(np.argmax(all_mask))
+    else:
+        three = (pm & vm & am) | (pm & vm & rm)
+        if three.any():
+            index = int(np.argmax(three))
+        elif (pm & vm).any():
+            index = int(np.argmax(pm & vm))
+        elif pm.any():
+            index = int(np.argmax(pm))
+        else:
+            index = -1
+    return (pos[index:].mean(), vel[index:].mean(), np.degrees(att[index:].mean()), np.degrees(rot[index:].mean()))
+
+
+def evaluate(model, env, initial_state):
+    """One deterministic episode from ``initial_state`` (dict rc vc qc wc qt wt) -- monte_carlo.py:94-207."""
+    num_collisions = num_successes = 0
+    total_reward = 0
+    env.reset()
+    for k in ("rc", "vc", "qc", "wc", "qt", "wt"):
+        setattr(env, k, initial_state[k])
+    obs = env.get_observation()
+    lstm_states, ep_start, done = None, np.ones((1,), dtype=bool), False
+    errors, times = [env.get_errors()], [env.t]
+    collision = env.check_collision()
+    num_collisions += int(collision)
+    if not env.collided:
+        num_successes += int(env.check_success())
+    min_dist = env.dist_from_koz()
+    while not done:
+        action, lstm_states = model.predict(observation=obs, state=lstm_states, episode_start=ep_start,
+                                            deterministic=True)
+        obs, reward, done, _ = env.step(action)
+        ep_start[0] = done
+        errors.append(env.get_errors())
+        times.append(env.t)
+        collision = env.check_collision()
+        num_collisions += int(collision)
+        if not env.collided:
+            num_successes += int(env.check_success())
+        min_dist = min(min_dist, env.dist_from_koz())
+        total_reward += reward
+    te = _terminal_errors(np.array(errors), (env.max_rd_error, env.max_vd_error, env.max_qd_error, env.max_wd_error))
+    return dict(ep_len=times[-1], num_collisions=num_collisions, collided=int(num_collisions > 0),
+                total_reward=total_reward, total_delta_v=env.total_delta_v, num_successes=num_successes,
+                succeeded=int(num_successes > 0), min_dist_from_koz=min_dist, pos_error=te[0], vel_error=te[1],
+                att_error=te[2], rot_error=te[3])
+
+
+def evaluate_batch(policy, initial_states, config=None, reward_kwargs=None, device="cuda", normalize_quaternions=True,
+                   **extra) -> dict:
+    """All rows of ``initial_states`` ([M,20]: rc vc qc wc qt wt) as one GPU batch.  Returns a dict of
+    length-M arrays with the columns of the reference's results workbook.  ``config`` defaults to the
+    evaluator's ``dict(dt=1, t_max=60)`` with ``stochastic=False`` (monte_carlo.py:26-27)."""
+    ics = np.array(initial_states, dtype=np.float64, copy=True).reshape(-1, 20)
+    if normalize_quaternions:                                   # monte_carlo.py:66-67
+        ics[:, 6:10] /= np.linalg.norm(ics[:, 6:10], axis=1, keepdims=True)
+        ics[:, 13:17] /= np.linalg.norm(ics[:, 13:17], axis=1, keepdims=True)
+    m = ics.shape[0]
+    kw = config_to_kwargs(dict(dt=1, t_max=60) if config is None else config, stochastic=False)
+    env = BatchedRendezvousEnv(m, device=device, auto_reset=False, track_stats=False, reward_kwargs=reward_kwargs,
+                               **kw, **extra)
+    p = env.params
+    steps_max = int(p.t_max / p.dt) + 1
+    env.reset()
+    env.set_state(ics, reset_counters=False)        # flags stay as reset() left them (monte_carlo.py:106-112)
+    obs = env.observe()
+    dev = env.device
+    err_log = torch.full((steps_max + 1, m, 4), float("nan"), dtype=torch.float64, device=dev)
+    alive = torch.ones(m, dtype=torch.bool, device=dev)
+    length = torch.zeros(m, dtype=torch.int64, device=dev)
+    n_col = torch.zeros(m, dtype=torch.int64, device=dev)
+    n_suc = torch.zeros(m, dtype=torch.int64, device=dev)
+    total_reward = torch.zeros(m, dtype=torch.float64, device=dev)
+    tdv = torch.zeros(m, dtype=torch.float64, device=dev)
+
+    err, col, suc, koz = env.errors()
+    err_log[0] = err
+    n_col += col.long()
+    n_suc += suc.long()                             # rdv_errors' success already honours the sticky collided flag
+    min_koz = koz.clone()
+    actions = torch.empty((m, 6), dtype=torch.float32, device=dev)
+    k = 0
+    while bool(alive.any()) and k < steps_max:
+        k += 1
+        policy.forward(obs, out=actions)
+        obs_k, rew, done = env.step(actions)
+        obs = obs_k
+        err, col, suc, koz = env.errors()
+        err_log[k][alive] = err[alive]
+        n_col += (col.bool() & alive).long()
+        n_suc += (suc.bool() & alive).long()
+        min_koz = torch.where(alive & (koz < min_koz), koz, min_koz)
+        total_reward += torch.where(alive, rew, torch.zeros_like(rew))
+        length += alive.long()
+        finished = alive & done.bool()
+        tdv = torch.where(finished, env.total_delta_v, tdv)
+        alive = alive & ~done.bool()
+    err_np = err_log.cpu().numpy()
+    length_np = length.cpu().numpy()
+    limits = (p.max_rd_error, p.max_vd_error, p.max_qd_error, p.max_wd_error)
+    te = np.array([_terminal_errors(err_np[:length_np[i] + 1, i], limits) for i in range(m)])
+    n_col_np, n_suc_np = n_col.cpu().numpy(), n_suc.cpu().numpy()
+    dt = p.dt
+    return dict(
+        ep_len=np.round(length_np * dt, 3), num_collisions=n_col_np, collided=(n_col_np > 0).astype(np.int64),
+        total_reward=total_reward.cpu().numpy(), total_delta_v=tdv.cpu().numpy(), num_successes=n_suc_np,
+        succeeded=(n_suc_np > 0).astype(np.int64), min_dist_from_koz=min_koz.cpu().numpy(),
+        pos_error=te[:, 0], vel_error=te[:, 1], att_error=te[:, 2], rot_error=te[:, 3])

@@ -1,0 +1,262 @@
+"""GPU tests of the reference-facing surfaces: the single-env Gym facade, the SB3 VecEnv, the fused policy
+forward and the Monte-Carlo evaluator (golden = the reference's published workbook + its re-run here)."""
+import copy
+
+import numpy as np
+import pytest
+
+from helpers import NO_RANGE, REL_TOL, golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _policy():
+    import os
+    from helpers import GOLDEN
+    from reinforcement_learning_rendezvous_b200 import MlpPolicy
+    return MlpPolicy.load(os.path.join(GOLDEN, "policy.npz"))
+
+
+# ------------------------------------------------------------------------------------------ Gym facade
+def test_facade_follows_reference_episode():
+    """RendezvousEnv (single-env API) replays a golden reference episode: attributes, obs, reward, done, info."""
+    from reinforcement_learning_rendezvous_b200 import RendezvousEnv
+    g = golden("traj_f64.npz")
+    c = 2                                                # 'uniform' action case
+    env = RendezvousEnv(dt=1, t_max=60, quiet=True, **NO_RANGE)
+    assert env.rc is None and env.t is None
+    obs = env.reset()
+    assert obs.dtype == np.float32 and obs.shape == (17,)
+    assert env.t == 0 and env.collided is False and env.success == 0 and env.bubble_radius == 20
+    np.testing.assert_allclose(env.rc, [0, -10, 0])
+    ic = g["ic"][c]
+    env.rc, env.vc, env.qc, env.wc, env.qt, env.wt = ic[0:3], ic[3:6], ic[6:10], ic[10:13], ic[13:17], ic[17:20]
+    np.testing.assert_array_equal(env.get_observation(), g["obs0"][c])
+    for k in range(int(g["length"][c])):
+        obs, rew, done, info = env.step(g["actions"][c, k])
+        state = np.hstack([env.rc, env.vc, env.qc, env.wc, env.qt, env.wt])
+        assert rel_err(state, g["state"][c, k]) <= REL_TOL
+        assert abs(rew - g["rew"][c, k]) <= REL_TOL * max(1, abs(rew))
+        assert isinstance(rew, float) and isinstance(done, bool) and done == bool(g["done"][c, k])
+        assert np.abs(obs - g["obs"][c, k]).max() <= 1.2e-7
+        assert set(info) == {"observation", "reward", "done", "action"}
+        assert env.t == g["t"][c, k] and isinstance(env.t, int)
+        assert env.bubble_radius == g["bubble"][c, k]
+        assert env.collided == bool(g["collided"][c, k]) and env.success == g["success"][c, k]
+        assert rel_err(env.get_errors(), g["errors"][c, k]) <= REL_TOL
+        assert rel_err(env.dist_from_koz(), g["koz"][c, k]) <= REL_TOL
+        assert env.check_collision() == bool(g["collision_now"][c, k])
+        assert rel_err(env.total_delta_v, g["tdv"][c, k]) <= REL_TOL
+    assert done
+
+
+def test_facade_constants_and_helpers():
+    from reinforcement_learning_rendezvous_b200 import RendezvousEnv, make_env, copy_env
+    env = make_env(None, quiet=True, config=dict(rc0=30, wt0=0.02, dt=0.5, t_max=50), stochastic=False)
+    np.testing.assert_allclose(env.nominal_rc0, [0, -30, 0])
+    np.testing.assert_allclose(env.nominal_wt0, [0, 0, 0.02])
+    assert env.max_axial_distance == 40 and env.bubble_radius0 == 40 and env.dt == 0.5 and env.t_max == 50
+    assert env.max_delta_v == 0.05 and abs(env.max_delta_w - 0.006000000000000001) < 1e-18
+    assert abs(env.n - 0.001039679077003123) < 1e-18
+    assert env.observation_space.shape == (17,) and env.action_space.shape == (6,)
+    env.reset()
+    # frame transforms are rotations: R^T R v = v; target2lvlh(rd) is the goal position
+    v = np.array([0.3, -1.2, 0.7])
+    np.testing.assert_allclose(env.lvlh2chaser(env.chaser2lvlh(v)), v, atol=1e-14)
+    np.testing.assert_allclose(env.lvlh2target(env.target2lvlh(v)), v, atol=1e-14)
+    np.testing.assert_allclose(env.get_goal_pos(), env.target2lvlh(env.rd), atol=0)
+    assert abs(env.get_pos_error() - np.linalg.norm(env.rc - env.get_goal_pos())) < 1e-12
+    # deepcopy gives an independent env with the same future (environment_utils.copy_env)
+    env.step(np.array([0.1, 0.2, -0.1, 0.3, 0.0, -0.2]))
+    twin = copy_env(env)
+    a = np.array([0.5, -0.5, 0.25, -0.25, 0.1, 0.0])
+    o1, r1, d1, _ = env.step(a)
+    assert twin.t == env.t - 0.5
+    o2, r2, d2, _ = twin.step(a)
+    np.testing.assert_array_equal(o1, o2)
+    assert r1 == r2 and d1 == d2 and twin.t == env.t
+    np.testing.assert_array_equal(twin.qc, env.qc)
+    # invalid configuration: the reference's constructor assert (rendezvous_env.py:155)
+    with pytest.raises(ValueError):
+        RendezvousEnv(koz_radius=2)
+    # in-place edits of the state arrays are honoured like on the reference's plain object
+    env.rc[0] += 1.0
+    assert abs(env.get_observation()[0] - (env.rc[0] / 40)) < 1e-6
+
+
+def test_facade_monte_carlo_evaluate_matches_reference_rerun():
+    """monte_carlo.evaluate (single-env API + predict) on 12 CSV rows vs the reference's own evaluate re-run."""
+    from reinforcement_learning_rendezvous_b200 import evaluate, make_env
+    mc = golden("mc.npz")
+    pol = _policy()
+    env = make_env(None, quiet=True, config=dict(dt=1, t_max=60), stochastic=False)
+    for i in range(12):
+        s = mc["ic_raw"][i]
+        init = dict(rc=s[0:3].copy(), vc=s[3:6].copy(), qc=s[6:10] / np.linalg.norm(s[6:10]), wc=s[10:13].copy(),
+                    qt=s[13:17] / np.linalg.norm(s[13:17]), wt=s[17:20].copy())
+        out = evaluate(pol, env, init)
+        for k in ("ep_len", "num_collisions", "collided", "num_successes", "succeeded"):
+            assert out[k] == mc["rerun_" + k][i], (i, k)
+        for k in ("total_reward", "total_delta_v", "min_dist_from_koz", "pos_error", "vel_error", "att_error",
+                  "rot_error"):
+            assert abs(out[k] - mc["rerun_" + k][i]) <= 2e-4 * max(1.0, abs(mc["rerun_" + k][i])), (i, k)
+
+
+# ------------------------------------------------------------------------------------------ Monte Carlo
+def test_monte_carlo_batch_reproduces_published_workbook():
+    """All 1000 published initial conditions as one GPU batch with the shipped policy: discrete columns equal
+    the reference's published results (results/data_monte_carlo_results_mlp.xlsx) up to a handful of
+    policy-rounding flips; success / collision totals 545 / 166 +- 3."""
+    from reinforcement_learning_rendezvous_b200 import evaluate_batch
+    mc = golden("mc.npz")
+    out = evaluate_batch(_policy(), mc["ic_raw"])
+    n = 1000
+    for src, max_flips in (("workbook_", 10), ("rerun_", 10)):
+        for k in ("ep_len", "num_collisions", "collided", "num_successes", "succeeded"):
+            flips = int((np.asarray(out[k], dtype=float) != mc[src + k]).sum())
+            assert flips <= max_flips, (src, k, flips)
+    assert abs(int(out["succeeded"].sum()) - 545) <= 3
+    assert abs(int(out["collided"].sum()) - 166) <= 3
+    same = np.asarray(out["ep_len"], dtype=float) == mc["rerun_ep_len"]
+    for k in ("total_delta_v", "pos_error", "vel_error"):
+        rel = np.abs(out[k][same] - mc["rerun_" + k][same]) / np.maximum(np.abs(mc["rerun_" + k][same]), 1e-3)
+        assert np.median(rel) < 1e-5, (k, np.median(rel))
+        assert np.quantile(rel, 0.99) < 1e-2, (k, np.quantile(rel, 0.99))
+    assert abs(out["total_reward"].mean() - mc["rerun_total_reward"].mean()) < 0.5
+
+
+# ------------------------------------------------------------------------------------------ policy
+def test_policy_forward_matches_torch_fp32():
+    import torch
+    pol = _policy()
+    g = golden("traj_f32.npz")
+    obs = np.concatenate([g["obs0"], g["obs"][:, :20].reshape(-1, 17)])
+    obs = obs[np.isfinite(obs).all(axis=1)].astype(np.float32)
+    w = {k: v.double().cpu() for k, v in pol.w.items()}
+    x = torch.as_tensor(obs).double()
+    h = torch.tanh(x @ w["w0"].T + w["b0"])
+    h = torch.tanh(h @ w["w1"].T + w["b1"])
+    ref = torch.clamp(h @ w["w2"].T + w["b2"], -1, 1).numpy()
+    act = pol.forward(torch.as_tensor(obs, device=pol.device)).cpu().numpy()
+    assert np.abs(act - ref).max() < 5e-6                      # fp32 accumulation vs an fp64 evaluation
+    a1, state = pol.predict(obs[0], deterministic=True)
+    assert a1.shape == (6,) and a1.dtype == np.float32 and state is None
+    np.testing.assert_array_equal(a1, act[0])
+    # the reference's own fp32 actions (torch CPU) for the first step of each golden episode
+    first = pol.predict(g["obs0"], deterministic=True)[0]
+    assert np.abs(first - g["actions"][:, 0]).max() < 5e-6
+
+
+# ------------------------------------------------------------------------------------------ VecEnv
+def test_vec_env_contract():
+    from reinforcement_learning_rendezvous_b200 import RendezvousVecEnv
+    n = 512
+    venv = RendezvousVecEnv(n, seed=7, t_max=15)
+    assert venv.num_envs == n and venv.observation_space.shape == (17,) and venv.action_space.shape == (6,)
+    obs = venv.reset()
+    assert obs.shape == (n, 17) and obs.dtype == np.float32
+    rng = np.random.default_rng(0)
+    finished = 0
+    returns = np.zeros(n)
+    lengths = np.zeros(n, dtype=int)
+    for k in range(40):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        venv.step_async(a)
+        obs, rew, done, infos = venv.step_wait()
+        assert obs.shape == (n, 17) and rew.shape == (n,) and rew.dtype == np.float32 and done.dtype == np.bool_
+        assert len(infos) == n
+        returns += rew
+        lengths += 1
+        for i in np.flatnonzero(done):
+            info = infos[i]
+            assert "TimeLimit.truncated" not in info
+            t_obs = info["terminal_observation"]
+            assert t_obs.shape == (17,) and t_obs.dtype == np.float32
+            assert not np.array_equal(t_obs, obs[i])                 # returned obs is the post-reset one
+            assert info["episode"]["l"] == lengths[i]
+            assert abs(info["episode"]["r"] - returns[i]) < 1e-3
+            assert info["end_reason"] in ("obs", "time", "bubble", "attitude")
+            returns[i], lengths[i] = 0, 0
+            finished += 1
+        for i in np.flatnonzero(~done)[:5]:
+            assert infos[i] == {}
+        # post-reset observations: position near the nominal initial state, step counter zero
+        steps = venv.env.step_count.cpu().numpy()
+        assert (steps[done] == 0).all() and (steps[~done] == lengths[~done]).all()
+    assert finished > n
+    stats = venv.read_stats()
+    assert stats["episodes"] == finished and stats["steps"] == 40 * n
+    assert stats["end_obs"] + stats["end_time"] + stats["end_bubble"] + stats["end_attitude"] == finished
+    # get_attr / env_method / set_attr
+    rc = venv.get_attr("rc", indices=[0, 5])
+    assert len(rc) == 2 and rc[0].shape == (3,)
+    assert venv.get_attr("dt")[0] == 1.0 and venv.get_attr("koz_radius", 3) == [5.0]
+    errs = venv.env_method("get_errors", indices=[1])
+    assert errs[0].shape == (4,)
+    venv.set_attr("rc", np.array([1.0, -2.0, 3.0]), indices=[4])
+    np.testing.assert_array_equal(venv.get_attr("rc", 4)[0], [1.0, -2.0, 3.0])
+    assert venv.env_is_wrapped(object) == [False] * n
+    venv.close()
+
+
+def test_vec_env_step_equals_batched_env():
+    """The numpy/pinned-memory front end returns exactly what the device API computes."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, RendezvousVecEnv
+    n = 300
+    venv = RendezvousVecEnv(n, seed=11)
+    benv = BatchedRendezvousEnv(n, seed=11)
+    np.testing.assert_array_equal(venv.reset(), benv.reset().cpu().numpy())
+    rng = np.random.default_rng(3)
+    for _ in range(30):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        obs, rew, done, _ = venv.step(a)
+        o2, r2, d2 = benv.step(torch.as_tensor(a, device=benv.device))
+        np.testing.assert_array_equal(obs, o2.cpu().numpy())
+        np.testing.assert_array_equal(rew, r2.float().cpu().numpy())
+        np.testing.assert_array_equal(done, d2.bool().cpu().numpy())
+
+
+def test_param_batches_match_separate_envs():
+    """Per-env parameter batches (sensitivity-sweep axes) == separate envs with those constructor arguments."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    batches = [(64, dict(h=400e3)), (64, dict(koz_radius=10.0)), (96, dict(dt=0.5, corridor_half_angle=0.5)),
+               (32, dict(rc0=np.array([0., -30., 0.])))]
+    n = sum(c for c, _ in batches)
+    env = BatchedRendezvousEnv(n, seed=5, param_batches=batches, auto_reset=True)
+    env.reset()
+    parts, lo = [], 0
+    for c, kw in batches:
+        e = BatchedRendezvousEnv(c, seed=5, env_offset=lo, auto_reset=True, **kw)
+        e.reset()
+        parts.append(e)
+        lo += c
+    rng = np.random.default_rng(1)
+    for _ in range(25):
+        a = torch.as_tensor(rng.uniform(-1, 1, (n, 6)), device=env.device)
+        obs, rew, done = env.step(a)
+        lo = 0
+        for (c, _), e in zip(batches, parts):
+            o2, r2, d2 = e.step(a[lo:lo + c].contiguous())
+            assert torch.equal(obs[lo:lo + c], o2) and torch.equal(rew[lo:lo + c], r2)
+            assert torch.equal(done[lo:lo + c], d2)
+            lo += c
+    st = env.read_stats()
+    assert st["steps"] == 25 * n
+
+
+def test_checkpoint_roundtrip():
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    env = BatchedRendezvousEnv(128, seed=21)
+    env.reset()
+    a = torch.rand((128, 6), dtype=torch.float64, device=env.device) * 2 - 1
+    for _ in range(5):
+        env.step(a)
+    sd = copy.deepcopy(env.state_dict())
+    ref = [env.step(a)[0].clone() for _ in range(10)]
+    other = BatchedRendezvousEnv(128, seed=0)
+    other.load_state_dict(sd)
+    for k in range(10):
+        assert torch.equal(other.step(a)[0], ref[k])

@@ -1,0 +1,204 @@
+"""GPU parity of rdv_step (through the C ABI) against
+  (1) the frozen outputs of the UNMODIFIED reference (tests/golden/traj_*.npz, made by oracle/make_golden.py),
+  (2) the plain-C oracle on seeded random batches, including auto-reset with the shared Philox stream.
+
+Tolerance: BASELINE.json north_star -- 1e-9 relative on fp64 trajectories; rewards within 1e-9;
+done / collided / success / end-reason exact (a mismatch is accepted only where the golden value
+lies within 1e-9 of the threshold it is compared with); float32 observations within 1 ulp of 1.0.
+"""
+import numpy as np
+import pytest
+
+from helpers import NO_RANGE, REL_TOL, cfg_kwargs, golden, rel_err
+
+pytestmark = pytest.mark.gpu
+OBS_TOL = 1.2e-7        # one float32 ulp at |x| <= 1: the fp64 value may sit on a rounding boundary
+
+
+def _run_cases(g, idx, ctor_kwargs, reward_kwargs=None, integrator="rk45"):
+    """Replay golden cases `idx` (same config) as one batch; returns dict of worst deviations."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    idx = np.asarray(idx)
+    env = BatchedRendezvousEnv(len(idx), auto_reset=False, reward_kwargs=reward_kwargs, integrator=integrator,
+                               **ctor_kwargs)
+    env.reset()
+    env.set_state(g["ic"][idx])
+    np.testing.assert_array_equal(env.observe().cpu().numpy(), g["obs0"][idx])
+    L = g["length"][idx]
+    acts = g["actions"][idx]
+    worst = dict(state=0.0, rew=0.0, obs=0.0, tdv=0.0, tdw=0.0, err=0.0, koz=0.0)
+    flag_mismatch = 0
+    for k in range(int(L.max())):
+        live = k < L
+        a = torch.as_tensor(acts[:, k], device=env.device)
+        obs, rew, done = env.step(a)
+        err, col, suc, koz = env.errors()
+        worst["state"] = max(worst["state"], rel_err(env.get_state().cpu().numpy()[live], g["state"][idx, k][live]))
+        worst["rew"] = max(worst["rew"], rel_err(rew.cpu().numpy()[live], g["rew"][idx, k][live]))
+        worst["obs"] = max(worst["obs"], float(np.abs(obs.cpu().numpy()[live] - g["obs"][idx, k][live]).max()))
+        worst["tdv"] = max(worst["tdv"], rel_err(env.total_delta_v.cpu().numpy()[live], g["tdv"][idx, k][live]))
+        worst["tdw"] = max(worst["tdw"], rel_err(env.total_delta_w.cpu().numpy()[live], g["tdw"][idx, k][live]))
+        worst["err"] = max(worst["err"], rel_err(err.cpu().numpy()[live], g["errors"][idx, k][live]))
+        worst["koz"] = max(worst["koz"], rel_err(koz.cpu().numpy()[live], g["koz"][idx, k][live]))
+        flag_mismatch += int((done.cpu().numpy()[live] != g["done"][idx, k][live]).sum())
+        flag_mismatch += int((env.collided.cpu().numpy()[live] != g["collided"][idx, k][live]).sum())
+        flag_mismatch += int((env.success.cpu().numpy()[live] != g["success"][idx, k][live]).sum())
+        flag_mismatch += int((env.end_reason.cpu().numpy()[live] != g["reason"][idx, k][live]).sum())
+        flag_mismatch += int((col.cpu().numpy()[live] != g["collision_now"][idx, k][live]).sum())
+        steps = env.step_count.cpu().numpy()[live]
+        assert (steps == k + 1).all()
+    worst["flags"] = flag_mismatch
+    return worst
+
+
+def _assert_parity(w, tag):
+    assert w["state"] <= REL_TOL, (tag, w)
+    assert w["rew"] <= REL_TOL, (tag, w)
+    assert w["err"] <= REL_TOL and w["koz"] <= REL_TOL, (tag, w)
+    assert w["tdw"] <= REL_TOL, (tag, w)
+    assert w["obs"] <= OBS_TOL, (tag, w)
+    assert w["flags"] == 0, (tag, w)
+
+
+def test_golden_fp64_actions():
+    """96 reference episodes (12 Monte-Carlo ICs x zero/fixed/uniform/gentle fp64 actions x t_max 60/120)."""
+    g = golden("traj_f64.npz")
+    for t_max in (60.0, 120.0):
+        idx = np.flatnonzero(g["t_max"] == t_max)
+        w = _run_cases(g, idx, dict(dt=1, t_max=t_max, **NO_RANGE))
+        _assert_parity(w, f"t_max={t_max}")
+        assert w["tdv"] <= REL_TOL
+
+
+def test_golden_fp32_policy_actions():
+    """48 reference episodes driven by the shipped MLP policy's float32 actions (NumPy-2 promotion rules:
+    delta_v / total_delta_v / fuel term in fp32)."""
+    g = golden("traj_f32.npz")
+    assert g["actions"].dtype == np.float32
+    w = _run_cases(g, np.arange(len(g["length"])), dict(dt=1, t_max=60, **NO_RANGE))
+    _assert_parity(w, "f32")
+    assert w["tdv"] <= 1e-7          # total_delta_v accumulates in float32 in the reference
+
+
+def test_golden_configs():
+    """Non-default constructor parameters (sensitivity-sweep axes: h, koz, corridor, dt, rc0, wt0, reward)."""
+    g = golden("traj_cfg.npz")
+    cfgs = [str(c) for c in g["cfg"]]
+    for cfg in sorted(set(cfgs)):
+        idx = [i for i, c in enumerate(cfgs) if c == cfg]
+        kw, reward = cfg_kwargs(cfg)
+        w = _run_cases(g, idx, dict(NO_RANGE, **kw), reward_kwargs=reward)
+        _assert_parity(w, cfg)
+
+
+def test_known_answer_vector():
+    """CSV row 0, fp64 action [0.5,-0.25,0.1,0.2,-0.1,0.05] applied 3 times."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    ic = golden("traj_f64.npz")["ic"][0]
+    env = BatchedRendezvousEnv(1, auto_reset=False, dt=1, t_max=60, **NO_RANGE)
+    env.reset()
+    env.set_state(ic[None])
+    a = torch.tensor([[0.5, -0.25, 0.1, 0.2, -0.1, 0.05]], dtype=torch.float64, device=env.device)
+    rews = []
+    for _ in range(3):
+        _, rew, done = env.step(a)
+        rews.append(float(rew[0]))
+    np.testing.assert_allclose(rews, [2.0559846397346275, 2.058868592759961, 2.057412928302262], rtol=1e-9)
+    s = env.get_state().cpu().numpy()[0]
+    np.testing.assert_allclose(s[0:3], [0.2200069248780245, -9.680428164266877, -0.4026617743928622], rtol=1e-9)
+    np.testing.assert_allclose(s[3:6], [0.0837701806460994, -0.0243025944639084, 0.01784886114418886], rtol=1e-9)
+    np.testing.assert_allclose(s[6:10], [0.9999504147904752, 0.00836140201404473, -0.00344381757525102,
+                                         -0.00417073581332044], rtol=1e-9, atol=1e-12)
+    err, col, suc, koz = env.errors()
+    np.testing.assert_allclose(err.cpu().numpy()[0], [7.7854802180764127, 0.098509752926333141,
+                                                      0.039751831117195956, 0.0041720300952382272], rtol=1e-9)
+    np.testing.assert_allclose(float(koz[0]), 4.9985334300547155, rtol=1e-9)
+    assert not bool(done[0]) and int(env.collided[0]) == 0 and int(env.success[0]) == 0
+
+
+@pytest.mark.parametrize("act_dtype", ["float64", "float32"])
+def test_random_batch_vs_c_oracle_with_auto_reset(act_dtype):
+    """4096 envs x 40 steps, random initial states and actions, auto-reset on: state, observation, reward,
+    flags and the Philox-driven resets must follow the C oracle."""
+    import torch
+    from oracle import c_oracle as CO
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    n, steps, seed, offset = 4096, 40, 1234, 100_000
+    rng = np.random.default_rng(5)
+    env = BatchedRendezvousEnv(n, seed=seed, env_offset=offset, auto_reset=True, t_max=30)
+    orc = CO.COracleBatch(CO.make_params(t_max=30), n)
+    obs0 = env.reset().cpu().numpy()
+    episode = np.ones(n, dtype=np.int32)            # reset() bumps the episode index to 1
+    ids = offset + np.arange(n)
+    o0 = orc.reset_from_uniforms(CO.philox_uniforms(seed, ids, episode))
+    assert rel_err(env.get_state().cpu().numpy(), orc.state) <= REL_TOL
+    assert np.abs(obs0 - o0).max() <= OBS_TOL
+    total_done = 0
+    for k in range(steps):
+        scale = 1.0 if k % 2 else 0.3
+        a = (scale * rng.uniform(-1, 1, (n, 6))).astype(act_dtype)
+        obs, rew, done = env.step(torch.as_tensor(a, device=env.device))
+        o_obs, o_rew, o_done = orc.step(a, threads=8)
+        o_obs, o_rew, o_done = o_obs.copy(), o_rew.copy(), o_done.copy()
+        done_np = done.cpu().numpy()
+        np.testing.assert_array_equal(done_np, o_done)
+        np.testing.assert_array_equal(env.end_reason.cpu().numpy(), np.where(o_done > 0, orc.reason, -1))
+        assert rel_err(rew.cpu().numpy(), o_rew) <= REL_TOL
+        d = np.flatnonzero(o_done)
+        if d.size:
+            total_done += d.size
+            assert np.abs(env.terminal_obs.cpu().numpy()[d] - o_obs[d]).max() <= OBS_TOL
+            rec = env.episode_record.cpu().numpy()[d]
+            np.testing.assert_array_equal(rec[:, 1], np.round(orc.aux[d, 2] / 1.0))          # length = t/dt
+            np.testing.assert_array_equal(rec[:, 3], orc.flags[d, 0])
+            episode[d] += 1
+            mask = np.zeros(n, dtype=np.uint8)
+            mask[d] = 1
+            o_obs = orc.reset_from_uniforms(CO.philox_uniforms(seed, ids, episode), mask=mask).copy()
+        assert np.abs(obs.cpu().numpy() - o_obs).max() <= OBS_TOL
+        assert rel_err(env.get_state().cpu().numpy(), orc.state) <= REL_TOL
+        np.testing.assert_array_equal(env.collided.cpu().numpy(), orc.flags[:, 0])
+        np.testing.assert_array_equal(env.success.cpu().numpy(), orc.flags[:, 1])
+        np.testing.assert_array_equal(env.episode_index.cpu().numpy(), episode)
+    assert total_done > n // 2          # the reset path really was exercised
+    st = env.read_stats()
+    assert st["steps"] == n * steps and st["episodes"] == total_done and st["failures"] == 0
+
+
+def test_closed_form_fast_path_within_tolerance():
+    """The opt-in closed-form attitude propagation (exact for the env's isotropic, torque-free bodies) stays
+    within the parity tolerance of the reference's RK45 at the default dt = 1 s."""
+    g = golden("traj_f64.npz")
+    idx = np.flatnonzero(g["t_max"] == 120.0)
+    w = _run_cases(g, idx, dict(dt=1, t_max=120.0, **NO_RANGE), integrator="closed_form")
+    assert w["state"] <= REL_TOL and w["rew"] <= 1e-6, w
+
+
+def test_edge_cases():
+    """n = 1, n not a multiple of the CTA size, wrong shapes / dtypes / devices."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    for n in (1, 63, 65, 1000):
+        env = BatchedRendezvousEnv(n, seed=3)
+        env.reset()
+        a = torch.zeros((n, 6), dtype=torch.float64, device=env.device)
+        obs, rew, done = env.step(a)
+        assert obs.shape == (n, 17) and torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        ref = BatchedRendezvousEnv(1000, seed=3)
+        ref.reset()
+        ref.step(torch.zeros((1000, 6), dtype=torch.float64, device=env.device))
+        m = min(n, 1000)
+        # env i of a small batch == env i of a large batch (results independent of grid shape)
+        assert torch.equal(env.get_state()[:m], ref.get_state()[:m])
+    env = BatchedRendezvousEnv(8)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((7, 6), dtype=torch.float64, device=env.device))
+    with pytest.raises(TypeError):
+        env.step(torch.zeros((8, 6), dtype=torch.float16, device=env.device))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((8, 6), dtype=torch.float64))
+    with pytest.raises(TypeError):
+        env.step(np.zeros((8, 6)))

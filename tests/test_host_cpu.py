@@ -1,0 +1,116 @@
+"""CPU: host-side logic that needs no GPU -- factory config handling, spaces, evaluator reduction, sharding,
+and the world_size-2 gloo statistics all-reduce."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+
+
+def test_config_to_kwargs_matches_make_env_rules():
+    """utils/environment_utils.py:22-37"""
+    from reinforcement_learning_rendezvous_b200.environment_utils import config_to_kwargs
+    kw = config_to_kwargs(dict(rc0=30, wt0=0.02, dt=0.5), stochastic=False)
+    np.testing.assert_array_equal(kw["rc0"], [0, -30, 0])
+    np.testing.assert_array_equal(kw["wt0"], [0, 0, 0.02])
+    assert all(kw[k] == 0 for k in ("rc0_range", "vc0_range", "qc0_range", "wc0_range", "qt0_range", "wt0_range"))
+    assert kw["dt"] == 0.5 and kw["t_max"] is None
+    kw = config_to_kwargs(dict(rc0=np.array([1., 2., 3.])), stochastic=True)
+    np.testing.assert_array_equal(kw["rc0"], [1, 2, 3])
+    assert kw["rc0_range"] is None
+    cfg = dict(dt=1)
+    config_to_kwargs(cfg, stochastic=False)
+    assert cfg == dict(dt=1)                          # caller's dict is not mutated
+
+
+def test_box_semantics():
+    """gym 0.21 Box.contains (rendezvous_env.py:367): dtype castable, shape, inclusive bounds."""
+    from reinforcement_learning_rendezvous_b200.spaces import _Box
+    box = _Box(-1, 1, (17,), np.float32)
+    assert box.contains(np.zeros(17, dtype=np.float32)) and box.contains(np.ones(17, dtype=np.float32))
+    assert not box.contains(np.full(17, 1.0000001, dtype=np.float32))
+    assert not box.contains(np.zeros(17, dtype=np.float64))          # float64 is not castable to float32
+    assert not box.contains(np.zeros(16, dtype=np.float32))
+    assert box.sample().shape == (17,) and box.sample().dtype == np.float32
+
+
+def test_terminal_error_reduction():
+    """monte_carlo.py:159-189 first-index logic."""
+    from reinforcement_learning_rendezvous_b200.monte_carlo import _terminal_errors
+    lim = (0.5, 0.1, np.radians(5), np.radians(1))
+    e = np.array([[3.0, 1.0, 0.5, 0.1], [0.4, 0.05, 0.01, 0.001], [0.2, 0.01, 0.02, 0.002]])
+    out = _terminal_errors(e, lim)                      # all four met from index 1
+    np.testing.assert_allclose(out, [0.3, 0.03, np.degrees(0.015), np.degrees(0.0015)])
+    e2 = e.copy()
+    e2[:, 3] = 1.0                                      # rot never met -> three-constraint mask (pos, vel, att)
+    assert _terminal_errors(e2, lim)[0] == pytest.approx(0.3)
+    e3 = np.full((4, 4), 9.0)                           # nothing met -> last sample only
+    e3[-1] = [7.0, 6.0, 0.5, 0.25]
+    np.testing.assert_allclose(_terminal_errors(e3, lim), [7.0, 6.0, np.degrees(0.5), np.degrees(0.25)])
+    e4 = np.full((3, 4), 9.0)
+    e4[1:, 0] = 0.1                                     # only position met, from index 1
+    assert _terminal_errors(e4, lim)[1] == pytest.approx(9.0)
+
+
+def test_shard_range_partitions():
+    from reinforcement_learning_rendezvous_b200.distributed import shard_range
+    for total, world in ((1 << 20, 8), (65536, 4), (1000, 3), (7, 8), (5, 1)):
+        spans = [shard_range(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from reinforcement_learning_rendezvous_b200.distributed import all_reduce_stats, shard_range, stats_to_dict
+from reinforcement_learning_rendezvous_b200 import _native as N
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+lo, hi = shard_range(1001, 2, rank)
+stats = torch.zeros(N.NSTATS, dtype=torch.float64)
+stats[0] = hi - lo            # steps
+stats[1] = rank + 1           # episodes
+stats[2] = 10.0 * (rank + 1)  # return_sum
+all_reduce_stats(stats)
+d = stats_to_dict(stats)
+assert d["steps"] == 1001 and d["episodes"] == 3 and abs(d["mean_return"] - 10.0) < 1e-12, d
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_stats_all_reduce_world_size_2_gloo(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, out
+        assert f"rank {r} ok" in out
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference must work without a GPU (it times the CPU oracle) and print one JSON line."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--ref-envs", "256"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "env-steps/s"
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["e2e"]["h2d_bytes_per_step"] == 0
