@@ -12,7 +12,7 @@ actions, auto-reset on, fp64 state.  A "step" is one env step of every env of th
                         larger than L2), K steps back to back, CUDA events, max over ranks
   e2e                   same metric through RendezvousVecEnv.step(numpy actions): pinned H2D of the actions and
                         D2H of obs / reward / done / terminal obs / episode records inside the timed region
-  roofline              dominant kernel (step_kernel) timed alone with CUDA events (deferred-reset mode);
+  roofline              dominant kernel (step_kernel, the only kernel of a step) timed per launch with CUDA events;
                         fp64-pipe bound: algorithmic flop per env-step x envs / duration vs the
                         DFMA peak measured in this run; the HBM view is in roofline["hbm"]
   cpu_baseline          the reference algorithm (numpy restatement incl. scipy's RK45, bit-exact vs the reference)
@@ -234,19 +234,17 @@ def run_cuda(args):
     value = world * n * K / (ms * 1e-3)
     rk_mean = stats["rk_accepted"] / (2.0 * max(total_steps, 1.0))
 
-    # ---------------- roofline leg: step_kernel alone (deferred reset), per-launch events ----------------
+    # ---------------- roofline leg: per-launch CUDA events around the step kernel ----------------
     R = min(K, 200)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(R)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(R)]
     torch.cuda.synchronize()
     for k in range(R):
         ev[k][0].record()
-        env.step(ring[k % RING], defer_reset=True)
+        env.step(ring[k % RING])
         ev[k][1].record()
-        env.run_deferred_reset()
-        ev[k][2].record()
     torch.cuda.synchronize()
-    t_step = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(R)) / R
-    t_reset = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(R)) / R
+    t_launches = sorted(a.elapsed_time(b) for a, b in ev)
+    t_step = sum(t_launches) / R
 
     # fp64 peak: DFMA probe, best of 5
     blocks, threads, iters = 148 * 8, 256, 4096
@@ -276,7 +274,7 @@ def run_cuda(args):
         "peak_source": peak_src if closed else "rdv_fp64_peak_probe (DFMA microbenchmark, this run; "
                                                  "MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s)",
         "flop_per_env_step": f_step, "rk45_steps_per_solve": rk_mean,
-        "kernel_ms": t_step, "reset_kernel_ms": t_reset, "launches_timed": R,
+        "kernel_ms": t_step, "kernel_ms_min": t_launches[0], "launches_timed": R,
         "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                 "bytes_per_env_step": B_STEP_F64, "peak_source": peak_src},
         "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak},
@@ -339,7 +337,7 @@ def run_cuda(args):
                    "ms_per_step_l2_flushed": ms_flushed,
                    "parallelism": f"{world} x independent env shards, no data-path collective; one "
                                   "16-double statistics all-reduce per rollout"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * K,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": K,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "episode_stats": {"episodes": stats["episodes"], "mean_length": stats["length_sum"] / max(stats["episodes"], 1),
                           "success_rate": stats["succeeded"] / max(stats["episodes"], 1),

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 5
+#define RDV_ABI_VERSION 6
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -123,7 +123,6 @@ typedef struct RdvStepIO {
     int8_t  *end_reason;     /* nullable [n]: -1 running, 0 obs, 1 time, 2 bubble, 3 attitude      */
     double  *episode_record; /* nullable [n][RDV_EP_NCOL]: written for finished episodes only      */
     double  *stats;          /* nullable [RDV_NSTATS] device accumulator                           */
-    int32_t *reset_scratch;  /* [n+2] int32, zeroed ONCE by the caller; required when auto_reset   */
 } RdvStepIO;
 
 /* -- constants ------------------------------------------------------------------------------ */
@@ -144,11 +143,6 @@ int  rdv_params_derive(RdvParams *p);
  * of env 0 of this shard (Philox key for resets). */
 int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t n,
              uint64_t seed, int64_t env_offset, void *cuda_stream);
-
-/* Second half of rdv_step(auto_reset = 1): reset() every env queued in reset_scratch by a preceding
- * rdv_step(auto_reset = 2) and write its post-reset observation; clears the queue. */
-int rdv_auto_reset(const RdvParams *p, const RdvState *s, float *obs, int32_t *reset_scratch, int64_t n,
-                   uint64_t seed, int64_t env_offset, void *cuda_stream);
 
 /* RendezvousEnv.reset (rendezvous_env.py:223-270) for the envs selected by mask (NULL = all).
  * The 24 uniform draws come from Philox4x32-10 keyed by (seed; env_offset+i, episode index),

@@ -19,11 +19,11 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-LIB_PATH = os.path.join(CSRC_DIR, "librdv_b200.so")
+LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200.so")   # env: A/B experiments
 SOURCES = ("rdv_b200.cu",)
 HEADERS = ("rdv_math.cuh", "rdv_env.cuh")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -74,7 +74,7 @@ class RdvStepIO(C.Structure):
         ("actions", C.c_void_p), ("act_f64", C.c_int32), ("auto_reset", C.c_int32),
         ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
         ("terminal_obs", C.c_void_p), ("end_reason", C.c_void_p), ("episode_record", C.c_void_p),
-        ("stats", C.c_void_p), ("reset_scratch", C.c_void_p),
+        ("stats", C.c_void_p),
     ]
 
 
@@ -94,8 +94,6 @@ PROTOTYPES = {
     "rdv_params_derive": (C.c_int, [C.POINTER(RdvParams)]),
     "rdv_step": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.POINTER(RdvStepIO), C.c_int64,
                            C.c_uint64, C.c_int64, C.c_void_p]),
-    "rdv_auto_reset": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_void_p, C.c_int64,
-                                 C.c_uint64, C.c_int64, C.c_void_p]),
     "rdv_reset": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "rdv_observe": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_int64, C.c_void_p]),

@@ -104,8 +104,6 @@ class BatchedRendezvousEnv:
         self.end_reason = torch.full((n,), -1, dtype=torch.int8, device=dev)
         self.episode_record = torch.zeros((n, N.EP_NCOL), dtype=torch.float64, device=dev)
         self.stats = torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) if track_stats else None
-        # one self-clearing reset list per param group: {count, ticket, env indices...}
-        self._reset_scratch = [torch.zeros(g.n + 2, dtype=torch.int32, device=dev) for g in groups]
         self._io_cache = {}
         self._keepalive = None
 
@@ -125,13 +123,11 @@ class BatchedRendezvousEnv:
         return actions if actions.is_contiguous() else actions.contiguous()
 
     # ------------------------------------------------------------------ hot path
-    def step(self, actions: torch.Tensor, defer_reset: bool = False):
+    def step(self, actions: torch.Tensor):
         """One step of every env.  Returns (obs f32[N,17], reward f64[N], done u8[N]) -- views of the
-        env's output buffers, valid until the next ``step``.  Asynchronous on the current stream.
-        ``defer_reset`` (auto-reset envs only) queues finished envs instead of resetting them; the caller
-        must then call :meth:`run_deferred_reset` before the next step (used to time the two kernels apart)."""
+        env's output buffers, valid until the next ``step``.  Asynchronous on the current stream."""
         actions = self._check_actions(actions)
-        mode = (2 if defer_reset else 1) if self.auto_reset else 0
+        mode = 1 if self.auto_reset else 0
         act_f64 = 1 if actions.dtype == torch.float64 else 0
         esz = 8 if act_f64 else 4
         stream = _stream_ptr(self.device)
@@ -143,24 +139,12 @@ class BatchedRendezvousEnv:
                     self.done.data_ptr() + g.lo,
                     self.terminal_obs.data_ptr() + g.lo * N.OBS_DIM * 4, self.end_reason.data_ptr() + g.lo,
                     self.episode_record.data_ptr() + g.lo * N.EP_NCOL * 8,
-                    self.stats.data_ptr() if self.stats is not None else None,
-                    self._reset_scratch[gi].data_ptr())
+                    self.stats.data_ptr() if self.stats is not None else None)
                 st = self._state_of(g)
                 N.check(self.lib.rdv_step(C.byref(g.params), C.byref(st), C.byref(io), g.n, self.seed,
                                           self.env_offset + g.lo, stream), "rdv_step")
         self._keepalive = actions
         return self.obs, self.reward, self.done
-
-    def run_deferred_reset(self):
-        """Second half of an auto-reset step issued with ``defer_reset=True``."""
-        stream = _stream_ptr(self.device)
-        with torch.cuda.device(self.device):
-            for gi, g in enumerate(self.groups):
-                st = self._state_of(g)
-                N.check(self.lib.rdv_auto_reset(C.byref(g.params), C.byref(st),
-                                                self.obs.data_ptr() + g.lo * N.OBS_DIM * 4,
-                                                self._reset_scratch[gi].data_ptr(), g.n, self.seed,
-                                                self.env_offset + g.lo, stream), "rdv_auto_reset")
 
     def reset(self, mask: Optional[torch.Tensor] = None, uniforms: Optional[torch.Tensor] = None,
               bump_episode: bool = True) -> torch.Tensor:
@@ -307,6 +291,5 @@ class BatchedRendezvousEnv:
         for name in ("f64", "i32", "obs", "reward", "done", "terminal_obs", "end_reason", "episode_record"):
             setattr(other, name, getattr(self, name).clone())
         other.stats = None if self.stats is None else self.stats.clone()
-        other._reset_scratch = [t.clone() for t in self._reset_scratch]
         other._keepalive = None
         return other

@@ -13,7 +13,6 @@
 
 namespace rdv {
 
-constexpr int TPB = 64;   // 65,536 envs -> 1024 CTAs = 6.9 per SM on 148 SMs (1 % tail), see DESIGN.md
 
 // ---------------------------------------------------------------------------------
 // warp / block reduction of the statistics vector
@@ -27,7 +26,7 @@ RDV_DEV double warp_sum(double v)
 
 struct StepStats {
     // per-thread contributions; integers go through REDUX (__reduce_add_sync), doubles through shuffles
-    unsigned steps, episodes, succeeded, collided, end[4], rk_acc, rk_rej, fail;
+    unsigned steps, episodes, succeeded, collided, end0, end1, end2, end3, rk_acc, rk_rej, fail;
     double ep_return, ep_length, delta_v, delta_w, reward;
 };
 
@@ -48,7 +47,7 @@ RDV_DEV void reduce_stats(const StepStats &st, double *g_stats, double (*s_stats
         v[RDV_S_SUCCEEDED] = (double)__reduce_add_sync(full, st.succeeded);
         v[RDV_S_COLLIDED] = (double)__reduce_add_sync(full, st.collided);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[RDV_S_END_OBS + k] = (double)__reduce_add_sync(full, st.end[k]);
+        for (int k = 0; k < 4; ++k) v[RDV_S_END_OBS + k] = (double)__reduce_add_sync(full, (k==0?st.end0:k==1?st.end1:k==2?st.end2:st.end3));
         v[RDV_S_RETURN] = warp_sum(st.ep_return);
         v[RDV_S_LENGTH] = warp_sum(st.ep_length);
         v[RDV_S_DELTA_V] = warp_sum(st.delta_v);
@@ -72,256 +71,332 @@ RDV_DEV void reduce_stats(const StepStats &st, double *g_stats, double (*s_stats
     }
 }
 
+__constant__ double c_zero3[3] = {0.0, 0.0, 0.0};     // the target carries no torque (:585)
+
+RDV_DEV double pair_swap(double v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
+RDV_DEV int pair_swap(int v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
+
 // ---------------------------------------------------------------------------------
-// step kernel: RendezvousEnv.step (rendezvous_env.py:160-221), one thread per env.
-// Finished envs are appended to reset_list (count in reset_list[0]) for the compacted
-// reset kernel below, so the rare, long reset path never diverges a stepping warp.
+// step kernel: RendezvousEnv.step (rendezvous_env.py:160-221).
+//
+// TWO threads per environment, adjacent lanes of one warp:
+//   lane 2e   ("chaser lane"): chaser attitude propagation, attitude error, time / bubble / done /
+//                              reward assembly, counters, statistics;
+//   lane 2e+1 ("target lane"): target attitude propagation, the chaser's translation (impulse + CW
+//                              transition), corridor angle / collision, position / velocity / rate errors.
+// The two adaptive RK45 solves -- 88 % of the reference's step time -- run concurrently, which halves the
+// serial length of a thread, halves its live state (~120 registers instead of 244, so 16 warps per SM are
+// resident instead of 8) and doubles the number of warps the fp64 pipe can pick from.  The lanes trade
+// ~20 doubles per step through warp shuffles.  Finished envs are appended to reset_list (count in
+// reset_list[0]) for the compacted reset kernel below, so the rare reset path never diverges a stepping warp.
 // ---------------------------------------------------------------------------------
+#ifndef RDV_STEP_MIN_CTAS
+#define RDV_STEP_MIN_CTAS 4          // 4 CTAs x 4 warps = 16 resident warps per SM at <= 128 registers
+#endif
+constexpr int EPB = 64;             // environments per CTA
+constexpr int TPB = 2 * EPB;        // threads per CTA
+
 template <bool ISO, bool ACT_F64, bool CLOSED>
-__global__ void __launch_bounds__(TPB) step_kernel(const __grid_constant__ RdvParams P, const RdvState S,
-                                                   const RdvStepIO io, const int64_t n, int32_t *reset_list)
+__global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __grid_constant__ RdvParams P, const RdvState S,
+                                                      const RdvStepIO io, const int64_t n, const uint64_t seed,
+                                                      const int64_t env_offset)
 {
-    __shared__ __align__(16) float s_obs[TPB * RDV_OBS_DIM];
+    __shared__ __align__(16) float s_obs[EPB * RDV_OBS_DIM];
     __shared__ double s_stats[TPB / 32][RDV_NSTATS];
+    __shared__ double s_team[TPB / RDV_TEAM][RDV_TEAM_ROW];   // scratch rows of the reset teams
+    __shared__ int s_reset_idx[EPB];                          // envs of this CTA whose episode just ended
+    __shared__ int s_reset_n;
+    if (threadIdx.x == 0) s_reset_n = 0;
+    __syncthreads();
 
-    const int64_t base = (int64_t)blockIdx.x * TPB;
-    const int64_t i = base + threadIdx.x;
-    const bool active = i < n;
-    StepStats st;
-    memset(&st, 0, sizeof(st));
+    const int body = threadIdx.x & 1;                         // 0: chaser lane, 1: target lane
+    const int64_t base = (int64_t)blockIdx.x * EPB;
+    const int64_t i_raw = base + (threadIdx.x >> 1);
+    const bool active = i_raw < n;
+    const int64_t i = active ? i_raw : n - 1;                 // idle pairs shadow the last env (no stores)
+    const int64_t ld = S.ld;
+    const double *f = S.f64 + i;
+    StepStats st = {};
 
+    // ---- own body: attitude quaternion and body rate ----
+    const int qrow = body ? RDV_QTW : RDV_QCW, wrow = body ? RDV_WTX : RDV_WCX;
+    double y[7];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = f[(qrow + k) * ld];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) y[4 + k] = f[(wrow + k) * ld];
+
+    // ---- action ingest (:168-173, :201-202, :333): the target lane takes a[0:3] (delta-v), the chaser
+    //      lane a[3:6] (delta-w); `total` is total_delta_v on the target lane, total_delta_w on the chaser lane
+    double act[3], total = f[(body ? RDV_TDV : RDV_TDW) * ld], fuel = 0.0;
+    if (ACT_F64) {
+        const double *ap = static_cast<const double *>(io.actions) + 6 * i + (body ? 0 : 3);
+        const double a0 = ap[0], a1 = ap[1], a2 = ap[2];
+        const double scale = body ? P.max_delta_v : P.max_delta_w;
+        const double sum = fabs(a0) + fabs(a1) + fabs(a2);
+        act[0] = a0 * scale; act[1] = a1 * scale; act[2] = a2 * scale;
+        total += sum * scale;
+        fuel = __ddiv_rn(P.dt * P.fuel_coef * sum, 3.0 * P.max_delta_v);
+    } else {
+        // float32 actions follow NumPy-2 promotion: delta_v, total_delta_v and the
+        // fuel term are rounded in fp32; delta_w and total_delta_w are fp64.
+        const float *ap = static_cast<const float *>(io.actions) + 6 * i + (body ? 0 : 3);
+        const float a0 = ap[0], a1 = ap[1], a2 = ap[2];
+        const float sum = __fadd_rn(__fadd_rn(fabsf(a0), fabsf(a1)), fabsf(a2));
+        if (body) {
+            act[0] = (double)__fmul_rn(a0, P.max_delta_v_f32);
+            act[1] = (double)__fmul_rn(a1, P.max_delta_v_f32);
+            act[2] = (double)__fmul_rn(a2, P.max_delta_v_f32);
+            total = (double)__fadd_rn((float)total, __fmul_rn(sum, P.max_delta_v_f32));
+            fuel = (double)__fdiv_rn(__fmul_rn(P.fuel_num_f32, sum), P.fuel_den_f32);
+        } else {
+            act[0] = (double)a0 * P.max_delta_w; act[1] = (double)a1 * P.max_delta_w;
+            act[2] = (double)a2 * P.max_delta_w;
+            total += (double)sum * P.max_delta_w;
+        }
+    }
+
+    // ---- translation on the target lane: impulse rotated by the chaser's OLD attitude, then the CW
+    //      transition (:172-177, dynamics.py:24-55).  The chaser lane applies its rate impulse (:180).
+    double qo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) qo[k] = pair_swap(y[k]);      // target lane receives qc_old
+    double rc[3] = {0.0, 0.0, 0.0}, vc[3] = {0.0, 0.0, 0.0};
+    if (body) {
+        const Rot Rc_old = rot_from_quat(qo);
+        double dv[3];
+        rot_apply(Rc_old, act, dv);
+        const double r0 = f[RDV_RCX * ld], r1 = f[RDV_RCY * ld], r2 = f[RDV_RCZ * ld];
+        const double v0 = f[RDV_VCX * ld] + dv[0], v1 = f[RDV_VCY * ld] + dv[1], v2 = f[RDV_VCZ * ld] + dv[2];
+        const double *c = P.cw;
+        rc[0] = fma(c[2], v1, fma(c[1], v0, c[0] * r0));
+        rc[1] = fma(c[6], v1, fma(c[5], v0, fma(c[3], r0, c[4] * r1)));
+        rc[2] = fma(c[8], v2, c[7] * r2);
+        vc[0] = fma(c[11], v1, fma(c[10], v0, c[9] * r0));
+        vc[1] = fma(c[14], v1, fma(c[13], v0, c[12] * r0));
+        vc[2] = fma(c[16], v2, c[15] * r2);
+    } else {
+        y[4] += act[0]; y[5] += act[1]; y[6] += act[2];
+    }
+
+    // ---- attitude: torque-free propagation of this lane's body over dt (:180-184, :552-604) ----
+    int rk_acc = 0, rk_rej = 0, fail = 0;
+    if (CLOSED) {
+        closed_form_attitude(y, P.dt);
+    } else {
+        BodyConst bc;
+        bc.I = body ? P.inertia_t : P.inertia_c;
+        bc.Iinv = body ? P.inv_inertia_t : P.inv_inertia_c;
+        bc.tau = body ? c_zero3 : P.torque_c;
+        const int k = rk45_attitude<ISO>(y, P.dt, bc, rk_rej);
+        if (k < 0) fail = 1; else rk_acc = k;
+    }
+    {
+        const double r = fast_rsqrt(dot4(y, y));               // q / |q|  (:574-575, :601-602)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[k] *= r;
+    }
+
+    // ---- post-step geometry, split over the pair ----
+    const Rot R = rot_from_quat(y);
+    double wl[3];
+    rot_apply(R, y + 4, wl);                                   // own body rate in LVLH (:451-468)
+    // swap: chaser lane sends wc_L, target lane sends rc
+    double got[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) got[k] = pair_swap(body ? rc[k] : wl[k]);
+    double part0, part1, part2;                                // target: pos^2, vel^2, rot^2 ; chaser: att, |rc|^2, -
+    int col_now = 0;
+    if (body) {
+        double rd_l[3], vd_l[3], ax[3], d[3];
+        rot_apply(R, P.rd, rd_l);
+        cross3(wl, rd_l, vd_l);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = rc[k] - rd_l[k];
+        part0 = dot3(d, d);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = vc[k] - vd_l[k];
+        part1 = dot3(d, d);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = got[k] - wl[k];     // wc_L - wt_L
+        part2 = dot3(d, d);
+        const double rc_sq = dot3(rc, rc);
+        if (sqrt(rc_sq) < P.koz_radius) {                      // check_collision (:388-404)
+            rot_apply(R, P.corridor_axis, ax);
+            const double th = rounded_angle_from(dot3(rc, ax), rc_sq, dot3(ax, ax));
+            col_now = th > P.corridor_half_angle ? 1 : 0;
+        }
+    } else {
+        double cap[3];
+        rot_apply(R, P.capture_axis, cap);
+        const double rc_sq = dot3(got, got);
+        part0 = rounded_angle_from(-dot3(got, cap), rc_sq, dot3(cap, cap));    // attitude error (:424-434)
+        part1 = rc_sq;
+        part2 = 0.0;
+    }
+    // chaser lane collects the target lane's results
+    const double pos_sq = pair_swap(part0), vel_sq = pair_swap(part1), rot_sq = pair_swap(part2);
+    const double fuel_t = pair_swap(fuel), total_t = pair_swap(total);
+    const int col_t = pair_swap(col_now);
+
+    // ---- observation (:205): each lane writes the slots it owns into the shared staging row ----
+    float *o = s_obs + (threadIdx.x >> 1) * RDV_OBS_DIM;
+    const ObsScale sc = obs_scale(P);
+    bool in_box = true;
+    if (body) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float a = (float)fma(2.0 * (rc[k] + sc.hi_r), sc.inv_r, -1.0);
+            const float b = (float)fma(2.0 * (vc[k] + sc.hi_v), sc.inv_v, -1.0);
+            o[k] = a; o[3 + k] = b;
+            in_box = in_box && a >= -1.0f && a <= 1.0f && b >= -1.0f && b <= 1.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = (float)y[k];
+            o[13 + k] = a;
+            in_box = in_box && a >= -1.0f && a <= 1.0f;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = (float)y[k];
+            o[6 + k] = a;
+            in_box = in_box && a >= -1.0f && a <= 1.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float a = (float)fma(2.0 * (y[4 + k] + sc.hi_w), sc.inv_w, -1.0);
+            o[10 + k] = a;
+            in_box = in_box && a >= -1.0f && a <= 1.0f;
+        }
+    }
+    const int box_t = pair_swap((int)in_box);
+
+    // ---- state write-back: every lane stores the rows it owns ----
+    double *fw = S.f64 + i;
     if (active) {
-        EnvRegs e;
-        load_env(S, i, e);
-        const int64_t ld = S.ld;
-        double tdv = S.f64[RDV_TDV * ld + i], tdw = S.f64[RDV_TDW * ld + i], ep_ret = S.f64[RDV_EPRET * ld + i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fw[(qrow + k) * ld] = y[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) fw[(wrow + k) * ld] = y[4 + k];
+        fw[(body ? RDV_TDV : RDV_TDW) * ld] = total;
+        if (body) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { fw[(RDV_RCX + k) * ld] = rc[k]; fw[(RDV_VCX + k) * ld] = vc[k]; }
+        }
+    }
+    st.rk_acc = active ? rk_acc : 0; st.rk_rej = active ? rk_rej : 0; st.fail = active ? fail : 0;
+
+    // ---- chaser lane: latch, time, bubble, done, reward, outputs ----
+    int done = 0;
+    if (!body) {
         int step = S.i32[RDV_I_STEP * ld + i], success = S.i32[RDV_I_SUCCESS * ld + i];
         int collided = S.i32[RDV_I_COLLIDED * ld + i];
-
-        // ---- action ingest (:168-173, :201-202, :333) ----
-        double dvb[3], dw[3], fuel;
-        if (ACT_F64) {
-            const double2 *ap = reinterpret_cast<const double2 *>(static_cast<const double *>(io.actions) + 6 * i);
-            double2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
-            dvb[0] = a01.x * P.max_delta_v; dvb[1] = a01.y * P.max_delta_v; dvb[2] = a23.x * P.max_delta_v;
-            dw[0] = a23.y * P.max_delta_w; dw[1] = a45.x * P.max_delta_w; dw[2] = a45.y * P.max_delta_w;
-            double sv = fabs(a01.x) + fabs(a01.y) + fabs(a23.x);
-            double sw = fabs(a23.y) + fabs(a45.x) + fabs(a45.y);
-            tdv += sv * P.max_delta_v;
-            tdw += sw * P.max_delta_w;
-            fuel = __ddiv_rn(P.dt * P.fuel_coef * sv, 3.0 * P.max_delta_v);
-        } else {
-            // float32 actions follow NumPy-2 promotion: delta_v, total_delta_v
-            // and the fuel term are rounded in fp32; delta_w and total_delta_w are fp64.
-            const float2 *ap = reinterpret_cast<const float2 *>(static_cast<const float *>(io.actions) + 6 * i);
-            float2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
-            dvb[0] = (double)__fmul_rn(a01.x, P.max_delta_v_f32);
-            dvb[1] = (double)__fmul_rn(a01.y, P.max_delta_v_f32);
-            dvb[2] = (double)__fmul_rn(a23.x, P.max_delta_v_f32);
-            dw[0] = (double)a23.y * P.max_delta_w; dw[1] = (double)a45.x * P.max_delta_w;
-            dw[2] = (double)a45.y * P.max_delta_w;
-            float sv = __fadd_rn(__fadd_rn(fabsf(a01.x), fabsf(a01.y)), fabsf(a23.x));
-            float sw = __fadd_rn(__fadd_rn(fabsf(a23.y), fabsf(a45.x)), fabsf(a45.y));
-            tdv = (double)__fadd_rn((float)tdv, __fmul_rn(sv, P.max_delta_v_f32));
-            tdw += (double)sw * P.max_delta_w;
-            fuel = (double)__fdiv_rn(__fmul_rn(P.fuel_num_f32, sv), P.fuel_den_f32);
-        }
-
-        // ---- translation: impulse in LVLH, then the CW transition (:172-177, dynamics.py:24-55) ----
-        {
-            Rot Rc_old = rot_from_quat(e.qc);
-            double dv[3];
-            rot_apply(Rc_old, dvb, dv);
-            double r0 = e.rc[0], r1 = e.rc[1], r2 = e.rc[2];
-            double v0 = e.vc[0] + dv[0], v1 = e.vc[1] + dv[1], v2 = e.vc[2] + dv[2];
-            const double *c = P.cw;
-            e.rc[0] = fma(c[2], v1, fma(c[1], v0, c[0] * r0));
-            e.rc[1] = fma(c[6], v1, fma(c[5], v0, fma(c[3], r0, c[4] * r1)));
-            e.rc[2] = fma(c[8], v2, c[7] * r2);
-            e.vc[0] = fma(c[11], v1, fma(c[10], v0, c[9] * r0));
-            e.vc[1] = fma(c[14], v1, fma(c[13], v0, c[12] * r0));
-            e.vc[2] = fma(c[16], v2, c[15] * r2);
-        }
-
-        // ---- attitude: impulsive rate change, then torque-free propagation of both bodies (:180-184) ----
-        int rk_acc = 0, rk_rej = 0, fail = 0;
-        {
-            double y[7] = {e.qc[0], e.qc[1], e.qc[2], e.qc[3], e.wc[0] + dw[0], e.wc[1] + dw[1], e.wc[2] + dw[2]};
-            double z[7] = {e.qt[0], e.qt[1], e.qt[2], e.qt[3], e.wt[0], e.wt[1], e.wt[2]};
-#pragma unroll 1
-            for (int body = 0; body < 2; ++body) {
-                if (CLOSED) {
-                    closed_form_attitude(y, P.dt);
-                } else {
-                    BodyConst bc;
-                    bc.I = body ? P.inertia_t : P.inertia_c;
-                    bc.Iinv = body ? P.inv_inertia_t : P.inv_inertia_c;
-                    const double zero3[3] = {0.0, 0.0, 0.0};
-                    bc.tau = body ? zero3 : P.torque_c;
-                    int k = rk45_attitude<ISO>(y, P.dt, bc, rk_rej);
-                    if (k < 0) fail = 1; else rk_acc += k;
-                }
-                double r = fast_rsqrt(dot4(y, y));                 // q / |q|  (:574-575, :601-602)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) y[k] *= r;
-#pragma unroll
-                for (int k = 0; k < 7; ++k) { double t = y[k]; y[k] = z[k]; z[k] = t; }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { e.qc[k] = y[k]; e.qt[k] = z[k]; }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { e.wc[k] = y[4 + k]; e.wt[k] = z[4 + k]; }
-        }
-
-        // ---- collision / success latch (:186-190) ----
-        const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
-        const double rc_sq = dot3(e.rc, e.rc), rc_n = sqrt(rc_sq);
-        const double att = attitude_error(P, e, Rc, rc_sq);
-        const bool col_now = collision_now(P, e, Rt, rc_sq, rc_n);
-        ErrSq es = errors_sq(P, e, Rc, Rt);
+        double ep_ret = f[RDV_EPRET * ld];
+        const double att = part0, rc_n = sqrt(part1);
+        const double pos_err = sqrt(pos_sq);
+        // collision / success latch (:186-190)
         if (!collided) {
-            collided = col_now ? 1 : 0;
-            if (!collided && sqrt(es.pos) <= P.max_rd_error && sqrt(es.vel) <= P.max_vd_error &&
-                att <= P.max_qd_error && sqrt(es.rot) <= P.max_wd_error)
+            collided = col_t;
+            if (!collided && pos_err <= P.max_rd_error && sqrt(vel_sq) <= P.max_vd_error && att <= P.max_qd_error &&
+                sqrt(rot_sq) <= P.max_wd_error)
                 success += 1;
         }
-        // ---- time and bubble (:193-198), derived from the step counter ----
+        // time and bubble (:193-198), derived from the step counter
         step += 1;
         const double t = __ddiv_rn(rint((double)step * P.dt * 1000.0), 1000.0);
         const double bubble = fmax(fma(-(double)step, P.bubble_rate, P.bubble0), P.bubble_min);
-
-        // ---- observation (:205) into the shared staging row ----
-        float *o = s_obs + threadIdx.x * RDV_OBS_DIM;
-        float ov[RDV_OBS_DIM];
-        make_obs(e, obs_scale(P), ov);
-#pragma unroll
-        for (int k = 0; k < RDV_OBS_DIM; ++k) o[k] = ov[k];
-
-        // ---- done (:355-386): first true condition is the end reason ----
-        const bool c0 = !obs_in_box(ov), c1 = t >= P.t_max, c2 = rc_n > bubble, c3 = att > P.max_attitude_error;
-        const bool done = c0 || c1 || c2 || c3;
+        // done (:355-386): first true condition is the end reason
+        const bool c0 = !(in_box && box_t), c1 = t >= P.t_max, c2 = rc_n > bubble, c3 = att > P.max_attitude_error;
+        done = (c0 || c1 || c2 || c3) ? 1 : 0;
         const int reason = c0 ? 0 : c1 ? 1 : c2 ? 2 : c3 ? 3 : -1;
-
-        // ---- reward (:313-353) ----
+        // reward (:313-353)
         double rew = (P.dt * P.att_coef) * (1.0 - __ddiv_rn(att, P.max_attitude_error));
-        rew += fuel;
-        if (col_now) rew -= P.dt * P.collision_coef;
-        if (rc_n < P.koz_radius && !collided) {
-            double pos_err = sqrt(es.pos);
-            if (pos_err < P.max_rd_error) {
-                rew += P.dt * P.bonus_coef * (2.0 - __ddiv_rn(pos_err, P.max_rd_error));
-                if (att < P.max_qd_error) rew += P.dt * P.bonus_coef * (2.0 - __ddiv_rn(att, P.max_qd_error));
-            }
+        rew += fuel_t;
+        if (col_t) rew -= P.dt * P.collision_coef;
+        if (rc_n < P.koz_radius && !collided && pos_err < P.max_rd_error) {
+            rew += P.dt * P.bonus_coef * (2.0 - __ddiv_rn(pos_err, P.max_rd_error));
+            if (att < P.max_qd_error) rew += P.dt * P.bonus_coef * (2.0 - __ddiv_rn(att, P.max_qd_error));
         }
         ep_ret += rew;
-
-        // ---- outputs ----
-        io.reward[i] = rew;
-        io.done[i] = done ? 1 : 0;
-        if (io.end_reason) io.end_reason[i] = (int8_t)reason;
-        st.steps = 1; st.reward = rew; st.rk_acc = rk_acc; st.rk_rej = rk_rej; st.fail = fail;
-        if (done) {
-            st.episodes = 1; st.succeeded = success > 0; st.collided = collided; st.end[reason] = 1;
-            st.ep_return = ep_ret; st.ep_length = (double)step; st.delta_v = tdv; st.delta_w = tdw;
-            if (io.episode_record) {
-                double *rec = io.episode_record + RDV_EP_NCOL * i;
-                rec[RDV_EP_RETURN] = ep_ret; rec[RDV_EP_LENGTH] = (double)step; rec[RDV_EP_SUCCESS] = (double)success;
-                rec[RDV_EP_COLLIDED] = (double)collided; rec[RDV_EP_DELTA_V] = tdv; rec[RDV_EP_DELTA_W] = tdw;
-            }
-            if (io.terminal_obs) {
-                float *to = io.terminal_obs + RDV_OBS_DIM * i;
-#pragma unroll
-                for (int k = 0; k < RDV_OBS_DIM; ++k) to[k] = ov[k];
-            }
-            if (io.auto_reset) {
-                int slot = atomicAdd(reset_list, 1);
-                reset_list[2 + slot] = (int32_t)(i);       // local env index; the reset kernel rewrites state + obs
+        if (active) {
+            io.reward[i] = rew;
+            io.done[i] = (uint8_t)done;
+            if (io.end_reason) io.end_reason[i] = (int8_t)reason;
+            st.steps = 1; st.reward = rew;
+            fw[RDV_EPRET * ld] = ep_ret;
+            S.i32[RDV_I_STEP * ld + i] = step; S.i32[RDV_I_SUCCESS * ld + i] = success;
+            S.i32[RDV_I_COLLIDED * ld + i] = collided;
+            if (done) {
+                st.episodes = 1; st.succeeded = success > 0; st.collided = collided;
+                st.end0 = reason == 0; st.end1 = reason == 1; st.end2 = reason == 2; st.end3 = reason == 3;
+                st.ep_return = ep_ret; st.ep_length = (double)step; st.delta_v = total_t; st.delta_w = total;
+                if (io.episode_record) {
+                    double *rec = io.episode_record + RDV_EP_NCOL * i;
+                    rec[RDV_EP_RETURN] = ep_ret; rec[RDV_EP_LENGTH] = (double)step;
+                    rec[RDV_EP_SUCCESS] = (double)success; rec[RDV_EP_COLLIDED] = (double)collided;
+                    rec[RDV_EP_DELTA_V] = total_t; rec[RDV_EP_DELTA_W] = total;
+                }
+                if (io.auto_reset) s_reset_idx[atomicAdd(&s_reset_n, 1)] = threadIdx.x >> 1;
             }
         }
-        store_env(S, i, e);
-        S.f64[RDV_TDV * ld + i] = tdv; S.f64[RDV_TDW * ld + i] = tdw; S.f64[RDV_EPRET * ld + i] = ep_ret;
-        S.i32[RDV_I_STEP * ld + i] = step; S.i32[RDV_I_SUCCESS * ld + i] = success;
-        S.i32[RDV_I_COLLIDED * ld + i] = collided;
+    }
+
+    // ---- terminal observation of finished episodes: the pair copies its staged row ----
+    __syncwarp();
+    if (io.terminal_obs) {
+        const int done_pair = __shfl_sync(0xffffffffu, done, (threadIdx.x & 31) & ~1);
+        if (done_pair && active) {
+            float *to = io.terminal_obs + RDV_OBS_DIM * i;
+            for (int k = body; k < RDV_OBS_DIM; k += 2) to[k] = o[k];
+        }
+    }
+
+    // ---- auto-reset (what DummyVecEnv.step_wait does around step, main.py:33-34): the CTA's finished envs
+    //      are reset by teams of 8 lanes, 16 envs per pass; their staged observation rows are replaced by
+    //      the post-reset observation.  The stores are ordered after the step's own by the barrier.
+    __syncthreads();
+    if (io.auto_reset) {
+        const int count = s_reset_n, team = threadIdx.x / RDV_TEAM;
+        for (int b = 0; b < count; b += TPB / RDV_TEAM) {
+            const bool valid = b + team < count;
+            const int local = valid ? s_reset_idx[b + team] : 0;
+            const int64_t ie = base + local < n ? base + local : n - 1;
+            team_reset(P, S, seed, env_offset + ie, ie, valid, 1, nullptr, s_team[team], s_obs + local * RDV_OBS_DIM);
+        }
+        __syncthreads();
     }
 
     // ---- coalesced observation write-out: the CTA's rows are contiguous in obs[n][17] ----
-    __syncthreads();
     {
-        const int64_t rows = (n - base) < TPB ? (n - base) : TPB;
-        const int total = (int)rows * RDV_OBS_DIM;
-        float *dst = io.obs + base * RDV_OBS_DIM;              // base*17*4 B is a multiple of 16 (TPB = 64)
-        const int nvec = total >> 2;
+        const int64_t rows = (n - base) < EPB ? (n - base) : EPB;
+        const int total_f = (int)rows * RDV_OBS_DIM;
+        float *dst = io.obs + base * RDV_OBS_DIM;              // base*17*4 B is a multiple of 16 (EPB = 64)
+        const int nvec = total_f >> 2;
         const float4 *src4 = reinterpret_cast<const float4 *>(s_obs);
         float4 *dst4 = reinterpret_cast<float4 *>(dst);
         for (int k = threadIdx.x; k < nvec; k += TPB) dst4[k] = src4[k];
-        for (int k = (nvec << 2) + threadIdx.x; k < total; k += TPB) dst[k] = s_obs[k];
+        for (int k = (nvec << 2) + threadIdx.x; k < total_f; k += TPB) dst[k] = s_obs[k];
     }
     if (io.stats) reduce_stats<TPB / 32>(st, io.stats, s_stats);
 }
 
 // ---------------------------------------------------------------------------------
-// compacted auto-reset: one thread per finished env (list built by step_kernel).
-// reset_list = {count, ticket, idx...}; the last CTA to finish clears count and ticket.
+// reset() for masked envs (rendezvous_env.py:223-270): 8 lanes per env (team_reset), 16 envs per CTA.
+// Draws come from Philox or from the caller's uniforms (test hook).
 // ---------------------------------------------------------------------------------
-RDV_DEV void write_reset_state(const RdvParams &P, const RdvState &S, int64_t i, const EnvRegs &e, int collided,
-                               int success, int episode, float *obs_row)
-{
-    const int64_t ld = S.ld;
-    store_env(S, i, e);
-    S.f64[RDV_TDV * ld + i] = 0.0; S.f64[RDV_TDW * ld + i] = 0.0; S.f64[RDV_EPRET * ld + i] = 0.0;
-    S.i32[RDV_I_STEP * ld + i] = 0; S.i32[RDV_I_SUCCESS * ld + i] = success;
-    S.i32[RDV_I_COLLIDED * ld + i] = collided; S.i32[RDV_I_EPISODE * ld + i] = episode;
-    if (obs_row) {
-        float ov[RDV_OBS_DIM];
-        make_obs(e, obs_scale(P), ov);
-#pragma unroll
-        for (int k = 0; k < RDV_OBS_DIM; ++k) obs_row[k] = ov[k];
-    }
-}
-
-__global__ void __launch_bounds__(128) reset_list_kernel(const __grid_constant__ RdvParams P, const RdvState S,
-                                                         float *obs, int32_t *reset_list, uint64_t seed,
-                                                         int64_t env_offset)
-{
-    const int count = reset_list[0];
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-        const int64_t i = reset_list[2 + j];
-        const int episode = S.i32[RDV_I_EPISODE * S.ld + i] + 1;
-        double u[24];
-        draw_uniforms(seed, env_offset + i, episode, u);
-        EnvRegs e;
-        int collided, success;
-        reset_env(P, u, e, collided, success);
-        write_reset_state(P, S, i, e, collided, success, episode, obs + RDV_OBS_DIM * i);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        int ticket = atomicAdd(reset_list + 1, 1);
-        if (ticket == (int)gridDim.x - 1) { reset_list[0] = 0; reset_list[1] = 0; }
-    }
-}
-
-// reset() for masked envs (rendezvous_env.py:223-270); uniforms from Philox or from the caller.
 __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ RdvParams P, const RdvState S,
                                                     const uint8_t *mask, const double *uniforms, float *obs,
                                                     int64_t n, uint64_t seed, int64_t env_offset, int bump)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (mask && !mask[i]) return;
-    const int episode = S.i32[RDV_I_EPISODE * S.ld + i] + (bump ? 1 : 0);
-    double u[24];
-    if (uniforms) {
-#pragma unroll
-        for (int k = 0; k < 24; ++k) u[k] = uniforms[24 * i + k];
-    } else {
-        draw_uniforms(seed, env_offset + i, episode, u);
-    }
-    EnvRegs e;
-    int collided, success;
-    reset_env(P, u, e, collided, success);
-    write_reset_state(P, S, i, e, collided, success, episode, obs ? obs + RDV_OBS_DIM * i : nullptr);
+    __shared__ double s_team[128 / RDV_TEAM][RDV_TEAM_ROW];
+    const int team = threadIdx.x / RDV_TEAM;
+    const int64_t i_raw = (int64_t)blockIdx.x * (128 / RDV_TEAM) + team;
+    const int64_t i = i_raw < n ? i_raw : n - 1;
+    const bool valid = i_raw < n && (!mask || mask[i]);
+    team_reset(P, S, seed, env_offset + i, i, valid, bump, uniforms ? uniforms + RDV_N_UNIFORMS * i : nullptr,
+               s_team[team], obs ? obs + RDV_OBS_DIM * i : nullptr);
 }
 
 __global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ RdvParams P, const RdvState S,
@@ -583,39 +658,16 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
     if (((uintptr_t)io->actions & (io->act_f64 ? 15 : 7)) || ((uintptr_t)io->obs & 15) || ((uintptr_t)io->reward & 7))
         return RDV_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const unsigned grid = (unsigned)((n + TPB - 1) / TPB);
+    const unsigned grid = (unsigned)((n + EPB - 1) / EPB);
     const bool iso = p->iso_c && p->iso_t;
     const bool closed = p->integrator == RDV_INTEGRATOR_CLOSED_FORM;
-    int32_t *reset_list = nullptr;      // {count, ticket, env indices...}, self-clearing
-    if (io->auto_reset < 0 || io->auto_reset > 2) return RDV_ERR_SIZE;
-    if (io->auto_reset) {
-        if (!io->reset_scratch) return RDV_ERR_NULL;
-        reset_list = io->reset_scratch;
-    }
+    if (io->auto_reset != 0 && io->auto_reset != 1) return RDV_ERR_SIZE;
 #define RDV_LAUNCH(ISO_, F64_, CL_) \
-    step_kernel<ISO_, F64_, CL_><<<grid, TPB, 0, st>>>(*p, *s, *io, n, reset_list)
+    step_kernel<ISO_, F64_, CL_><<<grid, TPB, 0, st>>>(*p, *s, *io, n, seed, env_offset)
     if (closed) { if (io->act_f64) RDV_LAUNCH(true, true, true); else RDV_LAUNCH(true, false, true); }
     else if (iso) { if (io->act_f64) RDV_LAUNCH(true, true, false); else RDV_LAUNCH(true, false, false); }
     else { if (io->act_f64) RDV_LAUNCH(false, true, false); else RDV_LAUNCH(false, false, false); }
 #undef RDV_LAUNCH
-    rc = launch_status();
-    if (rc) return rc;
-    if (io->auto_reset == 1) rc = rdv_auto_reset(p, s, io->obs, reset_list, n, seed, env_offset, cuda_stream);
-    return rc;
-}
-
-int rdv_auto_reset(const RdvParams *p, const RdvState *s, float *obs, int32_t *reset_scratch, int64_t n,
-                   uint64_t seed, int64_t env_offset, void *cuda_stream)
-{
-    if (!p || !obs || !reset_scratch) return RDV_ERR_NULL;
-    int rc = check_state(s, n);
-    if (rc) return rc;
-    if (n == 0) return RDV_OK;
-    // grid sized for the common case (<= n/8 finished envs per step); grid-stride covers the rest
-    unsigned rgrid = (unsigned)((n / 8 + 127) / 128);
-    if (rgrid < 1) rgrid = 1;
-    if (rgrid > 4096) rgrid = 4096;
-    reset_list_kernel<<<rgrid, 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, obs, reset_scratch, seed, env_offset);
     return launch_status();
 }
 
@@ -626,8 +678,9 @@ int rdv_reset(const RdvParams *p, const RdvState *s, const uint8_t *mask, const 
     int rc = check_state(s, n);
     if (rc) return rc;
     if (n == 0) return RDV_OK;
-    reset_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, mask, uniforms, obs, n,
-                                                                                      seed, env_offset, bump_episode);
+    const int64_t per_cta = 128 / RDV_TEAM;
+    reset_kernel<<<(unsigned)((n + per_cta - 1) / per_cta), 128, 0, (cudaStream_t)cuda_stream>>>(
+        *p, *s, mask, uniforms, obs, n, seed, env_offset, bump_episode ? 1 : 0);
     return launch_status();
 }
 

@@ -133,88 +133,139 @@ RDV_DEV double koz_distance(const RdvParams &P, double r, double th)
 }
 
 // ---------------------------------------------------------------------------------
-// reset() (rendezvous_env.py:223-270).  u[24] are the uniform draws in the reference's order:
-// rc dir(3)+mag, vc dir(3)+mag, theta_c, axis_c(3), wc dir(3)+mag, theta_t, axis_t(3),
-// wt dir(3)+mag.  Uses IEEE sqrt/div: this path is rare and follows the reference op by op.
+// reset() (rendezvous_env.py:223-270), computed by a TEAM of 8 adjacent lanes per environment.
+//
+// The reference consumes 24 uniform draws in a fixed order: rc dir(3)+mag, vc dir(3)+mag, theta_c,
+// axis_c(3), wc dir(3)+mag, theta_t, axis_t(3), wt dir(3)+mag.  Lane `sub` (0..5) of a team owns
+// quantity `sub` of (rc, vc, qc, wc, qt, wt) and the four draws u[4 sub .. 4 sub + 3], which are
+// exactly Philox blocks 2 sub and 2 sub + 1 of the (seed; env id, episode) stream -- so the six
+// quantities are generated concurrently, the two body rates wait only for their quaternion
+// (lvlh2chaser / lvlh2target, :256, :258), and lane 0 evaluates the collided / success flags
+// (:260-261) while lanes 1..7 store the state and the observation.  One serial reset (~5 k
+// dependent instructions in the one-thread form) becomes ~0.7 k.
+//
+// `row` is a team-private scratch of RDV_TEAM_ROW doubles in shared memory.  Every lane of the warp
+// must call the function (teams with valid == false compute on env i but store nothing).
 // ---------------------------------------------------------------------------------
-RDV_DEV void unit_from_cube(const double *u, double o[3])      // utils/general.py:248-254
-{
-    double v[3] = {fma(2.0, u[0], -1.0), fma(2.0, u[1], -1.0), fma(2.0, u[2], -1.0)};
-    double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-    o[0] = v[0] / nv; o[1] = v[1] / nv; o[2] = v[2] / nv;
-}
-RDV_DEV void quat_from_axis_angle(const double ax_in[3], double theta, double q[4])   // quaternions.py:11-27
-{
-    double na = sqrt(ax_in[0] * ax_in[0] + ax_in[1] * ax_in[1] + ax_in[2] * ax_in[2]);
-    double s, c;
-    sincos(theta / 2, &s, &c);
-    q[0] = c; q[1] = ax_in[0] / na * s; q[2] = ax_in[1] / na * s; q[3] = ax_in[2] / na * s;
-    double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] /= nq;
-}
-RDV_DEV void quat_mul(const double a_in[4], const double b_in[4], double o[4])        // quaternions.py:149-170
-{
-    double na = sqrt(a_in[0] * a_in[0] + a_in[1] * a_in[1] + a_in[2] * a_in[2] + a_in[3] * a_in[3]);
-    double nb = sqrt(b_in[0] * b_in[0] + b_in[1] * b_in[1] + b_in[2] * b_in[2] + b_in[3] * b_in[3]);
-    double a[4], b[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { a[k] = a_in[k] / na; b[k] = b_in[k] / nb; }
-    o[0] = a[0] * b[0] - (a[1] * b[1] + a[2] * b[2] + a[3] * b[3]);
-    o[1] = a[0] * b[1] + b[0] * a[1] + (a[2] * b[3] - a[3] * b[2]);
-    o[2] = a[0] * b[2] + b[0] * a[2] + (a[3] * b[1] - a[1] * b[3]);
-    o[3] = a[0] * b[3] + b[0] * a[3] + (a[1] * b[2] - a[2] * b[1]);
-}
+constexpr int RDV_TEAM = 8;
+constexpr int RDV_TEAM_ROW = 24;
 
-RDV_DEV void reset_env(const RdvParams &P, const double (&u)[24], EnvRegs &e, int &collided, int &success)
+RDV_DEV void team_reset(const RdvParams &P, const RdvState &S, uint64_t seed, int64_t env_id, int64_t i,
+                        bool valid, int bump, const double *uniforms /* nullable [24] of this env */,
+                        double *row, float *obs_row /* staging row (shared) or global row */)
 {
-    double dir[3], qd[4], tmp[3];
-    unit_from_cube(u + 0, dir);
+    const int sub = threadIdx.x & (RDV_TEAM - 1);
+    const int64_t ld = S.ld;
+    const int episode = S.i32[RDV_I_EPISODE * ld + i] + bump;
+
+    // ---- phase 1: own quantity from own four draws ----
+    double val[4] = {0.0, 0.0, 0.0, 0.0};
+    if (sub < 6) {
+        double u0, u1, u2, u3;
+        if (uniforms) {
+            u0 = uniforms[4 * sub]; u1 = uniforms[4 * sub + 1]; u2 = uniforms[4 * sub + 2]; u3 = uniforms[4 * sub + 3];
+        } else {
+            philox_uniform_pair(seed, env_id, episode, 2 * sub, u0, u1);
+            philox_uniform_pair(seed, env_id, episode, 2 * sub + 1, u2, u3);
+        }
+        const bool quat = (sub == 2) || (sub == 4);
+        // random_unit_vector (utils/general.py:248-254): normalised U(-1,1)^3
+        const double a = quat ? u1 : u0, b = quat ? u2 : u1, c = quat ? u3 : u2, m = quat ? u0 : u3;
+        const double v[3] = {fma(2.0, a, -1.0), fma(2.0, b, -1.0), fma(2.0, c, -1.0)};
+        const double rn = fast_rsqrt(dot3(v, v));
+        const double dir[3] = {v[0] * rn, v[1] * rn, v[2] * rn};
+        const double range = sub == 0 ? P.rc0_range : sub == 1 ? P.vc0_range : sub == 2 ? P.qc0_range
+                           : sub == 3 ? P.wc0_range : sub == 4 ? P.qt0_range : P.wt0_range;
+        const double mag = range * m;                          // np.random.uniform(0, range)
+        if (!quat) {
+            const double *nom = sub == 0 ? P.rc0 : sub == 1 ? P.vc0 : sub == 3 ? P.wc0 : P.wt0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) e.rc[k] = P.rc0[k] + dir[k] * (P.rc0_range * u[3]);
-    unit_from_cube(u + 4, dir);
+            for (int k = 0; k < 3; ++k) val[k] = fma(dir[k], mag, nom[k]);
+        } else {
+            // rot2quat (quaternions.py:11-27) then quat_product(dev, nominal) (:149-170); both normalise
+            double sn, cs;
+            sincos(0.5 * mag, &sn, &cs);
+            const double ra = fast_rsqrt(dot3(dir, dir));
+            double qa[4] = {cs, dir[0] * ra * sn, dir[1] * ra * sn, dir[2] * ra * sn};
+            const double rq = fast_rsqrt(dot4(qa, qa));
+            const double *qn = sub == 2 ? P.qc0 : P.qt0;
+            const double rb = fast_rsqrt(dot4(qn, qn));
+            const double qb[4] = {qn[0] * rb, qn[1] * rb, qn[2] * rb, qn[3] * rb};
 #pragma unroll
-    for (int k = 0; k < 3; ++k) e.vc[k] = P.vc0[k] + dir[k] * (P.vc0_range * u[7]);
-    double theta_c = P.qc0_range * u[8];
-    unit_from_cube(u + 9, dir);
-    quat_from_axis_angle(dir, theta_c, qd);
-    quat_mul(qd, P.qc0, e.qc);
-    unit_from_cube(u + 12, dir);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) tmp[k] = P.wc0[k] + dir[k] * (P.wc0_range * u[15]);
-    Rot Rc = rot_from_quat(e.qc);
-    rot_apply_T(Rc, tmp, e.wc);
-    double theta_t = P.qt0_range * u[16];
-    unit_from_cube(u + 17, dir);
-    quat_from_axis_angle(dir, theta_t, qd);
-    quat_mul(qd, P.qt0, e.qt);
-    unit_from_cube(u + 20, dir);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) tmp[k] = P.wt0[k] + dir[k] * (P.wt0_range * u[23]);
-    Rot Rt = rot_from_quat(e.qt);
-    rot_apply_T(Rt, tmp, e.wt);
-    // collided = check_collision(); success = int(check_success())   (:260-261)
-    double rc_sq = dot3(e.rc, e.rc), rc_n = sqrt(rc_sq);
-    collided = collision_now(P, e, Rt, rc_sq, rc_n) ? 1 : 0;
-    success = 0;
-    if (!collided) {
-        ErrSq s = errors_sq(P, e, Rc, Rt);
-        double att = attitude_error(P, e, Rc, rc_sq);
-        success = (sqrt(s.pos) <= P.max_rd_error && sqrt(s.vel) <= P.max_vd_error && att <= P.max_qd_error &&
-                   sqrt(s.rot) <= P.max_wd_error) ? 1 : 0;
+            for (int k = 0; k < 4; ++k) qa[k] *= rq;
+            val[0] = qa[0] * qb[0] - (qa[1] * qb[1] + qa[2] * qb[2] + qa[3] * qb[3]);
+            val[1] = qa[0] * qb[1] + qb[0] * qa[1] + (qa[2] * qb[3] - qa[3] * qb[2]);
+            val[2] = qa[0] * qb[2] + qb[0] * qa[2] + (qa[3] * qb[1] - qa[1] * qb[3]);
+            val[3] = qa[0] * qb[3] + qb[0] * qa[3] + (qa[1] * qb[2] - qa[2] * qb[1]);
+        }
     }
-}
-
-RDV_DEV void draw_uniforms(uint64_t seed, int64_t env_id, int32_t episode, double (&u)[24])
-{
-#pragma unroll 1
-    for (uint32_t blk = 0; blk < 12; ++blk) {
-        double a, b;
-        philox_uniform_pair(seed, env_id, episode, blk, a, b);
-        // dynamic index into a register array would spill; select with predicated moves
+    // ---- phase 2: the quaternions go to the scratch row; the rate lanes rotate into their body frame ----
+    constexpr int OFF[6] = {RDV_RCX, RDV_VCX, RDV_QCW, RDV_WCX, RDV_QTW, RDV_WTX};
+    if (sub == 2 || sub == 4) {
+        const int o = sub == 2 ? RDV_QCW : RDV_QTW;
 #pragma unroll
-        for (int k = 0; k < 12; ++k)
-            if (k == (int)blk) { u[2 * k] = a; u[2 * k + 1] = b; }
+        for (int k = 0; k < 4; ++k) row[o + k] = val[k];
+    }
+    __syncwarp();
+    if (sub == 3 || sub == 5) {
+        const int o = sub == 3 ? RDV_QCW : RDV_QTW;
+        const double q[4] = {row[o], row[o + 1], row[o + 2], row[o + 3]};
+        const Rot R = rot_from_quat(q);
+        double w[3];
+        rot_apply_T(R, val, w);
+        val[0] = w[0]; val[1] = w[1]; val[2] = w[2];
+    }
+    if (sub == 0 || sub == 1 || sub == 3 || sub == 5) {
+        const int o = sub == 0 ? OFF[0] : sub == 1 ? OFF[1] : sub == 3 ? OFF[3] : OFF[5];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) row[o + k] = val[k];
+    }
+    __syncwarp();
+
+    // ---- phase 3: lane 0 -> flags and counters; lanes 1..7 -> state rows and the observation ----
+    if (sub == 0) {
+        EnvRegs e;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { e.rc[k] = row[RDV_RCX + k]; e.vc[k] = row[RDV_VCX + k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { e.qc[k] = row[RDV_QCW + k]; e.qt[k] = row[RDV_QTW + k]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { e.wc[k] = row[RDV_WCX + k]; e.wt[k] = row[RDV_WTX + k]; }
+        const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
+        // collided = check_collision(); success = int(check_success())   (:260-261)
+        const double rc_sq = dot3(e.rc, e.rc), rc_n = sqrt(rc_sq);
+        const int collided = collision_now(P, e, Rt, rc_sq, rc_n) ? 1 : 0;
+        int success = 0;
+        if (!collided) {
+            const ErrSq es = errors_sq(P, e, Rc, Rt);
+            const double att = attitude_error(P, e, Rc, rc_sq);
+            success = (sqrt(es.pos) <= P.max_rd_error && sqrt(es.vel) <= P.max_vd_error && att <= P.max_qd_error &&
+                       sqrt(es.rot) <= P.max_wd_error) ? 1 : 0;
+        }
+        if (valid) {
+            S.f64[RDV_TDV * ld + i] = 0.0; S.f64[RDV_TDW * ld + i] = 0.0; S.f64[RDV_EPRET * ld + i] = 0.0;
+            S.i32[RDV_I_STEP * ld + i] = 0; S.i32[RDV_I_SUCCESS * ld + i] = success;
+            S.i32[RDV_I_COLLIDED * ld + i] = collided; S.i32[RDV_I_EPISODE * ld + i] = episode;
+        }
+    } else if (valid) {
+        const ObsScale sc = obs_scale(P);
+        for (int k = sub - 1; k < RDV_TDV; k += RDV_TEAM - 1) {
+            const double x = row[k];
+            S.f64[k * ld + i] = x;
+            if (obs_row) {
+                // get_observation (:294-311): rc/20, vc/5, qc, wc/rad(10), qt; wt is not observed
+                if (k < RDV_QCW) {
+                    const bool pos = k < RDV_VCX;
+                    obs_row[k] = (float)fma(2.0 * (x + (pos ? sc.hi_r : sc.hi_v)), pos ? sc.inv_r : sc.inv_v, -1.0);
+                } else if (k < RDV_WCX) {
+                    obs_row[k] = (float)x;
+                } else if (k < RDV_QTW) {
+                    obs_row[k] = (float)fma(2.0 * (x + sc.hi_w), sc.inv_w, -1.0);
+                } else if (k < RDV_WTX) {
+                    obs_row[k] = (float)x;
+                }
+            }
+        }
     }
 }
 

@@ -181,8 +181,16 @@ RDV_DEV void attitude_rhs(const double *y, const double *hw_iso, const BodyConst
 // branch (ivp.py:710-728) evaluates the dense-output polynomial at x == 1, which equals y_new
 // up to ~1 ulp; y_new is used.  Returns accepted steps, or -1 on TOO_SMALL_STEP / non-finite
 // error norm (the reference raises there); y is left at the last accepted state.
+#ifndef RDV_RK_INLINE
+#define RDV_RK_INLINE 1
+#endif
+#if RDV_RK_INLINE
+#define RDV_RK_FN RDV_DEV
+#else
+#define RDV_RK_FN __device__ __noinline__
+#endif
 template <bool ISO>
-RDV_DEV int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b, int &n_rejected)
+RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b, int &n_rejected)
 {
     constexpr int NA = ISO ? 4 : 7;         // components with a non-zero derivative
     double hw[3] = {0.5 * y[4], 0.5 * y[5], 0.5 * y[6]};

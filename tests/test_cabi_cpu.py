@@ -92,15 +92,15 @@ def test_argument_validation_without_gpu(lib):
     buf = (C.c_double * 4096)()
     base = C.addressof(buf)
     st = N.RdvState(base, base, 2)
-    io = N.RdvStepIO(base, 1, 0, base, base, base, None, None, None, None, None)
+    io = N.RdvStepIO(base, 1, 0, base, base, base, None, None, None, None)
     assert lib.rdv_step(C.byref(p), C.byref(st), C.byref(io), 4, 0, 0, None) == -2           # ld < n
     assert lib.rdv_step(C.byref(p), C.byref(st), C.byref(io), -1, 0, 0, None) == -2
     st = N.RdvState(base + 4, base, 8)
     assert lib.rdv_step(C.byref(p), C.byref(st), C.byref(io), 4, 0, 0, None) == -3           # misaligned
     st = N.RdvState(base, base, 8)
     assert lib.rdv_step(C.byref(p), C.byref(st), C.byref(io), 0, 0, 0, None) == 0            # n = 0: no-op
-    io.auto_reset = 1
-    assert lib.rdv_step(C.byref(p), C.byref(st), C.byref(io), 4, 0, 0, None) == -1           # scratch missing
+    io.auto_reset = 7
+    assert lib.rdv_step(C.byref(p), C.byref(st), C.byref(io), 4, 0, 0, None) == -2           # bad enum value
     assert lib.rdv_policy_forward(None, None, None, 1, None) == -1
     assert lib.rdv_fp64_peak_probe(None, 1, 1, 1, None) == -1
     for code in range(0, -7, -1):
