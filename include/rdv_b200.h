@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 6
+#define RDV_ABI_VERSION 7
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -99,7 +99,13 @@ typedef struct RdvParams {
     float fuel_num_f32;            /* (float)(dt*fuel_coef)                                            */
     float fuel_den_f32;            /* (float)(3*max_delta_v)                                           */
     int32_t iso_c, iso_t;          /* 1: inertia = c*Identity and zero torque -> rate is constant      */
-    int32_t reserved1;
+    int32_t done_steps;            /* smallest step count k with round(k*dt, 3) >= t_max (:193, :369)   */
+    /* reciprocals / squares / products of the constants above, so the per-step path has no division */
+    double inv_max_attitude_error, inv_max_rd_error, inv_max_qd_error;
+    double koz_radius_sq, max_rd_error_sq, max_vd_error_sq, max_wd_error_sq;
+    double fuel_scale;             /* dt*fuel_coef / (3*max_delta_v)   (:333)                          */
+    double att_scale, bonus_scale, collision_scale;   /* dt*att_coef, dt*bonus_coef, dt*collision_coef  */
+    double obs_inv_r, obs_inv_v, obs_inv_w;           /* 1/(2*max_axial_distance), 1/(2*5), 1/(2*max_wc) */
 } RdvParams;
 
 /* Environment state: device pointers into caller-owned buffers. */

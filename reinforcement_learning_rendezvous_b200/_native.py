@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200
 SOURCES = ("rdv_b200.cu",)
 HEADERS = ("rdv_math.cuh", "rdv_env.cuh")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -61,7 +61,13 @@ class RdvParams(C.Structure):
         ("bubble0", C.c_double), ("bubble_rate", C.c_double), ("bubble_min", C.c_double), ("n", C.c_double),
         ("cw", C.c_double * 17),
         ("max_delta_v_f32", C.c_float), ("fuel_num_f32", C.c_float), ("fuel_den_f32", C.c_float),
-        ("iso_c", C.c_int32), ("iso_t", C.c_int32), ("reserved1", C.c_int32),
+        ("iso_c", C.c_int32), ("iso_t", C.c_int32), ("done_steps", C.c_int32),
+        ("inv_max_attitude_error", C.c_double), ("inv_max_rd_error", C.c_double), ("inv_max_qd_error", C.c_double),
+        ("koz_radius_sq", C.c_double), ("max_rd_error_sq", C.c_double), ("max_vd_error_sq", C.c_double),
+        ("max_wd_error_sq", C.c_double),
+        ("fuel_scale", C.c_double),
+        ("att_scale", C.c_double), ("bonus_scale", C.c_double), ("collision_scale", C.c_double),
+        ("obs_inv_r", C.c_double), ("obs_inv_v", C.c_double), ("obs_inv_w", C.c_double),
     ]
 
 

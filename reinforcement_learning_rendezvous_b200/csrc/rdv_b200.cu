@@ -90,6 +90,9 @@ RDV_DEV int pair_swap(int v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 // ~20 doubles per step through warp shuffles.  Finished envs are appended to reset_list (count in
 // reset_list[0]) for the compacted reset kernel below, so the rare reset path never diverges a stepping warp.
 // ---------------------------------------------------------------------------------
+#ifndef RDV_STEP_LAYOUT
+#define RDV_STEP_LAYOUT 2              // 1: thread per env (lock-step or sequential solves); 2: lane pair per env
+#endif
 #ifndef RDV_STEP_MIN_CTAS
 #define RDV_STEP_MIN_CTAS 4          // 4 CTAs x 4 warps = 16 resident warps per SM at <= 128 registers
 #endif
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
         const double sum = fabs(a0) + fabs(a1) + fabs(a2);
         act[0] = a0 * scale; act[1] = a1 * scale; act[2] = a2 * scale;
         total += sum * scale;
-        fuel = __ddiv_rn(P.dt * P.fuel_coef * sum, 3.0 * P.max_delta_v);
+        fuel = P.fuel_scale * sum;
     } else {
         // float32 actions follow NumPy-2 promotion: delta_v, total_delta_v and the
         // fuel term are rounded in fp32; delta_w and total_delta_w are fp64.
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
         for (int k = 0; k < 3; ++k) d[k] = got[k] - wl[k];     // wc_L - wt_L
         part2 = dot3(d, d);
         const double rc_sq = dot3(rc, rc);
-        if (sqrt(rc_sq) < P.koz_radius) {                      // check_collision (:388-404)
+        if (rc_sq < P.koz_radius_sq) {                         // check_collision (:388-404)
             rot_apply(R, P.corridor_axis, ax);
             const double th = rounded_angle_from(dot3(rc, ax), rc_sq, dot3(ax, ax));
             col_now = th > P.corridor_half_angle ? 1 : 0;
@@ -294,30 +297,29 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
         int step = S.i32[RDV_I_STEP * ld + i], success = S.i32[RDV_I_SUCCESS * ld + i];
         int collided = S.i32[RDV_I_COLLIDED * ld + i];
         double ep_ret = f[RDV_EPRET * ld];
-        const double att = part0, rc_n = sqrt(part1);
-        const double pos_err = sqrt(pos_sq);
-        // collision / success latch (:186-190)
+        const double att = part0, rc_sq = part1;
+        // collision / success latch (:186-190); the three vector errors are compared as squares
         if (!collided) {
             collided = col_t;
-            if (!collided && pos_err <= P.max_rd_error && sqrt(vel_sq) <= P.max_vd_error && att <= P.max_qd_error &&
-                sqrt(rot_sq) <= P.max_wd_error)
+            if (!collided && pos_sq <= P.max_rd_error_sq && vel_sq <= P.max_vd_error_sq && att <= P.max_qd_error &&
+                rot_sq <= P.max_wd_error_sq)
                 success += 1;
         }
         // time and bubble (:193-198), derived from the step counter
         step += 1;
-        const double t = __ddiv_rn(rint((double)step * P.dt * 1000.0), 1000.0);
         const double bubble = fmax(fma(-(double)step, P.bubble_rate, P.bubble0), P.bubble_min);
         // done (:355-386): first true condition is the end reason
-        const bool c0 = !(in_box && box_t), c1 = t >= P.t_max, c2 = rc_n > bubble, c3 = att > P.max_attitude_error;
+        const bool c0 = !(in_box && box_t), c1 = step >= P.done_steps, c2 = rc_sq > bubble * bubble,
+                   c3 = att > P.max_attitude_error;
         done = (c0 || c1 || c2 || c3) ? 1 : 0;
         const int reason = c0 ? 0 : c1 ? 1 : c2 ? 2 : c3 ? 3 : -1;
         // reward (:313-353)
-        double rew = (P.dt * P.att_coef) * (1.0 - __ddiv_rn(att, P.max_attitude_error));
+        double rew = P.att_scale * fma(-att, P.inv_max_attitude_error, 1.0);
         rew += fuel_t;
-        if (col_t) rew -= P.dt * P.collision_coef;
-        if (rc_n < P.koz_radius && !collided && pos_err < P.max_rd_error) {
-            rew += P.dt * P.bonus_coef * (2.0 - __ddiv_rn(pos_err, P.max_rd_error));
-            if (att < P.max_qd_error) rew += P.dt * P.bonus_coef * (2.0 - __ddiv_rn(att, P.max_qd_error));
+        if (col_t) rew -= P.collision_scale;
+        if (rc_sq < P.koz_radius_sq && !collided && pos_sq < P.max_rd_error_sq) {
+            rew += P.bonus_scale * fma(-fast_sqrt(pos_sq), P.inv_max_rd_error, 2.0);
+            if (att < P.max_qd_error) rew += P.bonus_scale * fma(-att, P.inv_max_qd_error, 2.0);
         }
         ep_ret += rew;
         if (active) {
@@ -360,6 +362,8 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
     if (io.auto_reset) {
         const int count = s_reset_n, team = threadIdx.x / RDV_TEAM;
         for (int b = 0; b < count; b += TPB / RDV_TEAM) {
+            // the list is dense, so whole warps (4 teams each) drop out as soon as their first team is past it
+            if (b + (team & ~3) >= count) break;
             const bool valid = b + team < count;
             const int local = valid ? s_reset_idx[b + team] : 0;
             const int64_t ie = base + local < n ? base + local : n - 1;
@@ -380,6 +384,221 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
         for (int k = (nvec << 2) + threadIdx.x; k < total_f; k += TPB) dst[k] = s_obs[k];
     }
     if (io.stats) reduce_stats<TPB / 32>(st, io.stats, s_stats);
+}
+
+// ---------------------------------------------------------------------------------
+// step kernel, layout 1: ONE thread per environment; the chaser and target RK45 solves advance in
+// lock-step inside the thread (rk45_attitude_pair), which doubles the instruction-level parallelism of
+// the dependent fp64 chains without the shuffle / duplicated-work overhead of the lane-pair layout.
+// ---------------------------------------------------------------------------------
+#ifndef RDV_STEP1_MIN_CTAS
+#define RDV_STEP1_MIN_CTAS 4
+#endif
+#ifndef RDV_LOCKSTEP
+#define RDV_LOCKSTEP 1
+#endif
+constexpr int TPB1 = 64;
+
+template <bool ISO, bool ACT_F64, bool CLOSED>
+__global__ void __launch_bounds__(TPB1, RDV_STEP1_MIN_CTAS) step_kernel_env(const __grid_constant__ RdvParams P, const RdvState S,
+                                                   const RdvStepIO io, const int64_t n, const uint64_t seed,
+                                                   const int64_t env_offset)
+{
+    __shared__ __align__(16) float s_obs[TPB1 * RDV_OBS_DIM];
+    __shared__ double s_stats[TPB1 / 32][RDV_NSTATS];
+    __shared__ double s_team[TPB1 / RDV_TEAM][RDV_TEAM_ROW];  // scratch rows of the reset teams
+    __shared__ int s_reset_idx[TPB1];                         // envs of this CTA whose episode just ended
+    __shared__ int s_reset_n;
+    if (threadIdx.x == 0) s_reset_n = 0;
+    __syncthreads();
+
+    const int64_t base = (int64_t)blockIdx.x * TPB1;
+    const int64_t i = base + threadIdx.x;
+    const bool active = i < n;
+    StepStats st = {};
+
+    if (active) {
+        EnvRegs e;
+        load_env(S, i, e);
+        const int64_t ld = S.ld;
+        double tdv = S.f64[RDV_TDV * ld + i], tdw = S.f64[RDV_TDW * ld + i], ep_ret = S.f64[RDV_EPRET * ld + i];
+        int step = S.i32[RDV_I_STEP * ld + i], success = S.i32[RDV_I_SUCCESS * ld + i];
+        int collided = S.i32[RDV_I_COLLIDED * ld + i];
+
+        // ---- action ingest (:168-173, :201-202, :333) ----
+        double dvb[3], dw[3], fuel;
+        if (ACT_F64) {
+            const double2 *ap = reinterpret_cast<const double2 *>(static_cast<const double *>(io.actions) + 6 * i);
+            double2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
+            dvb[0] = a01.x * P.max_delta_v; dvb[1] = a01.y * P.max_delta_v; dvb[2] = a23.x * P.max_delta_v;
+            dw[0] = a23.y * P.max_delta_w; dw[1] = a45.x * P.max_delta_w; dw[2] = a45.y * P.max_delta_w;
+            double sv = fabs(a01.x) + fabs(a01.y) + fabs(a23.x);
+            double sw = fabs(a23.y) + fabs(a45.x) + fabs(a45.y);
+            tdv += sv * P.max_delta_v;
+            tdw += sw * P.max_delta_w;
+            fuel = P.fuel_scale * sv;
+        } else {
+            // float32 actions follow NumPy-2 promotion: delta_v, total_delta_v
+            // and the fuel term are rounded in fp32; delta_w and total_delta_w are fp64.
+            const float2 *ap = reinterpret_cast<const float2 *>(static_cast<const float *>(io.actions) + 6 * i);
+            float2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
+            dvb[0] = (double)__fmul_rn(a01.x, P.max_delta_v_f32);
+            dvb[1] = (double)__fmul_rn(a01.y, P.max_delta_v_f32);
+            dvb[2] = (double)__fmul_rn(a23.x, P.max_delta_v_f32);
+            dw[0] = (double)a23.y * P.max_delta_w; dw[1] = (double)a45.x * P.max_delta_w;
+            dw[2] = (double)a45.y * P.max_delta_w;
+            float sv = __fadd_rn(__fadd_rn(fabsf(a01.x), fabsf(a01.y)), fabsf(a23.x));
+            float sw = __fadd_rn(__fadd_rn(fabsf(a23.y), fabsf(a45.x)), fabsf(a45.y));
+            tdv = (double)__fadd_rn((float)tdv, __fmul_rn(sv, P.max_delta_v_f32));
+            tdw += (double)sw * P.max_delta_w;
+            fuel = (double)__fdiv_rn(__fmul_rn(P.fuel_num_f32, sv), P.fuel_den_f32);
+        }
+
+        // ---- translation: impulse in LVLH, then the CW transition (:172-177, dynamics.py:24-55) ----
+        {
+            Rot Rc_old = rot_from_quat(e.qc);
+            double dv[3];
+            rot_apply(Rc_old, dvb, dv);
+            double r0 = e.rc[0], r1 = e.rc[1], r2 = e.rc[2];
+            double v0 = e.vc[0] + dv[0], v1 = e.vc[1] + dv[1], v2 = e.vc[2] + dv[2];
+            const double *c = P.cw;
+            e.rc[0] = fma(c[2], v1, fma(c[1], v0, c[0] * r0));
+            e.rc[1] = fma(c[6], v1, fma(c[5], v0, fma(c[3], r0, c[4] * r1)));
+            e.rc[2] = fma(c[8], v2, c[7] * r2);
+            e.vc[0] = fma(c[11], v1, fma(c[10], v0, c[9] * r0));
+            e.vc[1] = fma(c[14], v1, fma(c[13], v0, c[12] * r0));
+            e.vc[2] = fma(c[16], v2, c[15] * r2);
+        }
+
+        // ---- attitude: impulsive rate change, then torque-free propagation of both bodies (:180-184) ----
+        int rk_acc = 0, rk_rej = 0, fail = 0;
+        {
+            double y[7] = {e.qc[0], e.qc[1], e.qc[2], e.qc[3], e.wc[0] + dw[0], e.wc[1] + dw[1], e.wc[2] + dw[2]};
+            double z[7] = {e.qt[0], e.qt[1], e.qt[2], e.qt[3], e.wt[0], e.wt[1], e.wt[2]};
+            if (CLOSED) {
+                closed_form_attitude(y, P.dt);
+                closed_form_attitude(z, P.dt);
+            } else {
+                BodyConst bc, bt;
+                bc.I = P.inertia_c; bc.Iinv = P.inv_inertia_c; bc.tau = P.torque_c;
+                bt.I = P.inertia_t; bt.Iinv = P.inv_inertia_t; bt.tau = c_zero3;
+                if (ISO && RDV_LOCKSTEP) {
+                    const int k = rk45_attitude_pair<true>(y, z, P.dt, bc, bt, rk_rej);   // both solves in lock-step
+                    if (k < 0) fail = 1; else rk_acc = k;
+                } else if (ISO) {
+                    // one solve after the other through a single copy of the solver code (bounded registers)
+#pragma unroll 1
+                    for (int body = 0; body < 2; ++body) {
+                        const int k = rk45_attitude<true>(y, P.dt, bc, rk_rej);
+                        if (k < 0) fail = 1; else rk_acc += k;
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) { const double t = y[j]; y[j] = z[j]; z[j] = t; }
+                    }
+                } else {
+                    const int kc = rk45_attitude<false>(y, P.dt, bc, rk_rej);
+                    const int kt = rk45_attitude<false>(z, P.dt, bt, rk_rej);
+                    if (kc < 0 || kt < 0) fail = 1; else rk_acc = kc + kt;
+                }
+            }
+            const double ry = fast_rsqrt(dot4(y, y)), rz = fast_rsqrt(dot4(z, z));   // q / |q|  (:574-575, :601-602)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { e.qc[k] = y[k] * ry; e.qt[k] = z[k] * rz; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { e.wc[k] = y[4 + k]; e.wt[k] = z[4 + k]; }
+        }
+
+        // ---- collision / success latch (:186-190) ----
+        const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
+        const double rc_sq = dot3(e.rc, e.rc);
+        const double att = attitude_error(P, e, Rc, rc_sq);
+        const bool col_now = rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle;
+        ErrSq es = errors_sq(P, e, Rc, Rt);
+        if (!collided) {
+            collided = col_now ? 1 : 0;
+            if (!collided && es.pos <= P.max_rd_error_sq && es.vel <= P.max_vd_error_sq && att <= P.max_qd_error &&
+                es.rot <= P.max_wd_error_sq)
+                success += 1;
+        }
+        // ---- time and bubble (:193-198), derived from the step counter ----
+        step += 1;
+        const double bubble = fmax(fma(-(double)step, P.bubble_rate, P.bubble0), P.bubble_min);
+
+        // ---- observation (:205) into the shared staging row ----
+        float *o = s_obs + threadIdx.x * RDV_OBS_DIM;
+        float ov[RDV_OBS_DIM];
+        make_obs(e, obs_scale(P), ov);
+#pragma unroll
+        for (int k = 0; k < RDV_OBS_DIM; ++k) o[k] = ov[k];
+
+        // ---- done (:355-386): first true condition is the end reason ----
+        const bool c0 = !obs_in_box(ov), c1 = step >= P.done_steps, c2 = rc_sq > bubble * bubble,
+                   c3 = att > P.max_attitude_error;
+        const bool done = c0 || c1 || c2 || c3;
+        const int reason = c0 ? 0 : c1 ? 1 : c2 ? 2 : c3 ? 3 : -1;
+
+        // ---- reward (:313-353) ----
+        double rew = P.att_scale * fma(-att, P.inv_max_attitude_error, 1.0);
+        rew += fuel;
+        if (col_now) rew -= P.collision_scale;
+        if (rc_sq < P.koz_radius_sq && !collided && es.pos < P.max_rd_error_sq) {
+            rew += P.bonus_scale * fma(-fast_sqrt(es.pos), P.inv_max_rd_error, 2.0);
+            if (att < P.max_qd_error) rew += P.bonus_scale * fma(-att, P.inv_max_qd_error, 2.0);
+        }
+        ep_ret += rew;
+
+        // ---- outputs ----
+        io.reward[i] = rew;
+        io.done[i] = done ? 1 : 0;
+        if (io.end_reason) io.end_reason[i] = (int8_t)reason;
+        st.steps = 1; st.reward = rew; st.rk_acc = rk_acc; st.rk_rej = rk_rej; st.fail = fail;
+        if (done) {
+            st.episodes = 1; st.succeeded = success > 0; st.collided = collided;
+            st.end0 = reason == 0; st.end1 = reason == 1; st.end2 = reason == 2; st.end3 = reason == 3;
+            st.ep_return = ep_ret; st.ep_length = (double)step; st.delta_v = tdv; st.delta_w = tdw;
+            if (io.episode_record) {
+                double *rec = io.episode_record + RDV_EP_NCOL * i;
+                rec[RDV_EP_RETURN] = ep_ret; rec[RDV_EP_LENGTH] = (double)step; rec[RDV_EP_SUCCESS] = (double)success;
+                rec[RDV_EP_COLLIDED] = (double)collided; rec[RDV_EP_DELTA_V] = tdv; rec[RDV_EP_DELTA_W] = tdw;
+            }
+            if (io.terminal_obs) {
+                float *to = io.terminal_obs + RDV_OBS_DIM * i;
+#pragma unroll
+                for (int k = 0; k < RDV_OBS_DIM; ++k) to[k] = ov[k];
+            }
+            if (io.auto_reset) s_reset_idx[atomicAdd(&s_reset_n, 1)] = threadIdx.x;
+        }
+        store_env(S, i, e);
+        S.f64[RDV_TDV * ld + i] = tdv; S.f64[RDV_TDW * ld + i] = tdw; S.f64[RDV_EPRET * ld + i] = ep_ret;
+        S.i32[RDV_I_STEP * ld + i] = step; S.i32[RDV_I_SUCCESS * ld + i] = success;
+        S.i32[RDV_I_COLLIDED * ld + i] = collided;
+    }
+
+    // ---- auto-reset by teams of 8 lanes (see step_kernel) ----
+    __syncthreads();
+    if (io.auto_reset) {
+        const int count = s_reset_n, team = threadIdx.x / RDV_TEAM;
+        for (int b = 0; b < count; b += TPB1 / RDV_TEAM) {
+            if (b + (team & ~3) >= count) break;
+            const bool valid = b + team < count;
+            const int local = valid ? s_reset_idx[b + team] : 0;
+            const int64_t ie = base + local < n ? base + local : n - 1;
+            team_reset(P, S, seed, env_offset + ie, ie, valid, 1, nullptr, s_team[team], s_obs + local * RDV_OBS_DIM);
+        }
+        __syncthreads();
+    }
+
+    // ---- coalesced observation write-out: the CTA's rows are contiguous in obs[n][17] ----
+    {
+        const int64_t rows = (n - base) < TPB1 ? (n - base) : TPB1;
+        const int total = (int)rows * RDV_OBS_DIM;
+        float *dst = io.obs + base * RDV_OBS_DIM;              // base*17*4 B is a multiple of 16 (TPB1 = 64)
+        const int nvec = total >> 2;
+        const float4 *src4 = reinterpret_cast<const float4 *>(s_obs);
+        float4 *dst4 = reinterpret_cast<float4 *>(dst);
+        for (int k = threadIdx.x; k < nvec; k += TPB1) dst4[k] = src4[k];
+        for (int k = (nvec << 2) + threadIdx.x; k < total; k += TPB1) dst[k] = s_obs[k];
+    }
+    if (io.stats) reduce_stats<TPB1 / 32>(st, io.stats, s_stats);
 }
 
 // ---------------------------------------------------------------------------------
@@ -422,7 +641,7 @@ __global__ void __launch_bounds__(128) errors_kernel(const __grid_constant__ Rdv
     EnvRegs e;
     load_env(S, i, e);
     const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
-    const double rc_sq = dot3(e.rc, e.rc), rc_n = sqrt(rc_sq);
+    const double rc_sq = dot3(e.rc, e.rc), rc_n = sqrt(rc_sq);      // evaluator path: IEEE sqrt, values are returned
     const double att = attitude_error(P, e, Rc, rc_sq);
     const double th = corridor_angle(P, e, Rt, rc_sq);
     const bool col = rc_n < P.koz_radius && th > P.corridor_half_angle;
@@ -641,6 +860,27 @@ int rdv_params_derive(RdvParams *p)
     p->max_delta_v_f32 = (float)p->max_delta_v;
     p->fuel_num_f32 = (float)(p->dt * p->fuel_coef);
     p->fuel_den_f32 = (float)(3 * p->max_delta_v);
+    p->inv_max_attitude_error = 1.0 / p->max_attitude_error;
+    p->inv_max_rd_error = 1.0 / p->max_rd_error;
+    p->inv_max_qd_error = 1.0 / p->max_qd_error;
+    p->koz_radius_sq = p->koz_radius * p->koz_radius;
+    p->max_rd_error_sq = p->max_rd_error * p->max_rd_error;
+    p->max_vd_error_sq = p->max_vd_error * p->max_vd_error;
+    p->max_wd_error_sq = p->max_wd_error * p->max_wd_error;
+    p->fuel_scale = p->dt * p->fuel_coef / (3 * p->max_delta_v);
+    p->att_scale = p->dt * p->att_coef;
+    p->bonus_scale = p->dt * p->bonus_coef;
+    p->collision_scale = p->dt * p->collision_coef;
+    p->obs_inv_r = 1.0 / (2.0 * p->max_axial_distance);
+    p->obs_inv_v = 1.0 / (2.0 * p->max_axial_speed);
+    p->obs_inv_w = 1.0 / (2.0 * p->max_wc);
+    {   // first step count whose time stamp t = round(k*dt, 3) reaches t_max (:193, :369)
+        double k = ceil(p->t_max / p->dt) - 2.0;
+        if (k < 1.0) k = 1.0;
+        while (rint(k * p->dt * 1000.0) / 1000.0 < p->t_max) k += 1.0;
+        if (k > 2147483647.0) return RDV_ERR_PARAMS;
+        p->done_steps = (int32_t)k;
+    }
     p->iso_c = is_isotropic(p->inertia_c, p->torque_c);
     p->iso_t = is_isotropic(p->inertia_t, nullptr);
     if (p->integrator != RDV_INTEGRATOR_RK45 && p->integrator != RDV_INTEGRATOR_CLOSED_FORM) return RDV_ERR_SIZE;
@@ -662,8 +902,14 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
     const bool iso = p->iso_c && p->iso_t;
     const bool closed = p->integrator == RDV_INTEGRATOR_CLOSED_FORM;
     if (io->auto_reset != 0 && io->auto_reset != 1) return RDV_ERR_SIZE;
+#if RDV_STEP_LAYOUT == 1
+    const unsigned grid1 = (unsigned)((n + TPB1 - 1) / TPB1);
+#define RDV_LAUNCH(ISO_, F64_, CL_) \
+    step_kernel_env<ISO_, F64_, CL_><<<grid1, TPB1, 0, st>>>(*p, *s, *io, n, seed, env_offset)
+#else
 #define RDV_LAUNCH(ISO_, F64_, CL_) \
     step_kernel<ISO_, F64_, CL_><<<grid, TPB, 0, st>>>(*p, *s, *io, n, seed, env_offset)
+#endif
     if (closed) { if (io->act_f64) RDV_LAUNCH(true, true, true); else RDV_LAUNCH(true, false, true); }
     else if (iso) { if (io->act_f64) RDV_LAUNCH(true, true, false); else RDV_LAUNCH(true, false, false); }
     else { if (io->act_f64) RDV_LAUNCH(false, true, false); else RDV_LAUNCH(false, false, false); }

@@ -51,9 +51,9 @@ struct ObsScale { double hi_r, inv_r, hi_v, inv_v, hi_w, inv_w; };
 RDV_DEV ObsScale obs_scale(const RdvParams &P)
 {
     ObsScale s;
-    s.hi_r = P.max_axial_distance; s.inv_r = 1.0 / (2.0 * P.max_axial_distance);
-    s.hi_v = P.max_axial_speed;    s.inv_v = 1.0 / (2.0 * P.max_axial_speed);
-    s.hi_w = P.max_wc;             s.inv_w = 1.0 / (2.0 * P.max_wc);
+    s.hi_r = P.max_axial_distance; s.inv_r = P.obs_inv_r;
+    s.hi_v = P.max_axial_speed;    s.inv_v = P.obs_inv_v;
+    s.hi_w = P.max_wc;             s.inv_w = P.obs_inv_w;
     return s;
 }
 RDV_DEV void make_obs(const EnvRegs &e, const ObsScale &s, float *o /* stride 1 */)
@@ -233,14 +233,13 @@ RDV_DEV void team_reset(const RdvParams &P, const RdvState &S, uint64_t seed, in
         for (int k = 0; k < 3; ++k) { e.wc[k] = row[RDV_WCX + k]; e.wt[k] = row[RDV_WTX + k]; }
         const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
         // collided = check_collision(); success = int(check_success())   (:260-261)
-        const double rc_sq = dot3(e.rc, e.rc), rc_n = sqrt(rc_sq);
-        const int collided = collision_now(P, e, Rt, rc_sq, rc_n) ? 1 : 0;
+        const double rc_sq = dot3(e.rc, e.rc);
+        const int collided = (rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle) ? 1 : 0;
         int success = 0;
         if (!collided) {
             const ErrSq es = errors_sq(P, e, Rc, Rt);
-            const double att = attitude_error(P, e, Rc, rc_sq);
-            success = (sqrt(es.pos) <= P.max_rd_error && sqrt(es.vel) <= P.max_vd_error && att <= P.max_qd_error &&
-                       sqrt(es.rot) <= P.max_wd_error) ? 1 : 0;
+            if (es.pos <= P.max_rd_error_sq && es.vel <= P.max_vd_error_sq && es.rot <= P.max_wd_error_sq)
+                success = attitude_error(P, e, Rc, rc_sq) <= P.max_qd_error ? 1 : 0;
         }
         if (valid) {
             S.f64[RDV_TDV * ld + i] = 0.0; S.f64[RDV_TDW * ld + i] = 0.0; S.f64[RDV_EPRET * ld + i] = 0.0;

@@ -102,12 +102,18 @@ RDV_DEV void rot_apply_T(const Rot &R, const double v[3], double o[3])          
     for (int i = 0; i < 3; ++i) o[i] = fma(R.m[6 + i], v[2], fma(R.m[3 + i], v[1], R.m[i] * v[0]));
 }
 
+// sqrt(x) for x >= 0 (<= 1 ulp): x * rsqrt(x)
+RDV_DEV double fast_sqrt(double x) { return x > 0.0 ? x * fast_rsqrt(x) : 0.0; }
+
 // angle_between_vectors (utils/general.py:163-181): acos(round(cos, 5)), with numpy's
-// round == rint(x*1e5)/1e5.  The final division is IEEE so that +-1 stay exactly +-1.
+// round == rint(x*1e5)/1e5.  k/1e5 is formed as k*1e-5 plus one Markstein correction step, which equals the
+// IEEE quotient for every integer |k| <= 1e5 (checked exhaustively) -- in particular +-1 stay exactly +-1.
 RDV_DEV double rounded_angle_from(double dot, double n1sq, double n2sq)
 {
-    double c = dot * fast_rsqrt(n1sq * n2sq);
-    return acos(__ddiv_rn(rint(c * 1e5), 1e5));
+    const double c = dot * fast_rsqrt(n1sq * n2sq);
+    const double k = rint(c * 1e5);
+    const double x0 = k * 1e-5;
+    return acos(fma(fma(-x0, 1e5, k), 1e-5, x0));
 }
 
 // ---------------------------------------------------------------------------------
@@ -316,6 +322,175 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
         for (int i = 0; i < NA; ++i) { y[i] = y_new[i]; K[0][i] = K[6][i]; }
         if (t - dt >= 0.0) return accepted;
     }
+}
+
+// ---------------------------------------------------------------------------------
+// Lock-step form of the same solver for TWO bodies in one thread (chaser and target of one env).
+//
+// rk45_attitude above is a chain of dependent fp64 operations with at most NA-way instruction-level
+// parallelism, and one thread can keep only a fraction of the fp64 pipe busy with it.  Here every
+// phase (initial step, one attempted Dormand-Prince step, error control) is written branch-free for one
+// body and issued for both bodies back to back, so the two independent dependency chains interleave in
+// the instruction stream (2x ILP at no extra instructions).  The control flow of scipy's _step_impl
+// (accept / reject, the factor clamps, the rejected-step rule, TOO_SMALL_STEP) becomes predicated
+// updates; a body that has reached t = dt keeps stepping in the shadow without committing anything.
+// Arithmetic per body is identical to rk45_attitude, operation for operation.
+// ---------------------------------------------------------------------------------
+RDV_DEV double pow_neg_tenth_nb(double x)           // branch-free; x is clamped to [1e-30, 1e30]
+{
+    x = fmin(fmax(x, 1e-30), 1e30);
+    const float lf = __log2f((float)x);
+    double y = (double)exp2f(-0.1f * lf);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4, y10 = y8 * y2;
+        y = fma(y * 0.1, fma(-x, y10, 1.0), y);
+    }
+    return y;
+}
+
+template <bool ISO>
+struct RkBody {
+    static constexpr int NA = ISO ? 4 : 7;
+    double y[7], hw[3], k0[NA];
+    double h_abs, t;
+    int accepted;
+    bool done, rejected, failed;
+};
+
+template <bool ISO>
+RDV_DEV void rk_begin(RkBody<ISO> &s, const double dt, const BodyConst &b)
+{
+    constexpr int NA = RkBody<ISO>::NA;
+    s.hw[0] = 0.5 * s.y[4]; s.hw[1] = 0.5 * s.y[5]; s.hw[2] = 0.5 * s.y[6];
+    attitude_rhs<ISO>(s.y, s.hw, b, s.k0);
+    // select_initial_step (scipy common.py:68-134), order 4
+    double inv_sc[7], d0s = 0.0, d1s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        inv_sc[i] = fast_rcp(fma(fabs(s.y[i]), RK_RTOL, RK_ATOL));
+        const double a = s.y[i] * inv_sc[i];
+        d0s = fma(a, a, d0s);
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const double a = s.k0[i] * inv_sc[i];
+        d1s = fma(a, a, d1s);
+    }
+    d0s *= (1.0 / 7.0);
+    d1s *= (1.0 / 7.0);
+    const bool tiny = d0s < 1e-10 || d1s < 1e-10;
+    const double ratio = d0s * fast_rcp(tiny ? 1.0 : d1s);
+    double h0 = tiny ? 1e-6 : 0.01 * (ratio * fast_rsqrt(ratio));
+    h0 = fmin(h0, dt);
+    double y1[7], f1[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) y1[i] = fma(h0, s.k0[i], s.y[i]);
+#pragma unroll
+    for (int i = NA; i < 7; ++i) y1[i] = s.y[i];
+    attitude_rhs<ISO>(y1, s.hw, b, f1);
+    double d2s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const double a = (f1[i] - s.k0[i]) * inv_sc[i];
+        d2s = fma(a, a, d2s);
+    }
+    const double inv_h0 = fast_rcp(h0);
+    d2s = d2s * (1.0 / 7.0) * inv_h0 * inv_h0;
+    const double h1 = (d1s <= 1e-30 && d2s <= 1e-30) ? fmax(1e-6, h0 * 1e-3) : pow_neg_tenth_nb(fmax(d1s, d2s) * 1e4);
+    s.h_abs = fmin(fmin(100.0 * h0, h1), dt);
+    s.t = 0.0;
+    s.accepted = 0;
+    s.done = s.rejected = s.failed = false;
+}
+
+// One iteration of the inner loop of _step_impl (scipy rk.py:111-179) with predicated commit.
+template <bool ISO>
+RDV_DEV void rk_attempt(RkBody<ISO> &s, const double dt, const BodyConst &b, int &n_rejected)
+{
+    constexpr int NA = RkBody<ISO>::NA;
+    const bool live = !s.done && !s.failed;
+    const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(s.t) + 1) - s.t);
+    bool failed = s.rejected && s.h_abs < min_step;               // TOO_SMALL_STEP after a rejection
+    double h_abs = s.rejected ? s.h_abs : fmax(s.h_abs, min_step);
+    double t_new = s.t + h_abs;
+    if (t_new - dt > 0.0) t_new = dt;
+    const double h = t_new - s.t;
+    h_abs = fabs(h);
+    double K1[NA], K2[NA], K3[NA], K4[NA], K5[NA], K6[NA], ys[7];
+    const double *K0 = s.k0, *y = s.y;
+    if (ISO) { ys[4] = y[4]; ys[5] = y[5]; ys[6] = y[6]; }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) ys[i] = fma(K0[i] * RK_A21, h, y[i]);
+    attitude_rhs<ISO>(ys, s.hw, b, K1);
+#pragma unroll
+    for (int i = 0; i < NA; ++i) ys[i] = fma(fma(K1[i], RK_A32, K0[i] * RK_A31), h, y[i]);
+    attitude_rhs<ISO>(ys, s.hw, b, K2);
+#pragma unroll
+    for (int i = 0; i < NA; ++i) ys[i] = fma(fma(K2[i], RK_A43, fma(K1[i], RK_A42, K0[i] * RK_A41)), h, y[i]);
+    attitude_rhs<ISO>(ys, s.hw, b, K3);
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+        ys[i] = fma(fma(K3[i], RK_A54, fma(K2[i], RK_A53, fma(K1[i], RK_A52, K0[i] * RK_A51))), h, y[i]);
+    attitude_rhs<ISO>(ys, s.hw, b, K4);
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+        ys[i] = fma(fma(K4[i], RK_A65, fma(K3[i], RK_A64, fma(K2[i], RK_A63, fma(K1[i], RK_A62, K0[i] * RK_A61)))), h,
+                    y[i]);
+    attitude_rhs<ISO>(ys, s.hw, b, K5);
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+        ys[i] = fma(h, fma(K5[i], RK_B6, fma(K4[i], RK_B5, fma(K3[i], RK_B4, fma(K2[i], RK_B3, K0[i] * RK_B1)))), y[i]);
+    attitude_rhs<ISO>(ys, s.hw, b, K6);                            // FSAL row; ys is y_new
+    double es = 0.0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        double e = fma(K6[i], RK_E7,
+                       fma(K5[i], RK_E6, fma(K4[i], RK_E5, fma(K3[i], RK_E4, fma(K2[i], RK_E3, K0[i] * RK_E1)))));
+        const double sc = fma(fmax(fabs(y[i]), fabs(ys[i])), RK_RTOL, RK_ATOL);
+        e = e * h * fast_rcp(sc);
+        es = fma(e, e, es);
+    }
+    es *= (1.0 / 7.0);                                             // err_norm^2
+    failed = failed || !(es < 1.0e300);                            // NaN / inf: the reference shrinks h to failure
+    const bool accept = es < 1.0;
+    // 0.9 err^-0.2, clamped where the min/max of the controller saturate anyway (10 below 3.5e-11, 0.2 above 1e7)
+    const double p = 0.9 * pow_neg_tenth_nb(fmin(fmax(es, 1e-12), 1e8));
+    double factor = accept ? fmin(10.0, p) : fmax(0.2, p);
+    if (accept && s.rejected) factor = fmin(1.0, factor);
+    const bool commit = live && !failed && accept;
+    if (live) {
+        s.failed = failed;
+        s.h_abs = failed ? s.h_abs : h_abs * factor;
+        s.rejected = !accept;
+        n_rejected += (!failed && !accept) ? 1 : 0;
+    }
+    if (commit) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) { s.y[i] = ys[i]; s.k0[i] = K6[i]; }
+        s.t = t_new;
+        s.accepted += 1;
+        s.done = t_new - dt >= 0.0;
+    }
+}
+
+// Both attitude solves of one env step.  Returns accepted steps of both bodies, or -1 on failure.
+template <bool ISO>
+RDV_DEV int rk45_attitude_pair(double (&ya)[7], double (&yb)[7], const double dt, const BodyConst &ba,
+                               const BodyConst &bb, int &n_rejected)
+{
+    RkBody<ISO> A, B;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { A.y[i] = ya[i]; B.y[i] = yb[i]; }
+    rk_begin<ISO>(A, dt, ba);
+    rk_begin<ISO>(B, dt, bb);
+    while (!((A.done || A.failed) && (B.done || B.failed))) {
+        rk_attempt<ISO>(A, dt, ba, n_rejected);
+        rk_attempt<ISO>(B, dt, bb, n_rejected);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { ya[i] = A.y[i]; yb[i] = B.y[i]; }
+    return (A.failed || B.failed) ? -1 : A.accepted + B.accepted;
 }
 
 // Closed-form alternative (opt-in, RDV_INTEGRATOR_CLOSED_FORM; only valid for ISO bodies):
