@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 7
+#define RDV_ABI_VERSION 8
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -149,6 +149,29 @@ int  rdv_params_derive(RdvParams *p);
  * of env 0 of this shard (Philox key for resets). */
 int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t n,
              uint64_t seed, int64_t env_offset, void *cuda_stream);
+
+/* K consecutive steps of every env in one launch (state stays in registers; finished envs are reset in
+ * place).  This is the rollout-collection loop of SB3's collect_rollouts around env.step
+ * (main.py:114 -> OnPolicyAlgorithm.collect_rollouts) with the action taken from `actions` or drawn on the
+ * device.  The per-step results a rollout buffer needs are optional outputs. */
+enum { RDV_ACTIONS_F32 = 0, RDV_ACTIONS_F64 = 1, RDV_ACTIONS_PHILOX = 2 };
+typedef struct RdvRolloutIO {
+    int32_t  steps;          /* K                                                                          */
+    int32_t  action_source;  /* RDV_ACTIONS_*                                                              */
+    int32_t  auto_reset;     /* 1: VecEnv semantics (finished envs restart inside the launch)              */
+    int32_t  reserved;
+    const void *actions;     /* [K][n][6] float32 / float64 for the tensor sources                         */
+    uint64_t action_seed;    /* RDV_ACTIONS_PHILOX: U(-1,1) fp64 actions from Philox(action_seed; global   */
+    int64_t  step_base;      /*   env id, step_base + k): 6 draws per env-step                             */
+    double  *actions_out;    /* nullable [K][n][6]: the Philox actions that were applied                   */
+    float   *obs;            /* [n][17] observation after the last step (post-reset for finished envs)     */
+    double  *rewards;        /* nullable [K][n]                                                            */
+    uint8_t *dones;          /* nullable [K][n]                                                            */
+    float   *obs_steps;      /* nullable [K][n][17] observation returned by every step                     */
+    double  *stats;          /* nullable [RDV_NSTATS] device accumulator                                   */
+} RdvRolloutIO;
+int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, int64_t n, uint64_t seed,
+                int64_t env_offset, void *cuda_stream);
 
 /* RendezvousEnv.reset (rendezvous_env.py:223-270) for the envs selected by mask (NULL = all).
  * The 24 uniform draws come from Philox4x32-10 keyed by (seed; env_offset+i, episode index),

@@ -60,6 +60,8 @@ def lib():
         assert _lib.orc_sizeof_params() == C.sizeof(OrcParams), "OrcParams layout mismatch"
         _lib.orc_philox_uniforms.argtypes = [C.c_uint64, C.c_int64, C.c_int32, C.c_void_p]
         _lib.orc_philox_raw.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib.orc_philox_uniforms_batch.argtypes = [C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_philox_actions.argtypes = [C.c_uint64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     return _lib
 
 
@@ -180,13 +182,21 @@ class COracleBatch:
 
 
 def philox_uniforms(seed, env_ids, episode_idx):
-    env_ids = np.asarray(env_ids, dtype=np.int64).ravel()
-    episode_idx = np.broadcast_to(np.asarray(episode_idx, dtype=np.int32), env_ids.shape)
+    """The 24 reset() draws of the device's Philox stream for (seed; env id, episode index)."""
+    env_ids = np.ascontiguousarray(np.asarray(env_ids, dtype=np.int64).ravel())
+    episode_idx = np.ascontiguousarray(np.broadcast_to(np.asarray(episode_idx, dtype=np.int32), env_ids.shape))
     out = np.zeros((env_ids.size, 24))
-    L = lib()
-    for i in range(env_ids.size):
-        L.orc_philox_uniforms(C.c_uint64(int(seed)), C.c_int64(int(env_ids[i])), C.c_int32(int(episode_idx[i])),
-                              C.c_void_p(out[i].ctypes.data))
+    lib().orc_philox_uniforms_batch(C.c_uint64(int(seed)), C.c_int64(env_ids.size), _ptr(env_ids), _ptr(episode_idx),
+                                    _ptr(out))
+    return out
+
+
+def philox_actions(seed, env_ids, step_index):
+    """The U(-1,1) fp64 actions the fused rollout draws for (action seed; env id, step index)."""
+    env_ids = np.ascontiguousarray(np.asarray(env_ids, dtype=np.int64).ravel())
+    out = np.zeros((env_ids.size, 6))
+    lib().orc_philox_actions(C.c_uint64(int(seed)), C.c_int64(env_ids.size), _ptr(env_ids), C.c_int64(int(step_index)),
+                             _ptr(out))
     return out
 
 

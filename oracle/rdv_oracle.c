@@ -572,5 +572,28 @@ void orc_philox_uniforms(uint64_t seed, int64_t env_id, int32_t episode_idx, dou
     }
 }
 
+/* U(-1,1) fp64 actions of the device's fused rollout (RDV_ACTIONS_PHILOX): counter = (env_id lo, env_id hi,
+ * step index lo, 0x40000000 | block | step index hi << 4), blocks 0..2, key = action seed; a = 2u - 1. */
+void orc_philox_actions(uint64_t seed, int64_t n, const int64_t *env_ids, int64_t step_index, double *actions)
+{
+    for (int64_t e = 0; e < n; ++e) {
+        for (uint32_t blk = 0; blk < 3; ++blk) {
+            uint32_t c[4] = {(uint32_t)env_ids[e], (uint32_t)((uint64_t)env_ids[e] >> 32), (uint32_t)step_index,
+                             0x40000000u | blk | (((uint32_t)((uint64_t)step_index >> 32) & 0x00FFFFFFu) << 4)};
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            double u0 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6)) / 9007199254740992.0;
+            double u1 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) / 9007199254740992.0;
+            actions[6 * e + 2 * blk] = 2.0 * u0 - 1.0;
+            actions[6 * e + 2 * blk + 1] = 2.0 * u1 - 1.0;
+        }
+    }
+}
+
+/* all 24 reset draws of many envs at once */
+void orc_philox_uniforms_batch(uint64_t seed, int64_t n, const int64_t *env_ids, const int32_t *episode_idx, double *u)
+{
+    for (int64_t e = 0; e < n; ++e) orc_philox_uniforms(seed, env_ids[e], episode_idx[e], u + 24 * e);
+}
+
 /* raw block function, exported for the Random123 known-answer test */
 void orc_philox_raw(uint32_t ctr[4], uint32_t k0, uint32_t k1) { philox4x32_10(ctr, k0, k1); }

@@ -21,9 +21,9 @@ CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200.so")   # env: A/B experiments
 SOURCES = ("rdv_b200.cu",)
-HEADERS = ("rdv_math.cuh", "rdv_env.cuh")
+HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -84,6 +84,18 @@ class RdvStepIO(C.Structure):
     ]
 
 
+class RdvRolloutIO(C.Structure):
+    _fields_ = [
+        ("steps", C.c_int32), ("action_source", C.c_int32), ("auto_reset", C.c_int32), ("reserved", C.c_int32),
+        ("actions", C.c_void_p), ("action_seed", C.c_uint64), ("step_base", C.c_int64),
+        ("actions_out", C.c_void_p), ("obs", C.c_void_p), ("rewards", C.c_void_p), ("dones", C.c_void_p),
+        ("obs_steps", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+ACTIONS_F32, ACTIONS_F64, ACTIONS_PHILOX = 0, 1, 2
+
+
 class RdvPolicy(C.Structure):
     _fields_ = [
         ("w0", C.c_void_p), ("b0", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p),
@@ -100,6 +112,8 @@ PROTOTYPES = {
     "rdv_params_derive": (C.c_int, [C.POINTER(RdvParams)]),
     "rdv_step": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.POINTER(RdvStepIO), C.c_int64,
                            C.c_uint64, C.c_int64, C.c_void_p]),
+    "rdv_rollout": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.POINTER(RdvRolloutIO), C.c_int64,
+                              C.c_uint64, C.c_int64, C.c_void_p]),
     "rdv_reset": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "rdv_observe": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_void_p, C.c_int64, C.c_void_p]),

@@ -146,6 +146,66 @@ class BatchedRendezvousEnv:
         self._keepalive = actions
         return self.obs, self.reward, self.done
 
+    def rollout(self, steps: int, actions: Optional[torch.Tensor] = None, action_seed: Optional[int] = None,
+                step_base: int = 0, record_rewards: bool = False, record_dones: bool = False,
+                record_obs: bool = False, record_actions: bool = False) -> dict:
+        """``steps`` consecutive env steps in ONE kernel launch (state stays in registers, finished envs restart
+        in place when ``auto_reset``).  Actions come from ``actions`` ([steps, N, 6] float32/float64 on the device) or,
+        when it is None, from the device Philox stream ``(action_seed; global env id, step_base + k)`` as U(-1,1) fp64
+        draws -- the "random actions" workload.  Returns a dict with ``obs`` (final observation, f32 [N,17]) and the
+        requested per-step records (``rewards`` f64 [steps,N], ``dones`` u8 [steps,N], ``obs_steps`` f32 [steps,N,17],
+        ``actions`` f64 [steps,N,6] for Philox actions).  Asynchronous on the current stream."""
+        steps = int(steps)
+        n, dev = self.num_envs, self.device
+        if steps < 0:
+            raise ValueError("steps must be >= 0")
+        if actions is not None:
+            if actions.device != dev or actions.dtype not in (torch.float32, torch.float64):
+                raise ValueError("actions must be a float32/float64 tensor on the env's device")
+            if tuple(actions.shape) != (steps, n, N.ACT_DIM):
+                raise ValueError(f"actions must have shape ({steps}, {n}, {N.ACT_DIM})")
+            actions = actions.contiguous()
+            source = N.ACTIONS_F64 if actions.dtype == torch.float64 else N.ACTIONS_F32
+            esz = 8 if actions.dtype == torch.float64 else 4
+        else:
+            if action_seed is None:
+                raise ValueError("give either an actions tensor or an action_seed for device-generated actions")
+            source, esz = N.ACTIONS_PHILOX, 0
+        out = {"obs": self.obs}
+        rew = torch.empty((steps, n), dtype=torch.float64, device=dev) if record_rewards else None
+        don = torch.empty((steps, n), dtype=torch.uint8, device=dev) if record_dones else None
+        obs_steps = torch.empty((steps, n, N.OBS_DIM), dtype=torch.float32, device=dev) if record_obs else None
+        act_out = torch.empty((steps, n, N.ACT_DIM), dtype=torch.float64, device=dev) \
+            if (record_actions and actions is None) else None
+        if len(self.groups) > 1 and (rew is not None or don is not None or obs_steps is not None or act_out is not None
+                                     or actions is not None):
+            raise NotImplementedError("per-step records / tensor actions with param_batches: use step()")
+        stream = _stream_ptr(dev)
+        with torch.cuda.device(dev):
+            for g in self.groups:
+                io = N.RdvRolloutIO(
+                    steps, source, int(self.auto_reset), 0,
+                    actions.data_ptr() if actions is not None else None,
+                    int(action_seed or 0) & 0xFFFFFFFFFFFFFFFF, int(step_base),
+                    act_out.data_ptr() if act_out is not None else None,
+                    self.obs.data_ptr() + g.lo * N.OBS_DIM * 4,
+                    rew.data_ptr() if rew is not None else None, don.data_ptr() if don is not None else None,
+                    obs_steps.data_ptr() if obs_steps is not None else None,
+                    self.stats.data_ptr() if self.stats is not None else None)
+                st = self._state_of(g)
+                N.check(self.lib.rdv_rollout(C.byref(g.params), C.byref(st), C.byref(io), g.n, self.seed,
+                                             self.env_offset + g.lo, stream), "rdv_rollout")
+        self._keepalive = actions
+        if rew is not None:
+            out["rewards"] = rew
+        if don is not None:
+            out["dones"] = don
+        if obs_steps is not None:
+            out["obs_steps"] = obs_steps
+        if act_out is not None:
+            out["actions"] = act_out
+        return out
+
     def reset(self, mask: Optional[torch.Tensor] = None, uniforms: Optional[torch.Tensor] = None,
               bump_episode: bool = True) -> torch.Tensor:
         """reset() for all envs, or those where ``mask`` (uint8/bool [N]) is set.  ``uniforms`` ([N,24] fp64 in

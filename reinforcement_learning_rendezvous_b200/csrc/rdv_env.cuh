@@ -150,13 +150,12 @@ RDV_DEV double koz_distance(const RdvParams &P, double r, double th)
 constexpr int RDV_TEAM = 8;
 constexpr int RDV_TEAM_ROW = 24;
 
-RDV_DEV void team_reset(const RdvParams &P, const RdvState &S, uint64_t seed, int64_t env_id, int64_t i,
-                        bool valid, int bump, const double *uniforms /* nullable [24] of this env */,
-                        double *row, float *obs_row /* staging row (shared) or global row */)
+// Core: after the call row[0..19] holds the new state (rc vc qc wc qt wt) and, on lane 0's return,
+// row[20] / row[21] the collided / success flags.  Ends with a __syncwarp().
+RDV_DEV void team_reset_core(const RdvParams &P, uint64_t seed, int64_t env_id, int episode,
+                             const double *uniforms /* nullable [24] of this env */, double *row)
 {
     const int sub = threadIdx.x & (RDV_TEAM - 1);
-    const int64_t ld = S.ld;
-    const int episode = S.i32[RDV_I_EPISODE * ld + i] + bump;
 
     // ---- phase 1: own quantity from own four draws ----
     double val[4] = {0.0, 0.0, 0.0, 0.0};
@@ -222,7 +221,7 @@ RDV_DEV void team_reset(const RdvParams &P, const RdvState &S, uint64_t seed, in
     }
     __syncwarp();
 
-    // ---- phase 3: lane 0 -> flags and counters; lanes 1..7 -> state rows and the observation ----
+    // ---- phase 3: lane 0 -> collided / success flags (:260-261) ----
     if (sub == 0) {
         EnvRegs e;
 #pragma unroll
@@ -232,7 +231,6 @@ RDV_DEV void team_reset(const RdvParams &P, const RdvState &S, uint64_t seed, in
 #pragma unroll
         for (int k = 0; k < 3; ++k) { e.wc[k] = row[RDV_WCX + k]; e.wt[k] = row[RDV_WTX + k]; }
         const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
-        // collided = check_collision(); success = int(check_success())   (:260-261)
         const double rc_sq = dot3(e.rc, e.rc);
         const int collided = (rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle) ? 1 : 0;
         int success = 0;
@@ -241,29 +239,44 @@ RDV_DEV void team_reset(const RdvParams &P, const RdvState &S, uint64_t seed, in
             if (es.pos <= P.max_rd_error_sq && es.vel <= P.max_vd_error_sq && es.rot <= P.max_wd_error_sq)
                 success = attitude_error(P, e, Rc, rc_sq) <= P.max_qd_error ? 1 : 0;
         }
-        if (valid) {
-            S.f64[RDV_TDV * ld + i] = 0.0; S.f64[RDV_TDW * ld + i] = 0.0; S.f64[RDV_EPRET * ld + i] = 0.0;
-            S.i32[RDV_I_STEP * ld + i] = 0; S.i32[RDV_I_SUCCESS * ld + i] = success;
-            S.i32[RDV_I_COLLIDED * ld + i] = collided; S.i32[RDV_I_EPISODE * ld + i] = episode;
-        }
-    } else if (valid) {
+        row[20] = (double)collided;
+        row[21] = (double)success;
+    }
+    __syncwarp();
+}
+
+// observation slot k (< 17) of a state value x: get_observation (:294-311) -- rc/20, vc/5, qc, wc/rad(10), qt
+RDV_DEV float obs_of_state_row(const ObsScale &sc, int k, double x)
+{
+    if (k < RDV_QCW) {
+        const bool pos = k < RDV_VCX;
+        return (float)fma(2.0 * (x + (pos ? sc.hi_r : sc.hi_v)), pos ? sc.inv_r : sc.inv_v, -1.0);
+    }
+    if (k >= RDV_WCX && k < RDV_QTW) return (float)fma(2.0 * (x + sc.hi_w), sc.inv_w, -1.0);
+    return (float)x;
+}
+
+// Reset of env i of the state arrays: team_reset_core, then the 8 lanes store the state rows, the counters
+// and the observation.
+RDV_DEV void team_reset(const RdvParams &P, const RdvState &S, uint64_t seed, int64_t env_id, int64_t i,
+                        bool valid, int bump, const double *uniforms /* nullable [24] of this env */,
+                        double *row, float *obs_row /* staging row (shared) or global row */)
+{
+    const int sub = threadIdx.x & (RDV_TEAM - 1);
+    const int64_t ld = S.ld;
+    const int episode = S.i32[RDV_I_EPISODE * ld + i] + bump;
+    team_reset_core(P, seed, env_id, episode, uniforms, row);
+    if (!valid) return;
+    if (sub == 0) {
+        S.f64[RDV_TDV * ld + i] = 0.0; S.f64[RDV_TDW * ld + i] = 0.0; S.f64[RDV_EPRET * ld + i] = 0.0;
+        S.i32[RDV_I_STEP * ld + i] = 0; S.i32[RDV_I_SUCCESS * ld + i] = (int)row[21];
+        S.i32[RDV_I_COLLIDED * ld + i] = (int)row[20]; S.i32[RDV_I_EPISODE * ld + i] = episode;
+    } else {
         const ObsScale sc = obs_scale(P);
         for (int k = sub - 1; k < RDV_TDV; k += RDV_TEAM - 1) {
             const double x = row[k];
             S.f64[k * ld + i] = x;
-            if (obs_row) {
-                // get_observation (:294-311): rc/20, vc/5, qc, wc/rad(10), qt; wt is not observed
-                if (k < RDV_QCW) {
-                    const bool pos = k < RDV_VCX;
-                    obs_row[k] = (float)fma(2.0 * (x + (pos ? sc.hi_r : sc.hi_v)), pos ? sc.inv_r : sc.inv_v, -1.0);
-                } else if (k < RDV_WCX) {
-                    obs_row[k] = (float)x;
-                } else if (k < RDV_QTW) {
-                    obs_row[k] = (float)fma(2.0 * (x + sc.hi_w), sc.inv_w, -1.0);
-                } else if (k < RDV_WTX) {
-                    obs_row[k] = (float)x;
-                }
-            }
+            if (obs_row && k < RDV_OBS_DIM) obs_row[k] = obs_of_state_row(sc, k, x);
         }
     }
 }

@@ -474,7 +474,8 @@ RDV_DEV void rk_attempt(RkBody<ISO> &s, const double dt, const BodyConst &b, int
     }
 }
 
-// Both attitude solves of one env step.  Returns accepted steps of both bodies, or -1 on failure.
+// Both attitude solves of one env step (general bodies): the two branch-free state machines above, called
+// back to back.  Returns accepted steps of both bodies, or -1 on failure.
 template <bool ISO>
 RDV_DEV int rk45_attitude_pair(double (&ya)[7], double (&yb)[7], const double dt, const BodyConst &ba,
                                const BodyConst &bb, int &n_rejected)
@@ -491,6 +492,162 @@ RDV_DEV int rk45_attitude_pair(double (&ya)[7], double (&yb)[7], const double dt
 #pragma unroll
     for (int i = 0; i < 7; ++i) { ya[i] = A.y[i]; yb[i] = B.y[i]; }
     return (A.failed || B.failed) ? -1 : A.accepted + B.accepted;
+}
+
+// ---------------------------------------------------------------------------------
+// The isotropic, torque-free case (the reference env: w is constant, only q moves) with the two
+// bodies interleaved STAGE BY STAGE in the source: "stage vector of body 0, stage vector of body 1,
+// right-hand side of body 0, right-hand side of body 1".  The two right-hand sides are independent
+// ~30-instruction dependency chains (dot product -> rsqrt -> Omega q) that sit next to each other in one
+// basic block, so the scheduler overlaps them; written as two whole solves one after the other the compiler
+// serialises them.  Arithmetic per body is identical to rk45_attitude<true>, operation for operation.
+// ---------------------------------------------------------------------------------
+RDV_DEV void rhs_iso(const double *q, const double *hw, double *f)
+{
+    const double r = fast_rsqrt(dot4(q, q));
+    const double g0 = -fma(hw[2], q[3], fma(hw[1], q[2], hw[0] * q[1]));
+    const double g1 = fma(-hw[1], q[3], fma(hw[2], q[2], hw[0] * q[0]));
+    const double g2 = fma(hw[0], q[3], fma(-hw[2], q[1], hw[1] * q[0]));
+    const double g3 = fma(-hw[0], q[2], fma(hw[1], q[1], hw[2] * q[0]));
+    f[0] = g0 * r; f[1] = g1 * r; f[2] = g2 * r; f[3] = g3 * r;
+}
+
+template <bool CTA_SYNC>
+RDV_DEV int rk45_iso_pair(double (&ya)[7], double (&yb)[7], const double dt, int &n_rejected)
+{
+    double y[2][4], w[2][3], hw[2][3], K0[2][4], h_abs[2], t[2];
+    int accepted[2] = {0, 0};
+    bool done[2] = {false, false}, rejected[2] = {false, false}, failed[2] = {false, false};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { y[0][i] = ya[i]; y[1][i] = yb[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        w[0][i] = ya[4 + i]; w[1][i] = yb[4 + i];
+        hw[0][i] = 0.5 * w[0][i]; hw[1][i] = 0.5 * w[1][i];
+    }
+    // ---- select_initial_step (scipy common.py:68-134) for both bodies ----
+    {
+        double inv_sc[2][4], d0s[2], d1s[2], h0[2], y1[2][4], f1[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) rhs_iso(y[b], hw[b], K0[b]);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            d0s[b] = 0.0; d1s[b] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                inv_sc[b][i] = fast_rcp(fma(fabs(y[b][i]), RK_RTOL, RK_ATOL));
+                const double a = y[b][i] * inv_sc[b][i];
+                d0s[b] = fma(a, a, d0s[b]);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {                       // the rate components only enter d0
+                const double a = w[b][i] * fast_rcp(fma(fabs(w[b][i]), RK_RTOL, RK_ATOL));
+                d0s[b] = fma(a, a, d0s[b]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double a = K0[b][i] * inv_sc[b][i];
+                d1s[b] = fma(a, a, d1s[b]);
+            }
+            d0s[b] *= (1.0 / 7.0);
+            d1s[b] *= (1.0 / 7.0);
+            const bool tiny = d0s[b] < 1e-10 || d1s[b] < 1e-10;
+            const double ratio = d0s[b] * fast_rcp(tiny ? 1.0 : d1s[b]);
+            h0[b] = fmin(tiny ? 1e-6 : 0.01 * (ratio * fast_rsqrt(ratio)), dt);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y1[b][i] = fma(h0[b], K0[b][i], y[b][i]);
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) rhs_iso(y1[b], hw[b], f1[b]);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            double d2s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double a = (f1[b][i] - K0[b][i]) * inv_sc[b][i];
+                d2s = fma(a, a, d2s);
+            }
+            const double inv_h0 = fast_rcp(h0[b]);
+            d2s = d2s * (1.0 / 7.0) * inv_h0 * inv_h0;
+            const double h1 = (d1s[b] <= 1e-30 && d2s <= 1e-30) ? fmax(1e-6, h0[b] * 1e-3)
+                                                                  : pow_neg_tenth_nb(fmax(d1s[b], d2s) * 1e4);
+            h_abs[b] = fmin(fmin(100.0 * h0[b], h1), dt);
+            t[b] = 0.0;
+        }
+    }
+    // ---- attempted steps (scipy rk.py:111-179), both bodies per pass, predicated commit ----
+    // CTA_SYNC: every warp of the CTA runs the same number of passes, re-converging at a barrier per pass, so
+    // that all resident warps fetch the same ~20 KB of straight-line code at the same time (the step is
+    // instruction-cache bound otherwise); a finished thread's extra passes commit nothing.
+    for (;;) {
+        bool more = !((done[0] || failed[0]) && (done[1] || failed[1]));
+        if (CTA_SYNC) more = __syncthreads_or(more);
+        if (!more) break;
+        double h[2], t_new[2], ha[2], ys[2][4];
+        bool fail_now[2];
+        double K1[2][4], K2[2][4], K3[2][4], K4[2][4], K5[2][4], K6[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t[b]) + 1) - t[b]);
+            fail_now[b] = rejected[b] && h_abs[b] < min_step;
+            ha[b] = rejected[b] ? h_abs[b] : fmax(h_abs[b], min_step);
+            t_new[b] = t[b] + ha[b];
+            if (t_new[b] - dt > 0.0) t_new[b] = dt;
+            h[b] = t_new[b] - t[b];
+            ha[b] = fabs(h[b]);
+        }
+#define RDV_STAGE(KOUT, EXPR)                                                      \
+        _Pragma("unroll") for (int b = 0; b < 2; ++b) {                            \
+            _Pragma("unroll") for (int i = 0; i < 4; ++i) ys[b][i] = (EXPR);       \
+        }                                                                          \
+        _Pragma("unroll") for (int b = 0; b < 2; ++b) rhs_iso(ys[b], hw[b], KOUT[b]);
+        RDV_STAGE(K1, fma(K0[b][i] * RK_A21, h[b], y[b][i]))
+        RDV_STAGE(K2, fma(fma(K1[b][i], RK_A32, K0[b][i] * RK_A31), h[b], y[b][i]))
+        RDV_STAGE(K3, fma(fma(K2[b][i], RK_A43, fma(K1[b][i], RK_A42, K0[b][i] * RK_A41)), h[b], y[b][i]))
+        RDV_STAGE(K4, fma(fma(K3[b][i], RK_A54, fma(K2[b][i], RK_A53, fma(K1[b][i], RK_A52, K0[b][i] * RK_A51))),
+                          h[b], y[b][i]))
+        RDV_STAGE(K5, fma(fma(K4[b][i], RK_A65, fma(K3[b][i], RK_A64, fma(K2[b][i], RK_A63,
+                          fma(K1[b][i], RK_A62, K0[b][i] * RK_A61)))), h[b], y[b][i]))
+        RDV_STAGE(K6, fma(h[b], fma(K5[b][i], RK_B6, fma(K4[b][i], RK_B5, fma(K3[b][i], RK_B4,
+                          fma(K2[b][i], RK_B3, K0[b][i] * RK_B1)))), y[b][i]))
+#undef RDV_STAGE
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            double es = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double e = fma(K6[b][i], RK_E7, fma(K5[b][i], RK_E6, fma(K4[b][i], RK_E5, fma(K3[b][i], RK_E4,
+                               fma(K2[b][i], RK_E3, K0[b][i] * RK_E1)))));
+                const double sc = fma(fmax(fabs(y[b][i]), fabs(ys[b][i])), RK_RTOL, RK_ATOL);
+                e = e * h[b] * fast_rcp(sc);
+                es = fma(e, e, es);
+            }
+            es *= (1.0 / 7.0);
+            const bool live = !done[b] && !failed[b];
+            const bool bad = fail_now[b] || !(es < 1.0e300);
+            const bool accept = es < 1.0;
+            const double p = 0.9 * pow_neg_tenth_nb(fmin(fmax(es, 1e-12), 1e8));
+            double factor = accept ? fmin(10.0, p) : fmax(0.2, p);
+            if (accept && rejected[b]) factor = fmin(1.0, factor);
+            const bool commit = live && !bad && accept;
+            if (live) {
+                failed[b] = bad;
+                h_abs[b] = bad ? h_abs[b] : ha[b] * factor;
+                rejected[b] = !accept;
+                n_rejected += (!bad && !accept) ? 1 : 0;
+            }
+            if (commit) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { y[b][i] = ys[b][i]; K0[b][i] = K6[b][i]; }
+                t[b] = t_new[b];
+                accepted[b] += 1;
+                done[b] = t_new[b] - dt >= 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ya[i] = y[0][i]; yb[i] = y[1][i]; }
+    return (failed[0] || failed[1]) ? -1 : accepted[0] + accepted[1];
 }
 
 // Closed-form alternative (opt-in, RDV_INTEGRATOR_CLOSED_FORM; only valid for ISO bodies):

@@ -1,0 +1,114 @@
+"""GPU parity of rdv_rollout (K fused steps per launch): against the per-step API (bit-identical), against the
+C oracle with the shared Philox action + reset streams, and the per-step records."""
+import numpy as np
+import pytest
+
+from helpers import REL_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_rollout_equals_repeated_step(dtype):
+    """Same actions through rollout() and through K step() calls: identical state, records and statistics."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    n, K = 1000, 48
+    a = BatchedRendezvousEnv(n, seed=3, env_offset=77, t_max=25)
+    b = BatchedRendezvousEnv(n, seed=3, env_offset=77, t_max=25)
+    a.reset()
+    b.reset()
+    g = torch.Generator(device=a.device)
+    g.manual_seed(0)
+    acts = (torch.rand((K, n, 6), dtype=torch.float64, device=a.device, generator=g) * 2 - 1).to(getattr(torch, dtype))
+    out = a.rollout(K, actions=acts, record_rewards=True, record_dones=True, record_obs=True)
+    for k in range(K):
+        obs, rew, done = b.step(acts[k])
+        # the thread-per-env rollout and the lane-pair step kernel order a few operations differently
+        assert rel_err(out["rewards"][k].cpu().numpy(), rew.cpu().numpy()) <= 1e-12
+        assert torch.equal(out["dones"][k], done)
+        assert (out["obs_steps"][k] - obs).abs().max().item() <= 1.2e-7
+    assert rel_err(a.get_state().cpu().numpy(), b.get_state().cpu().numpy()) <= 1e-11
+    assert torch.equal(a.i32[:, :n], b.i32[:, :n])
+    assert (out["obs"] - b.obs).abs().max().item() <= 1.2e-7
+    sa, sb = a.read_stats(), b.read_stats()
+    for key in ("steps", "episodes", "succeeded", "collided", "end_obs", "end_time", "end_bubble", "end_attitude",
+                "rk_accepted", "rk_rejected", "failures"):
+        assert sa[key] == sb[key], key
+    assert sa["episodes"] > n and abs(sa["reward_sum"] - sb["reward_sum"]) <= 1e-9 * abs(sb["reward_sum"])
+
+
+def test_rollout_philox_actions_vs_c_oracle():
+    """Device-generated actions + in-warp resets over 60 steps vs the C oracle driven by the same streams."""
+    import torch
+    from oracle import c_oracle as CO
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    n, K, seed, aseed, offset, base = 2048, 60, 11, 0xABCDEF0123, 5000, 1_000_000_000_000
+    env = BatchedRendezvousEnv(n, seed=seed, env_offset=offset, t_max=30)
+    orc = CO.COracleBatch(CO.make_params(t_max=30), n)
+    ids = offset + np.arange(n)
+    episode = np.ones(n, dtype=np.int32)
+    env.reset()
+    orc.reset_from_uniforms(CO.philox_uniforms(seed, ids, episode))
+    # two launches of 30 steps: the stream position (step_base) carries over
+    outs = [env.rollout(30, action_seed=aseed, step_base=base + 30 * j, record_rewards=True, record_dones=True,
+                        record_actions=True, record_obs=True) for j in range(2)]
+    rewards = torch.cat([o["rewards"] for o in outs]).cpu().numpy()
+    dones = torch.cat([o["dones"] for o in outs]).cpu().numpy()
+    actions = torch.cat([o["actions"] for o in outs]).cpu().numpy()
+    obs_steps = torch.cat([o["obs_steps"] for o in outs]).cpu().numpy()
+    total_done = 0
+    for k in range(K):
+        a = CO.philox_actions(aseed, ids, base + k)
+        np.testing.assert_array_equal(actions[k], a)
+        o_obs, o_rew, o_done = orc.step(a, threads=8)
+        o_obs, o_rew, o_done = o_obs.copy(), o_rew.copy(), o_done.copy()
+        np.testing.assert_array_equal(dones[k], o_done)
+        assert rel_err(rewards[k], o_rew) <= REL_TOL
+        d = np.flatnonzero(o_done)
+        if d.size:
+            total_done += d.size
+            episode[d] += 1
+            mask = np.zeros(n, dtype=np.uint8)
+            mask[d] = 1
+            o_obs = orc.reset_from_uniforms(CO.philox_uniforms(seed, ids, episode), mask=mask).copy()
+        assert np.abs(obs_steps[k] - o_obs).max() <= 1.2e-7
+    assert total_done > n
+    assert rel_err(env.get_state().cpu().numpy(), orc.state) <= REL_TOL
+    np.testing.assert_array_equal(env.episode_index.cpu().numpy(), episode)
+    np.testing.assert_array_equal(env.collided.cpu().numpy(), orc.flags[:, 0])
+    assert np.abs(env.obs.cpu().numpy() - orc.observe()).max() <= 1.2e-7
+    st = env.read_stats()
+    assert st["steps"] == n * K and st["episodes"] == total_done and st["failures"] == 0
+
+
+def test_rollout_shard_invariance_and_edges():
+    """Two shards == one batch (global env ids key both streams); n not a multiple of 32; steps = 0; bad args."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    whole = BatchedRendezvousEnv(777, seed=9)
+    lo = BatchedRendezvousEnv(400, seed=9, env_offset=0)
+    hi = BatchedRendezvousEnv(377, seed=9, env_offset=400)
+    for e in (whole, lo, hi):
+        e.reset()
+        e.rollout(40, action_seed=4)
+    s = whole.get_state()
+    assert torch.equal(s[:400], lo.get_state()) and torch.equal(s[400:], hi.get_state())
+    assert torch.equal(whole.obs[:400], lo.obs) and torch.equal(whole.obs[400:], hi.obs)
+    before = whole.get_state().clone()
+    whole.rollout(0, action_seed=1)
+    assert torch.equal(before, whole.get_state())
+    with pytest.raises(ValueError):
+        whole.rollout(3)
+    with pytest.raises(ValueError):
+        whole.rollout(3, actions=torch.zeros((2, 777, 6), dtype=torch.float64, device=whole.device))
+    # no auto-reset: finished envs keep stepping, like step()
+    a = BatchedRendezvousEnv(64, seed=1, auto_reset=False)
+    b = BatchedRendezvousEnv(64, seed=1, auto_reset=False)
+    a.reset(); b.reset()
+    acts = torch.rand((10, 64, 6), dtype=torch.float64, device=a.device) * 2 - 1
+    a.rollout(10, actions=acts)
+    for k in range(10):
+        b.step(acts[k])
+    assert rel_err(a.get_state().cpu().numpy(), b.get_state().cpu().numpy()) <= 1e-11
+    assert (a.episode_index == 1).all()
