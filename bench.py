@@ -8,13 +8,16 @@ Workload (BASELINE.json configs[1]): 65,536 envs per GPU, default constructor pa
 actions, auto-reset on, fp64 state.  A "step" is one env step of every env of the batch.  Prints ONE JSON line
 (rank 0).  Keys:
 
-  value / ms_per_step   device-resident loop: fp64 actions from a pre-generated 64-step device ring (201 MB,
-                        larger than L2), K steps back to back, CUDA events, max over ranks
+  value / ms_per_step   device-resident loop: K steps as fused rollouts (rdv_rollout, --steps-per-launch steps per
+                        launch), fp64 U(-1,1) actions drawn on the device (Philox), CUDA events, max over ranks
+  step_api              the same workload through the one-launch-per-step entry point (rdv_step) with fp64 actions
+                        from a pre-generated 64-step device ring (201 MB, larger than L2)
   e2e                   same metric through RendezvousVecEnv.step(numpy actions): pinned H2D of the actions and
                         D2H of obs / reward / done / terminal obs / episode records inside the timed region
-  roofline              dominant kernel (step_kernel, the only kernel of a step) timed per launch with CUDA events;
-                        fp64-pipe bound: algorithmic flop per env-step x envs / duration vs the
-                        DFMA peak measured in this run; the HBM view is in roofline["hbm"]
+  roofline              dominant kernel (rollout_kernel, the only kernel of the timed region) timed per launch with
+                        CUDA events inside the timed region; fp64-pipe bound: algorithmic flop per env-step
+                         x envs x steps / duration vs the DFMA peak measured in this run; the HBM view
+                        is in roofline["hbm"]
   cpu_baseline          the reference algorithm (numpy restatement incl. scipy's RK45, bit-exact vs the reference)
                         under a SubprocVecEnv-protocol harness on all host cores, bounded sample
 """
@@ -207,22 +210,27 @@ def run_cuda(args):
             return float(t[0])
         return ms
 
-    # ---------------- device-resident leg ----------------
+    # ---------------- device-resident leg: fused rollouts, KL steps per launch, Philox actions ----------------
+    KL = max(1, min(args.steps_per_launch, K))
+    launches = [KL] * (K // KL) + ([K % KL] if K % KL else [])
     env = BatchedRendezvousEnv(n, device=dev, seed=args.seed, env_offset=rank * n, auto_reset=True,
                                integrator=args.integrator)
     env.reset()
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1 + rank)
-    ring = torch.rand((RING, n, 6), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
-    for k in range(W):
-        env.step(ring[k % RING])
+    done_steps = 0
+    if W:
+        env.rollout(W, action_seed=args.seed + 1, step_base=0)
+        done_steps = W
     env.stats.zero_()
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(launches) + 1)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for k in range(K):
-        env.step(ring[k % RING])
+    ev[0].record()
+    for j, kl in enumerate(launches):
+        env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
+        done_steps += kl
+        ev[j + 1].record()
     all_reduce_stats(env.stats)                       # the per-rollout statistics reduction (NCCL when N > 1)
     e1.record()
     barrier()
@@ -233,20 +241,12 @@ def run_cuda(args):
     assert total_steps == world * n * K, (total_steps, world, n, K)
     value = world * n * K / (ms * 1e-3)
     rk_mean = stats["rk_accepted"] / (2.0 * max(total_steps, 1.0))
+    # dominant kernel: rollout_kernel, per-launch durations of the full-size launches inside the timed region
+    full = [ev[j].elapsed_time(ev[j + 1]) for j, kl in enumerate(launches) if kl == KL]
+    t_launch = sum(full) / len(full)
+    t_step = t_launch / KL
 
-    # ---------------- roofline leg: per-launch CUDA events around the step kernel ----------------
-    R = min(K, 200)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(R)]
-    torch.cuda.synchronize()
-    for k in range(R):
-        ev[k][0].record()
-        env.step(ring[k % RING])
-        ev[k][1].record()
-    torch.cuda.synchronize()
-    t_launches = sorted(a.elapsed_time(b) for a, b in ev)
-    t_step = sum(t_launches) / R
-
-    # fp64 peak: DFMA probe, best of 5
+    # fp64 peak: DFMA probe, best of 6
     blocks, threads, iters = 148 * 8, 256, 4096
     sink = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
     best = 1e30
@@ -263,35 +263,53 @@ def run_cuda(args):
     closed = args.integrator == "closed_form"
     f_step = F_STEP_CLOSED_FORM if closed else F_STEP_BASE + F_STEP_PER_RK * rk_mean
     peaks, peak_src = _peaks()
+    b_step = (386.0 + 68.0) / KL                       # state load + store and the final observation, once per launch
     ach_tf = f_step * n / (t_step * 1e-3) / 1e12
-    ach_gbs = B_STEP_F64 * n / (t_step * 1e-3) / 1e9
+    ach_gbs = b_step * n / (t_step * 1e-3) / 1e9
     roofline = {
-        "kernel": "step_kernel", "bound": "hbm" if closed else "fp64",
-        "achieved": ach_gbs if closed else ach_tf, "peak": peaks["hbm_gbs"] if closed else fp64_peak,
-        "unit": "GB/s" if closed else "TFLOP/s",
-        "frac": (ach_gbs / peaks["hbm_gbs"]) if closed else (ach_tf / fp64_peak),
-        "traffic": None,
-        "peak_source": peak_src if closed else "rdv_fp64_peak_probe (DFMA microbenchmark, this run; "
-                                                 "MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s)",
-        "flop_per_env_step": f_step, "rk45_steps_per_solve": rk_mean,
-        "kernel_ms": t_step, "kernel_ms_min": t_launches[0], "launches_timed": R,
+        "kernel": "rollout_kernel", "bound": "fp64",
+        "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak, "traffic": None,
+        "peak_source": "rdv_fp64_peak_probe (DFMA microbenchmark, this run; MEASURED_PEAKS.json has no fp64 entry; "
+                       "nominal 37 TFLOP/s)",
+        "flop_per_env_step": f_step, "rk45_steps_per_solve": rk_mean, "steps_per_launch": KL,
+        "launch_ms": t_launch, "launch_ms_min": min(full), "launches_timed": len(full),
         "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
-                "bytes_per_env_step": B_STEP_F64, "peak_source": peak_src},
-        "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak},
+                "bytes_per_env_step": b_step, "peak_source": peak_src},
     }
 
-    # ---------------- L2-flushed variant (per-step events; a 256 MB write between steps) ----------------
+    # ---------------- the same launches with L2 flushed in between (a 256 MB write before each) ----------------
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    F = min(K, 50)
+    F = min(len(launches), 8)
     fe = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(F)]
-    for k in range(F):
-        flush.fill_(k & 0xFF)
-        fe[k][0].record()
-        env.step(ring[k % RING])
-        fe[k][1].record()
+    for j in range(F):
+        flush.fill_(j & 0xFF)
+        fe[j][0].record()
+        env.rollout(KL, action_seed=args.seed + 1, step_base=done_steps)
+        done_steps += KL
+        fe[j][1].record()
     torch.cuda.synchronize()
-    ms_flushed = sum(a.elapsed_time(b) for a, b in fe) / F
+    ms_flushed = sum(a.elapsed_time(b) for a, b in fe) / F / KL
     del flush
+
+    # ---------------- per-step API (rdv_step, one launch per step, fp64 actions from a device ring) ----------------
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+    ring = torch.rand((RING, n, 6), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    KS = min(K, 500)
+    for k in range(10):
+        env.step(ring[k % RING])
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record()
+    for k in range(KS):
+        env.step(ring[k % RING])
+    s1.record()
+    barrier()
+    step_ms = max_over_ranks(s0.elapsed_time(s1))
+    step_api = {"value": world * n * KS / (step_ms * 1e-3), "unit": UNIT, "steps": KS, "ms_per_step": step_ms / KS,
+                "gpu_launches": KS, "kernel": "step_kernel",
+                "roofline_frac_fp64": f_step * n / (step_ms / KS * 1e-3) / 1e12 / fp64_peak,
+                "actions": f"fp64 U(-1,1), pre-generated {RING}-step device ring ({RING * n * 48 / 1e6:.0f} MB > L2)"}
 
     # ---------------- end-to-end leg: numpy actions in, numpy results out, through the VecEnv ----------------
     del env
@@ -330,15 +348,16 @@ def run_cuda(args):
         "config": {"workload": f"batched RendezvousEnv, {n:,} envs per GPU, random actions, fp64 step/reset "
                                "(BASELINE.json configs[1])",
                    "envs_per_gpu": n, "total_envs": world * n, "auto_reset": True, "integrator": args.integrator,
-                   "actions": f"fp64 U(-1,1), pre-generated {RING}-step device ring "
-                              f"({RING * n * 48 / 1e6:.0f} MB > 126 MB L2)",
-                   "l2": "state (12.6 MB at 65,536 envs) is carried step to step by the workload itself; the "
-                         "kernel is fp64-pipe bound, see ms_per_step_l2_flushed",
+                   "actions": "fp64 U(-1,1) drawn on the device every step from the Philox4x32-10 stream "
+                              "(action seed; global env id, step index)",
+                   "steps_per_launch": KL,
+                   "l2": "state lives in registers for the steps of a launch and is re-read from memory once per "
+                         "launch; ms_per_step_l2_flushed repeats the launches with a 256 MB L2 flush before each",
                    "ms_per_step_l2_flushed": ms_flushed,
                    "parallelism": f"{world} x independent env shards, no data-path collective; one "
                                   "16-double statistics all-reduce per rollout"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": K,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": len(launches),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "step_api": step_api,
         "episode_stats": {"episodes": stats["episodes"], "mean_length": stats["length_sum"] / max(stats["episodes"], 1),
                           "success_rate": stats["succeeded"] / max(stats["episodes"], 1),
                           "rk_rejected": stats["rk_rejected"], "failures": stats["failures"]},
@@ -357,6 +376,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--integrator", choices=("rk45", "closed_form"), default="rk45")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--steps-per-launch", type=int, default=64, help="env steps fused into one rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0)

@@ -151,7 +151,7 @@ def test_policy_forward_matches_torch_fp32():
 def test_vec_env_contract():
     from reinforcement_learning_rendezvous_b200 import RendezvousVecEnv
     n = 512
-    venv = RendezvousVecEnv(n, seed=7, t_max=15)
+    venv = RendezvousVecEnv(n, seed=7, t_max=15, rich_infos=True)
     assert venv.num_envs == n and venv.observation_space.shape == (17,) and venv.action_space.shape == (6,)
     obs = venv.reset()
     assert obs.shape == (n, 17) and obs.dtype == np.float32
