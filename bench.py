@@ -266,9 +266,18 @@ def run_cuda(args):
     b_step = (386.0 + 68.0) / KL                       # state load + store and the final observation, once per launch
     ach_tf = f_step * n / (t_step * 1e-3) / 1e12
     ach_gbs = b_step * n / (t_step * 1e-3) / 1e9
+    traffic = None
+    try:                                # dram bytes of one launch from the committed ncu capture (K-independent:
+        with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:      # state in + out, final obs)
+            tr = json.load(f)
+        if tr.get("envs") == n:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {
         "kernel": "rollout_kernel", "bound": "fp64",
-        "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak, "traffic": None,
+        "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak, "traffic": traffic,
+        "algorithmic_bytes_per_launch": b_step * n * KL,
         "peak_source": "rdv_fp64_peak_probe (DFMA microbenchmark, this run; MEASURED_PEAKS.json has no fp64 entry; "
                        "nominal 37 TFLOP/s)",
         "flop_per_env_step": f_step, "rk45_steps_per_solve": rk_mean, "steps_per_launch": KL,
