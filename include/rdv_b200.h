@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 8
+#define RDV_ABI_VERSION 9
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -106,6 +106,8 @@ typedef struct RdvParams {
     double fuel_scale;             /* dt*fuel_coef / (3*max_delta_v)   (:333)                          */
     double att_scale, bonus_scale, collision_scale;   /* dt*att_coef, dt*bonus_coef, dt*collision_coef  */
     double obs_inv_r, obs_inv_v, obs_inv_w;           /* 1/(2*max_axial_distance), 1/(2*5), 1/(2*max_wc) */
+    double near_sq;                /* max(koz, |rd| + max_rd_error)^2 (+margin): beyond it neither a collision,
+                                    * a success nor a reward bonus is possible (:397, :417, :348)        */
 } RdvParams;
 
 /* Environment state: device pointers into caller-owned buffers. */

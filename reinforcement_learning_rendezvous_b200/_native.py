@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200
 SOURCES = ("rdv_b200.cu",)
 HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -68,6 +68,7 @@ class RdvParams(C.Structure):
         ("fuel_scale", C.c_double),
         ("att_scale", C.c_double), ("bonus_scale", C.c_double), ("collision_scale", C.c_double),
         ("obs_inv_r", C.c_double), ("obs_inv_v", C.c_double), ("obs_inv_w", C.c_double),
+        ("near_sq", C.c_double),
     ]
 
 

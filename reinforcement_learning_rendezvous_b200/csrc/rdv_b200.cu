@@ -438,7 +438,7 @@ step_kernel_env(const __grid_constant__ RdvParams P, const RdvState S, const Rdv
             ingest_action_f32(P, a, c, t);
         }
         int rk_acc = 0, rk_rej = 0, fail = 0;
-        env_advance<ISO, CLOSED>(P, e, t, rk_acc, rk_rej, fail);
+        env_advance<ISO, CLOSED, (RDV_STEP1_MIN_CTAS <= 4)>(P, e, t, rk_acc, rk_rej, fail);
         float ov[RDV_OBS_DIM];
         const StepResult r = env_evaluate(P, e, t.fuel, c, ov);
         float *o = s_obs + threadIdx.x * RDV_OBS_DIM;
@@ -552,7 +552,11 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const RdvR
         make_obs(e, obs_scale(P), ov);
 
         for (int k = 0; k < io.steps; ++k) {
-            __syncthreads();      // keep the CTA's warps in the same code region (instruction-cache locality)
+#ifndef RDV_SYNC_PERIOD
+#define RDV_SYNC_PERIOD 1
+#endif
+            if ((k % RDV_SYNC_PERIOD) == 0)
+                __syncthreads();  // keep the CTA's warps in the same code region (instruction-cache locality)
             // ---- action ----
             ActionTerms t;
             const int64_t row = (int64_t)k * n + i;
@@ -579,7 +583,10 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const RdvR
             }
             // ---- step ----
             int rk_acc = 0, rk_rej = 0, fail = 0;
-            env_advance<ISO, CLOSED>(P, e, t, rk_acc, rk_rej, fail);
+#ifndef RDV_SYNC_SOLVES
+#define RDV_SYNC_SOLVES 0
+#endif
+            env_advance<ISO, CLOSED, (TPB_ <= 256), (RDV_SYNC_SOLVES != 0)>(P, e, t, rk_acc, rk_rej, fail);
             const StepResult r = env_evaluate(P, e, t.fuel, c, ov);
             const bool done = r.done && active;
             if (active) {
@@ -922,6 +929,10 @@ int rdv_params_derive(RdvParams *p)
     p->obs_inv_r = 1.0 / (2.0 * p->max_axial_distance);
     p->obs_inv_v = 1.0 / (2.0 * p->max_axial_speed);
     p->obs_inv_w = 1.0 / (2.0 * p->max_wc);
+    {
+        const double reach = rd_n + p->max_rd_error, lim = reach > p->koz_radius ? reach : p->koz_radius;
+        p->near_sq = lim * lim * (1.0 + 1e-9);
+    }
     {   // first step count whose time stamp t = round(k*dt, 3) reaches t_max (:193, :369)
         double k = ceil(p->t_max / p->dt) - 2.0;
         if (k < 1.0) k = 1.0;

@@ -10,10 +10,6 @@ namespace rdv {
 
 __constant__ double c_zero3[3] = {0.0, 0.0, 0.0};     // the target carries no torque (rendezvous_env.py:585)
 
-#ifndef RDV_LOCKSTEP
-#define RDV_LOCKSTEP 1
-#endif
-
 // Per-env quantities that live next to the 20 state numbers.
 struct EnvCounters {
     double tdv, tdw, ep_ret;          // total_delta_v, total_delta_w, running episode return
@@ -49,8 +45,11 @@ RDV_DEV void ingest_action_f32(const RdvParams &P, const float (&a)[6], EnvCount
 }
 
 // Translation (impulse rotated by the OLD chaser attitude, then the CW transition; dynamics.py:24-55) and the
-// two attitude propagations (:552-604).  ISO bodies advance in lock-step (rk45_attitude_pair).
-template <bool ISO, bool CLOSED, bool CTA_SYNC = false>
+// two attitude propagations (:552-604).  LOCKSTEP: the two isotropic solves advance interleaved stage by stage
+// (rk45_iso_pair, 2x ILP, ~240 registers) -- the right choice with <= 2 warps per SM sub-partition; otherwise one
+// solve after the other through a single copy of the solver (128 registers), which wins once 3-4 warps per
+// sub-partition hide the latency instead.
+template <bool ISO, bool CLOSED, bool LOCKSTEP, bool CTA_SYNC = false>
 RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, int &rk_acc, int &rk_rej, int &fail)
 {
     {
@@ -76,7 +75,7 @@ RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, i
         BodyConst bc, bt;
         bc.I = P.inertia_c; bc.Iinv = P.inv_inertia_c; bc.tau = P.torque_c;
         bt.I = P.inertia_t; bt.Iinv = P.inv_inertia_t; bt.tau = c_zero3;
-        if (ISO && RDV_LOCKSTEP) {
+        if (ISO && LOCKSTEP) {
             if (CTA_SYNC) __syncthreads();
             const int k = rk45_iso_pair<CTA_SYNC>(y, z, P.dt, rk_rej);
             if (CTA_SYNC) __syncthreads();
@@ -85,6 +84,7 @@ RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, i
             // one solve after the other through a single copy of the solver code (bounded registers)
 #pragma unroll 1
             for (int body = 0; body < 2; ++body) {
+                if (CTA_SYNC) __syncthreads();        // both solves start with the CTA's warps aligned
                 const int k = rk45_attitude<true>(y, P.dt, bc, rk_rej);
                 if (k < 0) fail = 1; else rk_acc += k;
 #pragma unroll
@@ -110,11 +110,21 @@ struct StepResult { double rew; int done, reason; };
 RDV_DEV StepResult env_evaluate(const RdvParams &P, const EnvRegs &e, const double fuel, EnvCounters &c,
                                 float (&ov)[RDV_OBS_DIM])
 {
-    const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
+    const Rot Rc = rot_from_quat(e.qc);
     const double rc_sq = dot3(e.rc, e.rc);
     const double att = attitude_error(P, e, Rc, rc_sq);
-    const bool col_now = rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle;
-    const ErrSq es = errors_sq(P, e, Rc, Rt);
+    // The target-relative quantities (corridor angle, position / velocity / rate errors) only matter near the
+    // target: a collision needs |rc| < koz, and success (:406-422) or the reward bonus (:348-351) need a position
+    // error <= max_rd_error, impossible unless | |rc| - |rd| | <= max_rd_error (|R(qt) rd| = |rd|).  Far away
+    // -- every step of a random-action episode -- the target rotation matrix is never formed.
+    bool col_now = false;
+    ErrSq es;
+    es.pos = es.vel = es.rot = 1.0e300;
+    if (rc_sq < P.near_sq) {
+        const Rot Rt = rot_from_quat(e.qt);
+        col_now = rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle;
+        es = errors_sq(P, e, Rc, Rt);
+    }
     if (!c.collided) {
         c.collided = col_now ? 1 : 0;
         if (!c.collided && es.pos <= P.max_rd_error_sq && es.vel <= P.max_vd_error_sq && att <= P.max_qd_error &&
