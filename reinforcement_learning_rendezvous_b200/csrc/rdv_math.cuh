@@ -151,7 +151,67 @@ RDV_DEV void attitude_rhs(const double *y, const double *hw_iso, const BodyConst
     }
 }
 
-// Dormand-Prince tableau (scipy rk.py, class RK45)
+// Dormand-Prince tableau (scipy rk.py, class RK45).  Kept in the constant bank so that DFMA reads each
+// coefficient as a c[][] operand instead of materialising a 64-bit immediate with two moves per use.
+#ifndef RDV_RK_CONST_BANK
+#define RDV_RK_CONST_BANK 1
+#endif
+#if RDV_RK_CONST_BANK
+__constant__ double c_rk[26] = {
+    1.0 / 5,
+    3.0 / 40,
+    9.0 / 40,
+    44.0 / 45,
+    -56.0 / 15,
+    32.0 / 9,
+    19372.0 / 6561,
+    -25360.0 / 2187,
+    64448.0 / 6561,
+    -212.0 / 729,
+    9017.0 / 3168,
+    -355.0 / 33,
+    46732.0 / 5247,
+    49.0 / 176,
+    -5103.0 / 18656,
+    35.0 / 384,
+    500.0 / 1113,
+    125.0 / 192,
+    -2187.0 / 6784,
+    11.0 / 84,
+    -71.0 / 57600,
+    71.0 / 16695,
+    -71.0 / 1920,
+    17253.0 / 339200,
+    -22.0 / 525,
+    1.0 / 40,
+};
+#define RK_A21 c_rk[0]
+#define RK_A31 c_rk[1]
+#define RK_A32 c_rk[2]
+#define RK_A41 c_rk[3]
+#define RK_A42 c_rk[4]
+#define RK_A43 c_rk[5]
+#define RK_A51 c_rk[6]
+#define RK_A52 c_rk[7]
+#define RK_A53 c_rk[8]
+#define RK_A54 c_rk[9]
+#define RK_A61 c_rk[10]
+#define RK_A62 c_rk[11]
+#define RK_A63 c_rk[12]
+#define RK_A64 c_rk[13]
+#define RK_A65 c_rk[14]
+#define RK_B1 c_rk[15]
+#define RK_B3 c_rk[16]
+#define RK_B4 c_rk[17]
+#define RK_B5 c_rk[18]
+#define RK_B6 c_rk[19]
+#define RK_E1 c_rk[20]
+#define RK_E3 c_rk[21]
+#define RK_E4 c_rk[22]
+#define RK_E5 c_rk[23]
+#define RK_E6 c_rk[24]
+#define RK_E7 c_rk[25]
+#else
 #define RK_A21 (1.0 / 5)
 #define RK_A31 (3.0 / 40)
 #define RK_A32 (9.0 / 40)
@@ -178,6 +238,7 @@ RDV_DEV void attitude_rhs(const double *y, const double *hw_iso, const BodyConst
 #define RK_E5 (17253.0 / 339200)
 #define RK_E6 (-22.0 / 525)
 #define RK_E7 (1.0 / 40)
+#endif
 #define RK_RTOL 1e-7     /* rendezvous_env.py:567, :594 */
 #define RK_ATOL 1e-6     /* rendezvous_env.py:568, :595 */
 
