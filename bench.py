@@ -345,6 +345,17 @@ def run_cuda(args):
            "d2h_bytes_per_step": venv.d2h_bytes_per_step,
            "api": "RendezvousVecEnv.step(np.float32[N,6]) -> (obs, rewards, dones, infos) numpy, pinned staging"}
 
+    # the same loop through the array-returning variant (no per-env Python objects)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(KE):
+        obs, rew, done, fin = venv.step_arrays(host_ring[k % RING])
+        checksum += float(rew[0]) + fin["episode_return"].sum()
+    barrier()
+    arr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e["arrays_api"] = {"value": world * n * KE / (arr_ms * 1e-3), "unit": UNIT, "ms_per_step": arr_ms / KE,
+                         "api": "RendezvousVecEnv.step_arrays: same transfers, finished episodes as arrays"}
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -375,6 +386,15 @@ def run_cuda(args):
     return 0
 
 
+def _json_only_stdout():
+    """Route everything libraries print on fd 1 (e.g. the NCCL version banner) to stderr and return a file
+    object on the original stdout, so that stdout carries exactly one JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,9 +414,14 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_cuda(args)
+    out = _json_only_stdout()
+    sys.stdout = out
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_cuda(args)
+    finally:
+        out.flush()
 
 
 if __name__ == "__main__":

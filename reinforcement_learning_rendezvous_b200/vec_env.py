@@ -110,7 +110,7 @@ class RendezvousVecEnv(_Base):
             self._d_act32.copy_(self._h_act32, non_blocking=True)
             self._pending = self._d_act32
 
-    def step_wait(self):
+    def _launch_and_fetch(self):
         if self._pending is None:
             raise RuntimeError("step_wait() called without step_async()")
         env = self.env
@@ -126,8 +126,30 @@ class RendezvousVecEnv(_Base):
         torch.cuda.current_stream(env.device).synchronize()
         obs, rew = self._h_obs.numpy(), self._h_rew.numpy()
         done = self._h_done.numpy().view(np.bool_)
+        return obs, rew, done, np.flatnonzero(done)
+
+    def step_arrays(self, actions):
+        """``step`` without per-env Python objects: returns ``(obs, rewards, dones, finished)`` where ``finished`` is
+        a dict of arrays over the envs whose episode just ended -- ``index``, ``terminal_observation`` [m,17],
+        ``episode_return``, ``episode_length``, ``is_success``, ``collided``, ``total_delta_v``, ``total_delta_w``,
+        ``end_reason`` (0 obs, 1 time, 2 bubble, 3 attitude).  Same data as the ``infos`` of ``step``."""
+        self.step_async(actions)
+        obs, rew, done, idx = self._launch_and_fetch()
+        rec = self._h_rec.numpy()[idx]
+        finished = {
+            "index": idx, "terminal_observation": self._h_term.numpy()[idx],
+            "episode_return": rec[:, N.EP_RETURN], "episode_length": rec[:, N.EP_LENGTH].astype(np.int64),
+            "is_success": rec[:, N.EP_SUCCESS] > 0, "collided": rec[:, N.EP_COLLIDED] > 0,
+            "total_delta_v": rec[:, N.EP_DELTA_V], "total_delta_w": rec[:, N.EP_DELTA_W],
+            "end_reason": self._h_reason.numpy()[idx],
+        }
+        if self.copy_outputs:
+            return obs.copy(), rew.copy(), done.copy(), finished
+        return obs, rew, done, finished
+
+    def step_wait(self):
+        obs, rew, done, idx = self._launch_and_fetch()
         infos: List[dict] = [_EMPTY_INFO] * self.num_envs
-        idx = np.flatnonzero(done)
         if idx.size:
             # bulk numpy work first, then one small dict per finished env
             rec = self._h_rec.numpy()[idx]

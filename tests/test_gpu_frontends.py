@@ -260,3 +260,28 @@ def test_checkpoint_roundtrip():
     other.load_state_dict(sd)
     for k in range(10):
         assert torch.equal(other.step(a)[0], ref[k])
+
+
+def test_vec_env_step_arrays_matches_step_infos():
+    from reinforcement_learning_rendezvous_b200 import RendezvousVecEnv
+    n = 400
+    a_env = RendezvousVecEnv(n, seed=13, t_max=12, rich_infos=True)
+    b_env = RendezvousVecEnv(n, seed=13, t_max=12)
+    a_env.reset(); b_env.reset()
+    rng = np.random.default_rng(1)
+    seen = 0
+    for _ in range(30):
+        act = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        obs, rew, done, infos = a_env.step(act)
+        o2, r2, d2, fin = b_env.step_arrays(act)
+        np.testing.assert_array_equal(obs, o2); np.testing.assert_array_equal(rew, r2); np.testing.assert_array_equal(done, d2)
+        np.testing.assert_array_equal(fin["index"], np.flatnonzero(done))
+        for j, i in enumerate(fin["index"]):
+            info = infos[i]
+            np.testing.assert_array_equal(info["terminal_observation"], fin["terminal_observation"][j])
+            assert info["episode"]["l"] == fin["episode_length"][j]
+            assert abs(info["episode"]["r"] - fin["episode_return"][j]) < 1e-6
+            assert info["is_success"] == bool(fin["is_success"][j]) and info["collided"] == bool(fin["collided"][j])
+            assert info["end_reason"] == ("obs", "time", "bubble", "attitude")[fin["end_reason"][j]]
+            seen += 1
+    assert seen > n
