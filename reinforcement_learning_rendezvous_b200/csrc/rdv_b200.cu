@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 
 // ---------------------------------------------------------------------------------
 // step kernel, layout 1: ONE thread per environment; the chaser and target RK45 solves advance in
-// lock-step inside the thread (rk45_attitude_pair), which doubles the instruction-level parallelism of
+// lock-step inside the thread (rk45_iso_pair), which doubles the instruction-level parallelism of
 // the dependent fp64 chains without the shuffle / duplicated-work overhead of the lane-pair layout.
 // ---------------------------------------------------------------------------------
 #ifndef RDV_STEP1_MIN_CTAS
@@ -1004,8 +1004,9 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     }
     const int64_t grid = n < sm_count ? n : sm_count;
     const int64_t per_cta = (n + grid - 1) / grid;
-    static int force_tpb = -1;                       // development override: RDV_ROLLOUT_TPB = 256 | 384 | 448 | 512
-    if (force_tpb < 0) { const char *e = getenv("RDV_ROLLOUT_TPB"); force_tpb = e ? atoi(e) : 0; }
+    // development / test override of the CTA size: RDV_ROLLOUT_TPB = 256 | 384 | 448 | 512
+    const char *tpb_env = getenv("RDV_ROLLOUT_TPB");
+    const int force_tpb = tpb_env ? atoi(tpb_env) : 0;
     const int64_t max_tpb = force_tpb > 0 ? force_tpb : 512;
     const int64_t passes = (per_cta + max_tpb - 1) / max_tpb;
     const int64_t chunk = force_tpb > 0 ? force_tpb : (per_cta + passes - 1) / passes;

@@ -248,6 +248,23 @@ __constant__ double c_rk[26] = {
 // branch (ivp.py:710-728) evaluates the dense-output polynomial at x == 1, which equals y_new
 // up to ~1 ulp; y_new is used.  Returns accepted steps, or -1 on TOO_SMALL_STEP / non-finite
 // error norm (the reference raises there); y is left at the last accepted state.
+#ifndef RDV_CTRL_F32
+#define RDV_CTRL_F32 1
+#endif
+// ---------------------------------------------------------------------------------
+// Step-size controller arithmetic in float32 (RDV_CTRL_F32).
+//
+// The error norm, the scale vector, the step factor 0.9 err^-0.2 and select_initial_step only steer the
+// step size; the propagated state never sees them except through h.  One accepted step changes by
+// d(y_new)/dh * dh ~ 5 err/h * dh, i.e. a 1e-6 relative error in h (what float32 + fast log2/exp2 give) moves
+// the state by ~1e-14 -- five orders below the 1e-9 parity bar -- while the fp64 pipe, the bottleneck, is
+// relieved of ~18 % of its instructions (4 reciprocals, the norm and a pow per attempt; 7 reciprocals,
+// three norms and a pow per solve).  The error ESTIMATE itself (the E-weighted sum of the stages, a
+// cancellation) stays fp64.  The accept test err < 1 is re-evaluated in full fp64 whenever the float32
+// value lies within 1e-3 of the threshold, so accept / reject decisions are those of the fp64 controller.
+// ---------------------------------------------------------------------------------
+RDV_DEV float pow_neg_tenth_f32(float x) { return exp2f(-0.1f * __log2f(x)); }
+
 #ifndef RDV_RK_INLINE
 #define RDV_RK_INLINE 1
 #endif
@@ -266,6 +283,47 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 
     // ---- select_initial_step (order 4) ----
     double h_abs;
+#if RDV_CTRL_F32
+    {
+        float inv_sc[7], d0s = 0.0f, d1s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const float yi = (float)y[i];
+            inv_sc[i] = __frcp_rn(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
+            const float a = yi * inv_sc[i];
+            d0s = fmaf(a, a, d0s);
+        }
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const float a = (float)K[0][i] * inv_sc[i];
+            d1s = fmaf(a, a, d1s);
+        }
+        d0s *= (1.0f / 7.0f);
+        d1s *= (1.0f / 7.0f);                                // squares of the rms norms d0, d1
+        float h0f;
+        if (d0s < 1e-10f || d1s < 1e-10f) h0f = 1e-6f;
+        else h0f = 0.01f * sqrtf(__fdividef(d0s, d1s));
+        const double h0 = fmin((double)h0f, dt);
+        double y1[7], f1[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) y1[i] = fma(h0, K[0][i], y[i]);
+#pragma unroll
+        for (int i = NA; i < 7; ++i) y1[i] = y[i];
+        attitude_rhs<ISO>(y1, hw, b, f1);
+        float d2s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const float a = (float)(f1[i] - K[0][i]) * inv_sc[i];
+            d2s = fmaf(a, a, d2s);
+        }
+        const float inv_h0 = __frcp_rn((float)h0);
+        d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
+        float h1;
+        if (d1s <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0 * 1e-3f);
+        else h1 = pow_neg_tenth_f32(fminf(fmaxf(d1s, d2s), 1e30f) * 1e4f);   // (0.01/max(d1,d2))**(1/5)
+        h_abs = fmin(fmin(100.0 * h0, (double)h1), dt);
+    }
+#else
     {
         double inv_sc[7], d0s = 0.0, d1s = 0.0;
 #pragma unroll
@@ -304,6 +362,7 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
         else h1 = pow_neg_tenth(fmax(d1s, d2s) * 1e4);        // (0.01/max(d1,d2))**(1/5)
         h_abs = fmin(fmin(100.0 * h0, h1), dt);
     }
+#endif
 
     double t = 0.0;
     int accepted = 0;
@@ -354,14 +413,48 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 #pragma unroll
             for (int i = 0; i < NA; ++i) y_new[i] = ys[i];
             // ---- error norm: rms((K^T E) h / scale), scale = atol + max(|y|,|y_new|) rtol ----
+            double eh[NA];
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+                eh[i] = h * fma(K[6][i], RK_E7,
+                                fma(K[5][i], RK_E6,
+                                    fma(K[4][i], RK_E5, fma(K[3][i], RK_E4, fma(K[2][i], RK_E3, K[0][i] * RK_E1)))));
+#if RDV_CTRL_F32
+            float esf = 0.0f;
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const float m = (float)fmax(fabs(y[i]), fabs(y_new[i]));
+                const float q = __fdividef((float)eh[i], fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
+                esf = fmaf(q, q, esf);
+            }
+            esf *= (1.0f / 7.0f);                      // err_norm^2
+            if (!(esf < 1.0e30f)) return -1;           // NaN / inf: the reference shrinks h to failure
+            bool accept = esf < 1.0f;
+            if (fabsf(esf - 1.0f) < 1.0e-3f) {         // threshold region: decide with the fp64 norm
+                double es = 0.0;
+#pragma unroll
+                for (int i = 0; i < NA; ++i) {
+                    const double e = eh[i] * fast_rcp(fma(fmax(fabs(y[i]), fabs(y_new[i])), RK_RTOL, RK_ATOL));
+                    es = fma(e, e, es);
+                }
+                accept = es * (1.0 / 7.0) < 1.0;
+            }
+            // 0.9 err^-0.2, clamped where the controller's min / max saturate anyway
+            const float p = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
+            if (accept) {
+                float factor = fminf(10.0f, p);
+                if (rejected) factor = fminf(1.0f, factor);
+                h_abs *= (double)factor;
+                break;
+            }
+            h_abs *= (double)fmaxf(0.2f, p);
+            rejected = true;
+            ++n_rejected;
+#else
             double es = 0.0;
 #pragma unroll
             for (int i = 0; i < NA; ++i) {
-                double e = fma(K[6][i], RK_E7,
-                               fma(K[5][i], RK_E6,
-                                   fma(K[4][i], RK_E5, fma(K[3][i], RK_E4, fma(K[2][i], RK_E3, K[0][i] * RK_E1)))));
-                double sc = fma(fmax(fabs(y[i]), fabs(y_new[i])), RK_RTOL, RK_ATOL);
-                e = e * h * fast_rcp(sc);
+                const double e = eh[i] * fast_rcp(fma(fmax(fabs(y[i]), fabs(y_new[i])), RK_RTOL, RK_ATOL));
                 es = fma(e, e, es);
             }
             es *= (1.0 / 7.0);                         // err_norm^2
@@ -376,6 +469,7 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
             h_abs *= (es > 1.0e7) ? 0.2 : fmax(0.2, 0.9 * pow_neg_tenth(es));
             rejected = true;
             ++n_rejected;
+#endif
         }
         ++accepted;
         t = t_new;
@@ -386,178 +480,15 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 }
 
 // ---------------------------------------------------------------------------------
-// Lock-step form of the same solver for TWO bodies in one thread (chaser and target of one env).
+// Lock-step form of the same solver for TWO bodies in one thread (chaser and target of one env), for the
+// isotropic, torque-free case (the reference env: w is constant, only q moves).
 //
-// rk45_attitude above is a chain of dependent fp64 operations with at most NA-way instruction-level
-// parallelism, and one thread can keep only a fraction of the fp64 pipe busy with it.  Here every
-// phase (initial step, one attempted Dormand-Prince step, error control) is written branch-free for one
-// body and issued for both bodies back to back, so the two independent dependency chains interleave in
-// the instruction stream (2x ILP at no extra instructions).  The control flow of scipy's _step_impl
-// (accept / reject, the factor clamps, the rejected-step rule, TOO_SMALL_STEP) becomes predicated
-// updates; a body that has reached t = dt keeps stepping in the shadow without committing anything.
-// Arithmetic per body is identical to rk45_attitude, operation for operation.
-// ---------------------------------------------------------------------------------
-RDV_DEV double pow_neg_tenth_nb(double x)           // branch-free; x is clamped to [1e-30, 1e30]
-{
-    x = fmin(fmax(x, 1e-30), 1e30);
-    const float lf = __log2f((float)x);
-    double y = (double)exp2f(-0.1f * lf);
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4, y10 = y8 * y2;
-        y = fma(y * 0.1, fma(-x, y10, 1.0), y);
-    }
-    return y;
-}
-
-template <bool ISO>
-struct RkBody {
-    static constexpr int NA = ISO ? 4 : 7;
-    double y[7], hw[3], k0[NA];
-    double h_abs, t;
-    int accepted;
-    bool done, rejected, failed;
-};
-
-template <bool ISO>
-RDV_DEV void rk_begin(RkBody<ISO> &s, const double dt, const BodyConst &b)
-{
-    constexpr int NA = RkBody<ISO>::NA;
-    s.hw[0] = 0.5 * s.y[4]; s.hw[1] = 0.5 * s.y[5]; s.hw[2] = 0.5 * s.y[6];
-    attitude_rhs<ISO>(s.y, s.hw, b, s.k0);
-    // select_initial_step (scipy common.py:68-134), order 4
-    double inv_sc[7], d0s = 0.0, d1s = 0.0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        inv_sc[i] = fast_rcp(fma(fabs(s.y[i]), RK_RTOL, RK_ATOL));
-        const double a = s.y[i] * inv_sc[i];
-        d0s = fma(a, a, d0s);
-    }
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-        const double a = s.k0[i] * inv_sc[i];
-        d1s = fma(a, a, d1s);
-    }
-    d0s *= (1.0 / 7.0);
-    d1s *= (1.0 / 7.0);
-    const bool tiny = d0s < 1e-10 || d1s < 1e-10;
-    const double ratio = d0s * fast_rcp(tiny ? 1.0 : d1s);
-    double h0 = tiny ? 1e-6 : 0.01 * (ratio * fast_rsqrt(ratio));
-    h0 = fmin(h0, dt);
-    double y1[7], f1[NA];
-#pragma unroll
-    for (int i = 0; i < NA; ++i) y1[i] = fma(h0, s.k0[i], s.y[i]);
-#pragma unroll
-    for (int i = NA; i < 7; ++i) y1[i] = s.y[i];
-    attitude_rhs<ISO>(y1, s.hw, b, f1);
-    double d2s = 0.0;
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-        const double a = (f1[i] - s.k0[i]) * inv_sc[i];
-        d2s = fma(a, a, d2s);
-    }
-    const double inv_h0 = fast_rcp(h0);
-    d2s = d2s * (1.0 / 7.0) * inv_h0 * inv_h0;
-    const double h1 = (d1s <= 1e-30 && d2s <= 1e-30) ? fmax(1e-6, h0 * 1e-3) : pow_neg_tenth_nb(fmax(d1s, d2s) * 1e4);
-    s.h_abs = fmin(fmin(100.0 * h0, h1), dt);
-    s.t = 0.0;
-    s.accepted = 0;
-    s.done = s.rejected = s.failed = false;
-}
-
-// One iteration of the inner loop of _step_impl (scipy rk.py:111-179) with predicated commit.
-template <bool ISO>
-RDV_DEV void rk_attempt(RkBody<ISO> &s, const double dt, const BodyConst &b, int &n_rejected)
-{
-    constexpr int NA = RkBody<ISO>::NA;
-    const bool live = !s.done && !s.failed;
-    const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(s.t) + 1) - s.t);
-    bool failed = s.rejected && s.h_abs < min_step;               // TOO_SMALL_STEP after a rejection
-    double h_abs = s.rejected ? s.h_abs : fmax(s.h_abs, min_step);
-    double t_new = s.t + h_abs;
-    if (t_new - dt > 0.0) t_new = dt;
-    const double h = t_new - s.t;
-    h_abs = fabs(h);
-    double K1[NA], K2[NA], K3[NA], K4[NA], K5[NA], K6[NA], ys[7];
-    const double *K0 = s.k0, *y = s.y;
-    if (ISO) { ys[4] = y[4]; ys[5] = y[5]; ys[6] = y[6]; }
-#pragma unroll
-    for (int i = 0; i < NA; ++i) ys[i] = fma(K0[i] * RK_A21, h, y[i]);
-    attitude_rhs<ISO>(ys, s.hw, b, K1);
-#pragma unroll
-    for (int i = 0; i < NA; ++i) ys[i] = fma(fma(K1[i], RK_A32, K0[i] * RK_A31), h, y[i]);
-    attitude_rhs<ISO>(ys, s.hw, b, K2);
-#pragma unroll
-    for (int i = 0; i < NA; ++i) ys[i] = fma(fma(K2[i], RK_A43, fma(K1[i], RK_A42, K0[i] * RK_A41)), h, y[i]);
-    attitude_rhs<ISO>(ys, s.hw, b, K3);
-#pragma unroll
-    for (int i = 0; i < NA; ++i)
-        ys[i] = fma(fma(K3[i], RK_A54, fma(K2[i], RK_A53, fma(K1[i], RK_A52, K0[i] * RK_A51))), h, y[i]);
-    attitude_rhs<ISO>(ys, s.hw, b, K4);
-#pragma unroll
-    for (int i = 0; i < NA; ++i)
-        ys[i] = fma(fma(K4[i], RK_A65, fma(K3[i], RK_A64, fma(K2[i], RK_A63, fma(K1[i], RK_A62, K0[i] * RK_A61)))), h,
-                    y[i]);
-    attitude_rhs<ISO>(ys, s.hw, b, K5);
-#pragma unroll
-    for (int i = 0; i < NA; ++i)
-        ys[i] = fma(h, fma(K5[i], RK_B6, fma(K4[i], RK_B5, fma(K3[i], RK_B4, fma(K2[i], RK_B3, K0[i] * RK_B1)))), y[i]);
-    attitude_rhs<ISO>(ys, s.hw, b, K6);                            // FSAL row; ys is y_new
-    double es = 0.0;
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-        double e = fma(K6[i], RK_E7,
-                       fma(K5[i], RK_E6, fma(K4[i], RK_E5, fma(K3[i], RK_E4, fma(K2[i], RK_E3, K0[i] * RK_E1)))));
-        const double sc = fma(fmax(fabs(y[i]), fabs(ys[i])), RK_RTOL, RK_ATOL);
-        e = e * h * fast_rcp(sc);
-        es = fma(e, e, es);
-    }
-    es *= (1.0 / 7.0);                                             // err_norm^2
-    failed = failed || !(es < 1.0e300);                            // NaN / inf: the reference shrinks h to failure
-    const bool accept = es < 1.0;
-    // 0.9 err^-0.2, clamped where the min/max of the controller saturate anyway (10 below 3.5e-11, 0.2 above 1e7)
-    const double p = 0.9 * pow_neg_tenth_nb(fmin(fmax(es, 1e-12), 1e8));
-    double factor = accept ? fmin(10.0, p) : fmax(0.2, p);
-    if (accept && s.rejected) factor = fmin(1.0, factor);
-    const bool commit = live && !failed && accept;
-    if (live) {
-        s.failed = failed;
-        s.h_abs = failed ? s.h_abs : h_abs * factor;
-        s.rejected = !accept;
-        n_rejected += (!failed && !accept) ? 1 : 0;
-    }
-    if (commit) {
-#pragma unroll
-        for (int i = 0; i < NA; ++i) { s.y[i] = ys[i]; s.k0[i] = K6[i]; }
-        s.t = t_new;
-        s.accepted += 1;
-        s.done = t_new - dt >= 0.0;
-    }
-}
-
-// Both attitude solves of one env step (general bodies): the two branch-free state machines above, called
-// back to back.  Returns accepted steps of both bodies, or -1 on failure.
-template <bool ISO>
-RDV_DEV int rk45_attitude_pair(double (&ya)[7], double (&yb)[7], const double dt, const BodyConst &ba,
-                               const BodyConst &bb, int &n_rejected)
-{
-    RkBody<ISO> A, B;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) { A.y[i] = ya[i]; B.y[i] = yb[i]; }
-    rk_begin<ISO>(A, dt, ba);
-    rk_begin<ISO>(B, dt, bb);
-    while (!((A.done || A.failed) && (B.done || B.failed))) {
-        rk_attempt<ISO>(A, dt, ba, n_rejected);
-        rk_attempt<ISO>(B, dt, bb, n_rejected);
-    }
-#pragma unroll
-    for (int i = 0; i < 7; ++i) { ya[i] = A.y[i]; yb[i] = B.y[i]; }
-    return (A.failed || B.failed) ? -1 : A.accepted + B.accepted;
-}
-
-// ---------------------------------------------------------------------------------
-// The isotropic, torque-free case (the reference env: w is constant, only q moves) with the two
-// bodies interleaved STAGE BY STAGE in the source: "stage vector of body 0, stage vector of body 1,
+// rk45_attitude above is a chain of dependent fp64 operations with at most 4-way instruction-level
+// parallelism (dependent DFMA latency ~12 cycles); with <= 2 warps per SM sub-partition one thread keeps
+// only a fraction of the fp64 pipe busy with it.  Here the control flow of scipy's _step_impl (accept /
+// reject, the factor clamps, the rejected-step rule, TOO_SMALL_STEP) is written as predicated updates, a body
+// that has reached t = dt keeps stepping in the shadow without committing anything, and the two bodies are
+// interleaved STAGE BY STAGE in the source: "stage vector of body 0, stage vector of body 1,
 // right-hand side of body 0, right-hand side of body 1".  The two right-hand sides are independent
 // ~30-instruction dependency chains (dot product -> rsqrt -> Omega q) that sit next to each other in one
 // basic block, so the scheduler overlaps them; written as two whole solves one after the other the compiler
@@ -586,35 +517,34 @@ RDV_DEV int rk45_iso_pair(double (&ya)[7], double (&yb)[7], const double dt, int
         w[0][i] = ya[4 + i]; w[1][i] = yb[4 + i];
         hw[0][i] = 0.5 * w[0][i]; hw[1][i] = 0.5 * w[1][i];
     }
-    // ---- select_initial_step (scipy common.py:68-134) for both bodies ----
+    // ---- select_initial_step (scipy common.py:68-134) for both bodies; float32 controller arithmetic,
+    //      expression for expression the one of rk45_attitude (bit-identical step sizes) ----
     {
-        double inv_sc[2][4], d0s[2], d1s[2], h0[2], y1[2][4], f1[2][4];
+        float inv_sc[2][7], d0s[2], d1s[2];
+        double h0[2], y1[2][4], f1[2][4];
 #pragma unroll
         for (int b = 0; b < 2; ++b) rhs_iso(y[b], hw[b], K0[b]);
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            d0s[b] = 0.0; d1s[b] = 0.0;
+            d0s[b] = 0.0f; d1s[b] = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                inv_sc[b][i] = fast_rcp(fma(fabs(y[b][i]), RK_RTOL, RK_ATOL));
-                const double a = y[b][i] * inv_sc[b][i];
-                d0s[b] = fma(a, a, d0s[b]);
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {                       // the rate components only enter d0
-                const double a = w[b][i] * fast_rcp(fma(fabs(w[b][i]), RK_RTOL, RK_ATOL));
-                d0s[b] = fma(a, a, d0s[b]);
+            for (int i = 0; i < 7; ++i) {
+                const float yi = (float)(i < 4 ? y[b][i < 4 ? i : 0] : w[b][i < 4 ? 0 : i - 4]);
+                inv_sc[b][i] = __frcp_rn(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
+                const float a = yi * inv_sc[b][i];
+                d0s[b] = fmaf(a, a, d0s[b]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double a = K0[b][i] * inv_sc[b][i];
-                d1s[b] = fma(a, a, d1s[b]);
+                const float a = (float)K0[b][i] * inv_sc[b][i];
+                d1s[b] = fmaf(a, a, d1s[b]);
             }
-            d0s[b] *= (1.0 / 7.0);
-            d1s[b] *= (1.0 / 7.0);
-            const bool tiny = d0s[b] < 1e-10 || d1s[b] < 1e-10;
-            const double ratio = d0s[b] * fast_rcp(tiny ? 1.0 : d1s[b]);
-            h0[b] = fmin(tiny ? 1e-6 : 0.01 * (ratio * fast_rsqrt(ratio)), dt);
+            d0s[b] *= (1.0f / 7.0f);
+            d1s[b] *= (1.0f / 7.0f);
+            float h0f;
+            if (d0s[b] < 1e-10f || d1s[b] < 1e-10f) h0f = 1e-6f;
+            else h0f = 0.01f * sqrtf(__fdividef(d0s[b], d1s[b]));
+            h0[b] = fmin((double)h0f, dt);
 #pragma unroll
             for (int i = 0; i < 4; ++i) y1[b][i] = fma(h0[b], K0[b][i], y[b][i]);
         }
@@ -622,17 +552,18 @@ RDV_DEV int rk45_iso_pair(double (&ya)[7], double (&yb)[7], const double dt, int
         for (int b = 0; b < 2; ++b) rhs_iso(y1[b], hw[b], f1[b]);
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            double d2s = 0.0;
+            float d2s = 0.0f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double a = (f1[b][i] - K0[b][i]) * inv_sc[b][i];
-                d2s = fma(a, a, d2s);
+                const float a = (float)(f1[b][i] - K0[b][i]) * inv_sc[b][i];
+                d2s = fmaf(a, a, d2s);
             }
-            const double inv_h0 = fast_rcp(h0[b]);
-            d2s = d2s * (1.0 / 7.0) * inv_h0 * inv_h0;
-            const double h1 = (d1s[b] <= 1e-30 && d2s <= 1e-30) ? fmax(1e-6, h0[b] * 1e-3)
-                                                                  : pow_neg_tenth_nb(fmax(d1s[b], d2s) * 1e4);
-            h_abs[b] = fmin(fmin(100.0 * h0[b], h1), dt);
+            const float inv_h0 = __frcp_rn((float)h0[b]);
+            d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
+            float h1;
+            if (d1s[b] <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0[b] * 1e-3f);
+            else h1 = pow_neg_tenth_f32(fminf(fmaxf(d1s[b], d2s), 1e30f) * 1e4f);
+            h_abs[b] = fmin(fmin(100.0 * h0[b], (double)h1), dt);
             t[b] = 0.0;
         }
     }
@@ -674,26 +605,38 @@ RDV_DEV int rk45_iso_pair(double (&ya)[7], double (&yb)[7], const double dt, int
 #undef RDV_STAGE
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            double es = 0.0;
+            double eh[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                eh[i] = h[b] * fma(K6[b][i], RK_E7, fma(K5[b][i], RK_E6, fma(K4[b][i], RK_E5, fma(K3[b][i], RK_E4,
+                                   fma(K2[b][i], RK_E3, K0[b][i] * RK_E1)))));
+            float esf = 0.0f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                double e = fma(K6[b][i], RK_E7, fma(K5[b][i], RK_E6, fma(K4[b][i], RK_E5, fma(K3[b][i], RK_E4,
-                               fma(K2[b][i], RK_E3, K0[b][i] * RK_E1)))));
-                const double sc = fma(fmax(fabs(y[b][i]), fabs(ys[b][i])), RK_RTOL, RK_ATOL);
-                e = e * h[b] * fast_rcp(sc);
-                es = fma(e, e, es);
+                const float m = (float)fmax(fabs(y[b][i]), fabs(ys[b][i]));
+                const float q = __fdividef((float)eh[i], fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
+                esf = fmaf(q, q, esf);
             }
-            es *= (1.0 / 7.0);
+            esf *= (1.0f / 7.0f);
             const bool live = !done[b] && !failed[b];
-            const bool bad = fail_now[b] || !(es < 1.0e300);
-            const bool accept = es < 1.0;
-            const double p = 0.9 * pow_neg_tenth_nb(fmin(fmax(es, 1e-12), 1e8));
-            double factor = accept ? fmin(10.0, p) : fmax(0.2, p);
-            if (accept && rejected[b]) factor = fmin(1.0, factor);
+            const bool bad = fail_now[b] || !(esf < 1.0e30f);
+            bool accept = esf < 1.0f;
+            if (fabsf(esf - 1.0f) < 1.0e-3f) {         // threshold region: decide with the fp64 norm
+                double es = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double e = eh[i] * fast_rcp(fma(fmax(fabs(y[b][i]), fabs(ys[b][i])), RK_RTOL, RK_ATOL));
+                    es = fma(e, e, es);
+                }
+                accept = es * (1.0 / 7.0) < 1.0;
+            }
+            const float p = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
+            float factor = accept ? fminf(10.0f, p) : fmaxf(0.2f, p);
+            if (accept && rejected[b]) factor = fminf(1.0f, factor);
             const bool commit = live && !bad && accept;
             if (live) {
                 failed[b] = bad;
-                h_abs[b] = bad ? h_abs[b] : ha[b] * factor;
+                h_abs[b] = bad ? h_abs[b] : ha[b] * (double)factor;
                 rejected[b] = !accept;
                 n_rejected += (!bad && !accept) ? 1 : 0;
             }

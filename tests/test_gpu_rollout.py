@@ -112,3 +112,22 @@ def test_rollout_shard_invariance_and_edges():
         b.step(acts[k])
     assert rel_err(a.get_state().cpu().numpy(), b.get_state().cpu().numpy()) <= 1e-11
     assert (a.episode_index == 1).all()
+
+
+def test_rollout_launch_shapes_are_bit_identical(monkeypatch):
+    """The lock-step (<= 256 envs per CTA) and the sequential (larger CTAs) solvers, and every CTA size, give the
+    same bits: results cannot depend on the batch size or on how a batch is sharded over GPUs."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    n, K = 3000, 40
+    states, obs, stats = [], [], []
+    for tpb in ("256", "384", "448", "512"):
+        monkeypatch.setenv("RDV_ROLLOUT_TPB", tpb)
+        env = BatchedRendezvousEnv(n, seed=2, t_max=25)
+        env.reset()
+        out = env.rollout(K, action_seed=7, record_rewards=True)
+        states.append(env.get_state().clone()); obs.append(out["rewards"].clone()); stats.append(env.read_stats())
+    monkeypatch.delenv("RDV_ROLLOUT_TPB")
+    for k in range(1, 4):
+        assert torch.equal(states[0], states[k]) and torch.equal(obs[0], obs[k])
+        assert stats[0]["rk_accepted"] == stats[k]["rk_accepted"] and stats[0]["episodes"] == stats[k]["episodes"]
