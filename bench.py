@@ -56,7 +56,7 @@ def _peaks():
 class ClockSampler:
     """SM clock + throttle reasons during the timed region (pynvml; nvidia-smi as a fallback)."""
 
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.01):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
@@ -398,7 +398,7 @@ def _json_only_stdout():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=5000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", choices=("cuda", "reference"), default="cuda")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
