@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 9
+#define RDV_ABI_VERSION 10
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -156,7 +156,16 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
  * place).  This is the rollout-collection loop of SB3's collect_rollouts around env.step
  * (main.py:114 -> OnPolicyAlgorithm.collect_rollouts) with the action taken from `actions` or drawn on the
  * device.  The per-step results a rollout buffer needs are optional outputs. */
-enum { RDV_ACTIONS_F32 = 0, RDV_ACTIONS_F64 = 1, RDV_ACTIONS_PHILOX = 2 };
+/* fp32 tanh MLP obs[17] -> hidden -> hidden -> action[6] of an SB3 MlpPolicy (main.py:39-48), deterministic mean
+ * clipped to [-1,1] (model.predict, monte_carlo.py:128-133).  Weights are row-major [out][in] as in torch.nn.Linear. */
+typedef struct RdvPolicy {
+    const float *w0, *b0;    /* [H][17], [H] */
+    const float *w1, *b1;    /* [H][H],  [H] */
+    const float *w2, *b2;    /* [6][H],  [6] */
+    int32_t hidden;          /* H, must be 64 */
+    int32_t reserved;
+} RdvPolicy;
+enum { RDV_ACTIONS_F32 = 0, RDV_ACTIONS_F64 = 1, RDV_ACTIONS_PHILOX = 2, RDV_ACTIONS_POLICY = 3 };
 typedef struct RdvRolloutIO {
     int32_t  steps;          /* K                                                                          */
     int32_t  action_source;  /* RDV_ACTIONS_*                                                              */
@@ -165,12 +174,13 @@ typedef struct RdvRolloutIO {
     const void *actions;     /* [K][n][6] float32 / float64 for the tensor sources                         */
     uint64_t action_seed;    /* RDV_ACTIONS_PHILOX: U(-1,1) fp64 actions from Philox(action_seed; global   */
     int64_t  step_base;      /*   env id, step_base + k): 6 draws per env-step                             */
-    double  *actions_out;    /* nullable [K][n][6]: the Philox actions that were applied                   */
+    double  *actions_out;    /* nullable [K][n][6]: the applied Philox (float64) or policy (float32!) actions */
     float   *obs;            /* [n][17] observation after the last step (post-reset for finished envs)     */
     double  *rewards;        /* nullable [K][n]                                                            */
     uint8_t *dones;          /* nullable [K][n]                                                            */
     float   *obs_steps;      /* nullable [K][n][17] observation returned by every step                     */
     double  *stats;          /* nullable [RDV_NSTATS] device accumulator                                   */
+    RdvPolicy policy;        /* RDV_ACTIONS_POLICY: a = clip(actor(obs)), evaluated in the launch (tensor cores) */
 } RdvRolloutIO;
 int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, int64_t n, uint64_t seed,
                 int64_t env_offset, void *cuda_stream);
@@ -206,13 +216,7 @@ int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n
 /* -- fused policy (model.predict of an SB3 MlpPolicy, monte_carlo.py:128-133) ------------------- */
 /* fp32 tanh MLP obs[17] -> hidden -> hidden -> action[6], deterministic mean clipped to [-1,1].
  * Weights are row-major [out][in] as in torch.nn.Linear. */
-typedef struct RdvPolicy {
-    const float *w0, *b0;    /* [H][17], [H] */
-    const float *w1, *b1;    /* [H][H],  [H] */
-    const float *w2, *b2;    /* [6][H],  [6] */
-    int32_t hidden;          /* H, must be 64 */
-    int32_t reserved;
-} RdvPolicy;
+
 int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
 
 /* Measured-peak helper for the roofline: runs `iters` dependent-chain-free DFMA per thread on

@@ -21,9 +21,9 @@ CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200.so")   # env: A/B experiments
 SOURCES = ("rdv_b200.cu",)
-HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh")
+HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh", "rdv_policy.cuh")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -85,23 +85,23 @@ class RdvStepIO(C.Structure):
     ]
 
 
-class RdvRolloutIO(C.Structure):
-    _fields_ = [
-        ("steps", C.c_int32), ("action_source", C.c_int32), ("auto_reset", C.c_int32), ("reserved", C.c_int32),
-        ("actions", C.c_void_p), ("action_seed", C.c_uint64), ("step_base", C.c_int64),
-        ("actions_out", C.c_void_p), ("obs", C.c_void_p), ("rewards", C.c_void_p), ("dones", C.c_void_p),
-        ("obs_steps", C.c_void_p), ("stats", C.c_void_p),
-    ]
-
-
-ACTIONS_F32, ACTIONS_F64, ACTIONS_PHILOX = 0, 1, 2
-
-
 class RdvPolicy(C.Structure):
     _fields_ = [
         ("w0", C.c_void_p), ("b0", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p),
         ("w2", C.c_void_p), ("b2", C.c_void_p), ("hidden", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class RdvRolloutIO(C.Structure):
+    _fields_ = [
+        ("steps", C.c_int32), ("action_source", C.c_int32), ("auto_reset", C.c_int32), ("reserved", C.c_int32),
+        ("actions", C.c_void_p), ("action_seed", C.c_uint64), ("step_base", C.c_int64),
+        ("actions_out", C.c_void_p), ("obs", C.c_void_p), ("rewards", C.c_void_p), ("dones", C.c_void_p),
+        ("obs_steps", C.c_void_p), ("stats", C.c_void_p), ("policy", RdvPolicy),
+    ]
+
+
+ACTIONS_F32, ACTIONS_F64, ACTIONS_PHILOX, ACTIONS_POLICY = 0, 1, 2, 3
 
 
 # name -> (restype, argtypes); every symbol include/rdv_b200.h declares

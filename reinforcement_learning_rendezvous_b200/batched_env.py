@@ -148,11 +148,13 @@ class BatchedRendezvousEnv:
 
     def rollout(self, steps: int, actions: Optional[torch.Tensor] = None, action_seed: Optional[int] = None,
                 step_base: int = 0, record_rewards: bool = False, record_dones: bool = False,
-                record_obs: bool = False, record_actions: bool = False) -> dict:
+                record_obs: bool = False, record_actions: bool = False, policy=None) -> dict:
         """``steps`` consecutive env steps in ONE kernel launch (state stays in registers, finished envs restart
         in place when ``auto_reset``).  Actions come from ``actions`` ([steps, N, 6] float32/float64 on the device) or,
         when it is None, from the device Philox stream ``(action_seed; global env id, step_base + k)`` as U(-1,1) fp64
-        draws -- the "random actions" workload.  Returns a dict with ``obs`` (final observation, f32 [N,17]) and the
+        draws -- the "random actions" workload -- or from ``policy`` (an :class:`MlpPolicy`): the deterministic actor
+        output ``clip(pi(obs), -1, 1)`` evaluated inside the launch on the tensor cores from the observation the
+        previous step returned (closed loop, float32 actions).  Returns a dict with ``obs`` (final observation, f32 [N,17]) and the
         requested per-step records (``rewards`` f64 [steps,N], ``dones`` u8 [steps,N], ``obs_steps`` f32 [steps,N,17],
         ``actions`` f64 [steps,N,6] for Philox actions).  Asynchronous on the current stream."""
         steps = int(steps)
@@ -167,16 +169,20 @@ class BatchedRendezvousEnv:
             actions = actions.contiguous()
             source = N.ACTIONS_F64 if actions.dtype == torch.float64 else N.ACTIONS_F32
             esz = 8 if actions.dtype == torch.float64 else 4
+        elif policy is not None:
+            if policy.device != dev:
+                raise ValueError("policy and env live on different devices")
+            source, esz = N.ACTIONS_POLICY, 0
         else:
             if action_seed is None:
-                raise ValueError("give either an actions tensor or an action_seed for device-generated actions")
+                raise ValueError("give an actions tensor, an action_seed (device-generated actions) or a policy")
             source, esz = N.ACTIONS_PHILOX, 0
         out = {"obs": self.obs}
         rew = torch.empty((steps, n), dtype=torch.float64, device=dev) if record_rewards else None
         don = torch.empty((steps, n), dtype=torch.uint8, device=dev) if record_dones else None
         obs_steps = torch.empty((steps, n, N.OBS_DIM), dtype=torch.float32, device=dev) if record_obs else None
-        act_out = torch.empty((steps, n, N.ACT_DIM), dtype=torch.float64, device=dev) \
-            if (record_actions and actions is None) else None
+        act_out = torch.empty((steps, n, N.ACT_DIM), dtype=torch.float32 if policy is not None else torch.float64,
+                              device=dev) if (record_actions and actions is None) else None
         if len(self.groups) > 1 and (rew is not None or don is not None or obs_steps is not None or act_out is not None
                                      or actions is not None):
             raise NotImplementedError("per-step records / tensor actions with param_batches: use step()")
@@ -191,11 +197,12 @@ class BatchedRendezvousEnv:
                     self.obs.data_ptr() + g.lo * N.OBS_DIM * 4,
                     rew.data_ptr() if rew is not None else None, don.data_ptr() if don is not None else None,
                     obs_steps.data_ptr() if obs_steps is not None else None,
-                    self.stats.data_ptr() if self.stats is not None else None)
+                    self.stats.data_ptr() if self.stats is not None else None,
+                    policy._c if policy is not None else N.RdvPolicy())
                 st = self._state_of(g)
                 N.check(self.lib.rdv_rollout(C.byref(g.params), C.byref(st), C.byref(io), g.n, self.seed,
                                              self.env_offset + g.lo, stream), "rdv_rollout")
-        self._keepalive = actions
+        self._keepalive = (actions, policy)
         if rew is not None:
             out["rewards"] = rew
         if don is not None:

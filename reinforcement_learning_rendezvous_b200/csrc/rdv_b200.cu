@@ -11,6 +11,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include "rdv_step.cuh"
+#include "rdv_policy.cuh"
 
 namespace rdv {
 
@@ -516,12 +517,20 @@ step_kernel_env(const __grid_constant__ RdvParams P, const RdvState S, const Rdv
 // at a barrier every step: the step is ~60 KB of straight-line code, and warps that drift apart thrash the
 // instruction cache (measured: 58 % hit rate and 3.1 of 6.2 stall cycles per instruction on "no instruction"
 // with four independent 64-thread CTAs per SM; in-phase warps run the same workload 1.7x faster).
-template <bool ISO, bool CLOSED, int TPB_>
+// POLICY: the action of every step is the deterministic output of the SB3 MlpPolicy actor evaluated by the warp on
+// the tensor cores (rdv_policy.cuh) from the observation the previous step produced.
+template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false>
 __global__ void __launch_bounds__(TPB_, 1)
-rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const RdvRolloutIO io, const int64_t n,
-               const uint64_t seed, const int64_t env_offset)
+rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __grid_constant__ RdvRolloutIO io,
+               const int64_t n, const uint64_t seed, const int64_t env_offset)
 {
     constexpr int NW = TPB_ / 32;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    PolicyShared *ps = reinterpret_cast<PolicyShared *>(dyn_smem);
+    if (POLICY) {
+        policy_load(io.policy, *ps);
+        __syncthreads();
+    }
     __shared__ __align__(16) float s_obs[NW][32 * RDV_OBS_DIM];
     __shared__ double s_stats[NW][RDV_NSTATS];
     __shared__ double s_team[NW][4][RDV_TEAM_ROW];
@@ -560,7 +569,19 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const RdvR
             // ---- action ----
             ActionTerms t;
             const int64_t row = (int64_t)k * n + i;
-            if (src == RDV_ACTIONS_F32) {
+            if (POLICY) {
+                float *stage = s_obs[warp];
+#pragma unroll
+                for (int j = 0; j < RDV_OBS_DIM; ++j) stage[lane * RDV_OBS_DIM + j] = ov[j];
+                __syncwarp();
+                float a[RDV_ACT_DIM];
+                policy_forward_warp(*ps, stage, stage, a);
+                if (io.actions_out && active) {
+                    float2 *op = reinterpret_cast<float2 *>(reinterpret_cast<float *>(io.actions_out) + 6 * row);
+                    op[0] = make_float2(a[0], a[1]); op[1] = make_float2(a[2], a[3]); op[2] = make_float2(a[4], a[5]);
+                }
+                ingest_action_f32(P, a, c, t);
+            } else if (src == RDV_ACTIONS_F32) {
                 const float2 *ap = reinterpret_cast<const float2 *>(static_cast<const float *>(io.actions) + 6 * row);
                 const float2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
                 const float a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
@@ -982,9 +1003,14 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     if (!p || !io || !io->obs) return RDV_ERR_NULL;
     int rc = check_state(s, n);
     if (rc) return rc;
-    if (io->steps < 0 || io->action_source < 0 || io->action_source > 2) return RDV_ERR_SIZE;
+    if (io->steps < 0 || io->action_source < 0 || io->action_source > RDV_ACTIONS_POLICY) return RDV_ERR_SIZE;
     if (io->auto_reset != 0 && io->auto_reset != 1) return RDV_ERR_SIZE;
-    if (io->action_source != RDV_ACTIONS_PHILOX && !io->actions) return RDV_ERR_NULL;
+    const bool policy = io->action_source == RDV_ACTIONS_POLICY;
+    if (policy) {
+        const RdvPolicy *pi = &io->policy;
+        if (!pi->w0 || !pi->b0 || !pi->w1 || !pi->b1 || !pi->w2 || !pi->b2) return RDV_ERR_NULL;
+        if (pi->hidden != PI_H) return RDV_ERR_UNSUPPORTED;
+    } else if (io->action_source != RDV_ACTIONS_PHILOX && !io->actions) return RDV_ERR_NULL;
     if (((uintptr_t)io->actions & (io->action_source == RDV_ACTIONS_F64 ? 15 : 7)) || ((uintptr_t)io->actions_out & 15) ||
         ((uintptr_t)io->obs & 3) || ((uintptr_t)io->rewards & 7))
         return RDV_ERR_ALIGN;
@@ -1016,9 +1042,28 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     else if (chunk <= 384) RDV_LAUNCH_R(ISO_, CL_, 384);       \
     else if (chunk <= 448) RDV_LAUNCH_R(ISO_, CL_, 448);       \
     else RDV_LAUNCH_R(ISO_, CL_, 512);
-    if (closed) { RDV_PICK_R(true, true) }
+#define RDV_LAUNCH_P(T_)                                                                                          \
+    {                                                                                                             \
+        static bool attr_done = false;                                                                            \
+        if (!attr_done) {                                                                                         \
+            if (cudaFuncSetAttribute(rollout_kernel<true, false, T_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)sizeof(PolicyShared)) != cudaSuccess) return RDV_ERR_CUDA;              \
+            attr_done = true;                                                                                     \
+        }                                                                                                         \
+        rollout_kernel<true, false, T_, true><<<(unsigned)grid, T_, sizeof(PolicyShared), st>>>(*p, *s, *io, n, seed, \
+                                                                                                env_offset);      \
+    }
+    if (policy) {
+        if (!iso || closed) return RDV_ERR_UNSUPPORTED;      // the fused policy is built for the reference's env
+        if (chunk <= 256) RDV_LAUNCH_P(256)
+        else if (chunk <= 384) RDV_LAUNCH_P(384)
+        else if (chunk <= 448) RDV_LAUNCH_P(448)
+        else RDV_LAUNCH_P(512)
+    }
+    else if (closed) { RDV_PICK_R(true, true) }
     else if (iso) { RDV_PICK_R(true, false) }
     else RDV_LAUNCH_R(false, false, 256);
+#undef RDV_LAUNCH_P
 #undef RDV_PICK_R
 #undef RDV_LAUNCH_R
     return launch_status();

@@ -131,3 +131,88 @@ def test_rollout_launch_shapes_are_bit_identical(monkeypatch):
     for k in range(1, 4):
         assert torch.equal(states[0], states[k]) and torch.equal(obs[0], obs[k])
         assert stats[0]["rk_accepted"] == stats[k]["rk_accepted"] and stats[0]["episodes"] == stats[k]["episodes"]
+
+
+def _policy():
+    import os
+    from helpers import GOLDEN
+    from reinforcement_learning_rendezvous_b200 import MlpPolicy
+    return MlpPolicy.load(os.path.join(GOLDEN, "policy.npz"))
+
+
+def test_fused_policy_rollout_matches_policy_kernel_and_step():
+    """Closed-loop rollout with the actor evaluated inside the launch (3xTF32 tensor-core MLP) vs the same loop
+    assembled from rdv_policy_forward (fp32 FFMA) + rdv_step.  Actions agree to fp32 rounding; the closed loops
+    are compared while that difference has not been amplified (12 steps) and statistically afterwards."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    pol = _policy()
+    mc = golden_mc()
+    n, K = 1000, 60
+    ics = mc["ic_raw"].copy()
+    ics[:, 6:10] /= np.linalg.norm(ics[:, 6:10], axis=1, keepdims=True)
+    ics[:, 13:17] /= np.linalg.norm(ics[:, 13:17], axis=1, keepdims=True)
+    kw = dict(dt=1, t_max=60, rc0_range=0, vc0_range=0, qc0_range=0, wc0_range=0, qt0_range=0, wt0_range=0)
+    a = BatchedRendezvousEnv(n, auto_reset=False, **kw)
+    b = BatchedRendezvousEnv(n, auto_reset=False, **kw)
+    for e in (a, b):
+        e.reset()
+        e.set_state(ics, reset_counters=False)
+    out = a.rollout(K, policy=pol, record_actions=True, record_obs=True, record_rewards=True, record_dones=True)
+    obs = b.observe()
+    alive = torch.ones(n, dtype=torch.bool, device=b.device)
+    max_act = 0.0
+    for k in range(K):
+        act = pol.forward(obs)
+        if k < 12:
+            max_act = max(max_act, float((out["actions"][k] - act)[alive].abs().max()))
+            assert float((out["obs_steps"][k - 1] - obs)[alive].abs().max()) < 2e-5 if k else True
+        obs_k, rew, done = b.step(act)
+        obs = obs_k.clone()
+        alive &= ~done.bool()
+    assert max_act < 2e-5, max_act
+    # every recorded action is the actor's output for the observation the kernel saw (open-loop check, all steps)
+    prev = torch.cat([a_obs0(ics, kw)[None], out["obs_steps"][:-1]])
+    worst = 0.0
+    for k in range(0, K, 7):
+        worst = max(worst, float((pol.forward(prev[k].contiguous()) - out["actions"][k]).abs().max()))
+    assert worst < 5e-6, worst
+    # same episodes, statistically: first-done step of every env
+    first_a = torch.where(out["dones"].bool().any(0), out["dones"].bool().float().argmax(0), torch.full((n,), K, device=a.device))
+    assert (first_a < K).float().mean() > 0.5
+
+
+def golden_mc():
+    from helpers import golden
+    return golden("mc.npz")
+
+
+def a_obs0(ics, kw):
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    e = BatchedRendezvousEnv(len(ics), auto_reset=False, **kw)
+    e.reset()
+    e.set_state(ics, reset_counters=False)
+    return e.observe()
+
+
+def test_fused_policy_monte_carlo_success_rate():
+    """The published Monte-Carlo experiment as ONE launch: 1000 initial conditions, 60 closed-loop steps with the
+    shipped policy; success and collision counts of the published workbook (545 / 166) within +-5."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    pol = _policy()
+    mc = golden_mc()
+    ics = mc["ic_raw"].copy()
+    ics[:, 6:10] /= np.linalg.norm(ics[:, 6:10], axis=1, keepdims=True)
+    ics[:, 13:17] /= np.linalg.norm(ics[:, 13:17], axis=1, keepdims=True)
+    env = BatchedRendezvousEnv(1000, auto_reset=False, dt=1, t_max=60, rc0_range=0, vc0_range=0, qc0_range=0,
+                               wc0_range=0, qt0_range=0, wt0_range=0)
+    env.reset()
+    env.set_state(ics, reset_counters=False)
+    out = env.rollout(60, policy=pol, record_dones=True)
+    done = out["dones"].bool()
+    ep_len = torch.where(done.any(0), done.float().argmax(0) + 1, torch.full((1000,), 60, device=env.device))
+    same_len = (ep_len.cpu().numpy() == mc["workbook_ep_len"]).mean()
+    assert same_len > 0.985, same_len
+    st = env.read_stats()
+    assert st["failures"] == 0
