@@ -320,6 +320,27 @@ def run_cuda(args):
                 "roofline_frac_fp64": f_step * n / (step_ms / KS * 1e-3) / 1e12 / fp64_peak,
                 "actions": f"fp64 U(-1,1), pre-generated {RING}-step device ring ({RING * n * 48 / 1e6:.0f} MB > L2)"}
 
+    # ---------------- closed-loop rollouts with the shipped policy fused into the launch (tensor-core MLP) --------
+    policy_rollout = None
+    pol_path = os.path.join(ROOT, "tests", "golden", "policy.npz")
+    if os.path.exists(pol_path) and not closed:
+        from reinforcement_learning_rendezvous_b200 import MlpPolicy
+        pol = MlpPolicy.load(pol_path, device=dev)
+        env.rollout(KL, policy=pol)
+        KP = min(K, 4 * KL)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        p0.record()
+        for j in range(KP // KL):
+            env.rollout(KL, policy=pol)
+        p1.record()
+        barrier()
+        pms = max_over_ranks(p0.elapsed_time(p1))
+        policy_rollout = {"value": world * n * (KP // KL) * KL / (pms * 1e-3), "unit": UNIT,
+                          "ms_per_step": pms / ((KP // KL) * KL), "steps": (KP // KL) * KL,
+                          "policy": "SB3 MlpPolicy actor 17-64-64-6 tanh (models/mlp_model_best weights), deterministic, "
+                                    "3xTF32 mma.sync inside rollout_kernel"}
+
     # ---------------- end-to-end leg: numpy actions in, numpy results out, through the VecEnv ----------------
     del env
     venv = RendezvousVecEnv(n, device=dev, seed=args.seed, env_offset=rank * n, integrator=args.integrator)
@@ -378,6 +399,7 @@ def run_cuda(args):
                                   "16-double statistics all-reduce per rollout"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": len(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "step_api": step_api,
+        "policy_rollout": policy_rollout,
         "episode_stats": {"episodes": stats["episodes"], "mean_length": stats["length_sum"] / max(stats["episodes"], 1),
                           "success_rate": stats["succeeded"] / max(stats["episodes"], 1),
                           "rk_rejected": stats["rk_rejected"], "failures": stats["failures"]},

@@ -8,6 +8,7 @@ Public surface (mirrors the reference):
 * ``make_env`` / ``copy_env`` factory with the reference signature (utils/environment_utils.py)
 * ``MlpPolicy``               fused fp32 policy forward (model.predict, monte_carlo.py:128-133)
 * ``evaluate`` / ``evaluate_batch``  Monte-Carlo evaluator (monte_carlo.py:94-207)
+* ``ppo.PPO``                 device-tensor PPO loop with main.py's hyper-parameters (main.py:39-48, :114-118)
 
 Importing the package needs neither a GPU nor the built library; using it does.  There is
 no CPU fallback.

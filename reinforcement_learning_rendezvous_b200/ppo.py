@@ -1,0 +1,211 @@
+"""PPO training loop on device tensors -- what ``main.py`` does through Stable-Baselines3
+(/root/reference/main.py:39-48, :114-118: ``PPO(MlpPolicy, lr 2e-3, batch_size 128, n_epochs 40, clip_range 0.25,
+activation Tanh)`` with SB3's defaults ``gamma 0.99, gae_lambda 0.95, ent_coef 0, vf_coef 0.5, max_grad_norm 0.5,
+normalize_advantage``), for the case where SB3 is not installed (it is not part of this image) or its host-side
+numpy rollout buffer is the bottleneck.  With SB3 present, ``make_vec_env`` + ``stable_baselines3.PPO`` works as
+in the reference; this module keeps every rollout tensor on the GPU instead:
+
+* collection: obs -> actor/critic (torch) -> Gaussian sample -> clip -> ``BatchedRendezvousEnv.step`` (CUDA kernels)
+* GAE(lambda) and the clipped-surrogate update in torch autograd (the optimiser is library code, not the hot path)
+* ``evaluate`` = the callback's deterministic evaluation (custom/custom_callbacks.py:427-475) as ONE fused
+  policy rollout (``rollout(policy=...)``), best model kept like ``CustomCallback`` (:477-493).
+
+The network has SB3's ``MlpPolicy`` layout and state-dict keys, so a trained model loads into
+:class:`~reinforcement_learning_rendezvous_b200.policy.MlpPolicy` (and into SB3) unchanged.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from .batched_env import BatchedRendezvousEnv
+from .policy import MlpPolicy
+
+
+class _Extractor(nn.Module):
+    def __init__(self, obs_dim, hidden):
+        super().__init__()
+        self.policy_net = nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh())
+        self.value_net = nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh())
+
+
+class ActorCritic(nn.Module):
+    """SB3 ``ActorCriticPolicy`` with ``net_arch=[64, 64]`` for pi and vf, Tanh, orthogonal init, state-independent
+    ``log_std`` -- same parameter names as the SB3 checkpoint (``mlp_extractor.policy_net.0.weight`` ...)."""
+
+    def __init__(self, obs_dim=17, act_dim=6, hidden=64, log_std_init=0.0):
+        super().__init__()
+        self.mlp_extractor = _Extractor(obs_dim, hidden)
+        self.action_net = nn.Linear(hidden, act_dim)
+        self.value_net = nn.Linear(hidden, 1)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+        for module, gain in ((self.mlp_extractor, np.sqrt(2)), (self.action_net, 0.01), (self.value_net, 1.0)):
+            for m in module.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain=gain)
+                    nn.init.zeros_(m.bias)
+
+    def forward(self, obs):
+        mean = self.action_net(self.mlp_extractor.policy_net(obs))
+        value = self.value_net(self.mlp_extractor.value_net(obs)).squeeze(-1)
+        return mean, value
+
+    def distribution(self, mean):
+        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean))
+
+    def to_mlp_policy(self, device) -> MlpPolicy:
+        sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
+        return MlpPolicy(sd, device=device)
+
+
+@dataclass
+class PPOConfig:
+    n_steps: int = 16                 # per env and iteration (the reference: 2048 with ONE env)
+    batch_size: int = 8192            # the reference: 128 with 2048-sample rollouts
+    n_epochs: int = 10                # the reference: 40
+    learning_rate: float = 2e-3       # main.py:42
+    clip_range: float = 0.25          # main.py:45
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    ent_coef: float = 0.0
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    normalize_advantage: bool = True
+    n_evals: int = 50                 # custom_callbacks.py: n_evals
+    seed: int = 0
+    log: list = field(default_factory=list)
+
+
+class PPO:
+    def __init__(self, env: BatchedRendezvousEnv, config: Optional[PPOConfig] = None, policy: Optional[ActorCritic] = None):
+        if not env.auto_reset:
+            raise ValueError("training needs an auto-resetting env")
+        self.env, self.cfg = env, config or PPOConfig()
+        self.device = env.device
+        torch.manual_seed(self.cfg.seed)
+        self.policy = (policy or ActorCritic()).to(self.device)
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
+        n, T = env.num_envs, self.cfg.n_steps
+        dev = self.device
+        self.buf_obs = torch.empty((T, n, 17), dtype=torch.float32, device=dev)
+        self.buf_act = torch.empty((T, n, 6), dtype=torch.float32, device=dev)
+        self.buf_logp = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.buf_val = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.buf_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.buf_done = torch.empty((T, n), dtype=torch.bool, device=dev)
+        self.obs = env.reset().clone()
+        self.episode_start = torch.ones(n, dtype=torch.bool, device=dev)
+        self.num_timesteps = 0
+        self.best_eval = -float("inf")
+        self.best_state = None
+        kw = {k: v for k, v in env.ctor_kwargs.items()}
+        self.eval_env = BatchedRendezvousEnv(self.cfg.n_evals, device=dev, seed=env.seed + 12345, auto_reset=False, **kw)
+
+    # -- rollout collection (OnPolicyAlgorithm.collect_rollouts) ------------------------------------------------
+    @torch.no_grad()
+    def collect(self):
+        env, T = self.env, self.cfg.n_steps
+        starts = torch.empty((T, env.num_envs), dtype=torch.bool, device=self.device)
+        for t in range(T):
+            mean, value = self.policy(self.obs)
+            dist = self.policy.distribution(mean)
+            action = dist.sample()
+            self.buf_obs[t], self.buf_act[t] = self.obs, action
+            self.buf_logp[t], self.buf_val[t] = dist.log_prob(action).sum(-1), value
+            starts[t] = self.episode_start
+            obs, rew, done = env.step(action.clamp(-1.0, 1.0).contiguous())       # SB3 clips to the Box before step
+            self.buf_rew[t], self.buf_done[t] = rew.float(), done.bool()
+            self.obs = obs.clone()
+            self.episode_start = done.bool()
+        _, last_value = self.policy(self.obs)
+        # GAE(lambda) (RolloutBuffer.compute_returns_and_advantage); no time-limit bootstrapping, like the reference
+        adv = torch.zeros_like(self.buf_rew)
+        last = torch.zeros(env.num_envs, device=self.device)
+        for t in reversed(range(T)):
+            next_value = last_value if t == T - 1 else self.buf_val[t + 1]
+            not_done = (~self.buf_done[t]).float()
+            delta = self.buf_rew[t] + self.cfg.gamma * next_value * not_done - self.buf_val[t]
+            last = delta + self.cfg.gamma * self.cfg.gae_lambda * not_done * last
+            adv[t] = last
+        self.num_timesteps += T * env.num_envs
+        return adv, adv + self.buf_val
+
+    # -- clipped-surrogate update (PPO.train) --------------------------------------------------------------------
+    def update(self, adv, ret):
+        cfg = self.cfg
+        N = adv.numel()
+        obs, act = self.buf_obs.reshape(N, 17), self.buf_act.reshape(N, 6)
+        old_logp, adv, ret = self.buf_logp.reshape(N), adv.reshape(N), ret.reshape(N)
+        stats = {}
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(N, device=self.device)
+            for s in range(0, N, cfg.batch_size):
+                idx = perm[s:s + cfg.batch_size]
+                mean, value = self.policy(obs[idx])
+                dist = self.policy.distribution(mean)
+                logp = dist.log_prob(act[idx]).sum(-1)
+                a = adv[idx]
+                if cfg.normalize_advantage and a.numel() > 1:
+                    a = (a - a.mean()) / (a.std() + 1e-8)
+                ratio = (logp - old_logp[idx]).exp()
+                pg_loss = -torch.min(a * ratio, a * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+                v_loss = nn.functional.mse_loss(ret[idx], value)
+                ent_loss = -dist.entropy().sum(-1).mean()
+                loss = pg_loss + cfg.ent_coef * ent_loss + cfg.vf_coef * v_loss
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+                self.optimizer.step()
+                stats = {"pg_loss": float(pg_loss.detach()), "value_loss": float(v_loss.detach()),
+                         "entropy": float(-ent_loss.detach())}
+        return stats
+
+    # -- deterministic evaluation (CustomCallback._on_rollout_start / evaluate_policy) --------------------------
+    @torch.no_grad()
+    def evaluate(self) -> dict:
+        env = self.eval_env
+        env.reset()
+        steps = int(env.params.done_steps)
+        out = env.rollout(steps, policy=self.policy.to_mlp_policy(self.device), record_rewards=True, record_dones=True)
+        done = out["dones"].bool()
+        first = torch.where(done.any(0), done.float().argmax(0), torch.full_like(done[0], steps - 1, dtype=torch.long))
+        mask = torch.arange(steps, device=self.device)[:, None] <= first[None, :]
+        returns = (out["rewards"] * mask).sum(0)
+        return {"mean_return": float(returns.mean()), "mean_length": float((first + 1).float().mean()),
+                "success_rate": float((env.success > 0).float().mean()), "collision_rate": float((env.collided > 0).float().mean())}
+
+    def learn(self, total_timesteps: int, eval_every: int = 1, verbose: bool = False):
+        it = 0
+        while self.num_timesteps < total_timesteps:
+            if eval_every and it % eval_every == 0:
+                ev = self.evaluate()
+                if ev["mean_return"] > self.best_eval:                      # CustomCallback: keep the best model
+                    self.best_eval = ev["mean_return"]
+                    self.best_state = {k: v.detach().clone() for k, v in self.policy.state_dict().items()}
+            else:
+                ev = {}
+            t0 = time.perf_counter()
+            adv, ret = self.collect()
+            torch.cuda.synchronize(self.device)
+            t1 = time.perf_counter()
+            st = self.update(adv, ret)
+            torch.cuda.synchronize(self.device)
+            t2 = time.perf_counter()
+            row = dict(iteration=it, timesteps=self.num_timesteps, collect_s=t1 - t0, update_s=t2 - t1,
+                       collect_steps_per_s=self.cfg.n_steps * self.env.num_envs / (t1 - t0),
+                       mean_step_reward=float(self.buf_rew.mean()), **st, **{"eval_" + k: v for k, v in ev.items()})
+            self.cfg.log.append(row)
+            if verbose:
+                print(row, flush=True)
+            it += 1
+        return self
+
+    def save(self, path: str):
+        """npz with the SB3 state-dict keys ('.' -> '__'), loadable by MlpPolicy.load."""
+        sd = self.best_state or self.policy.state_dict()
+        np.savez(path, **{k.replace(".", "__"): v.detach().float().cpu().numpy() for k, v in sd.items()})
