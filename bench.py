@@ -427,7 +427,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--integrator", choices=("rk45", "closed_form"), default="rk45")
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--steps-per-launch", type=int, default=64, help="env steps fused into one rollout launch")
+    ap.add_argument("--steps-per-launch", type=int, default=250, help="env steps fused into one rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0)

@@ -230,14 +230,18 @@ RDV_DEV void team_reset_core(const RdvParams &P, uint64_t seed, int64_t env_id, 
         for (int k = 0; k < 4; ++k) { e.qc[k] = row[RDV_QCW + k]; e.qt[k] = row[RDV_QTW + k]; }
 #pragma unroll
         for (int k = 0; k < 3; ++k) { e.wc[k] = row[RDV_WCX + k]; e.wt[k] = row[RDV_WTX + k]; }
-        const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
+        // the nominal start is ~10 m out: beyond near_sq neither a collision nor a success is possible and
+        // the rotation matrices, the corridor angle and the error vector are never formed
         const double rc_sq = dot3(e.rc, e.rc);
-        const int collided = (rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle) ? 1 : 0;
-        int success = 0;
-        if (!collided) {
-            const ErrSq es = errors_sq(P, e, Rc, Rt);
-            if (es.pos <= P.max_rd_error_sq && es.vel <= P.max_vd_error_sq && es.rot <= P.max_wd_error_sq)
-                success = attitude_error(P, e, Rc, rc_sq) <= P.max_qd_error ? 1 : 0;
+        int collided = 0, success = 0;
+        if (rc_sq < P.near_sq) {
+            const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
+            collided = (rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle) ? 1 : 0;
+            if (!collided) {
+                const ErrSq es = errors_sq(P, e, Rc, Rt);
+                if (es.pos <= P.max_rd_error_sq && es.vel <= P.max_vd_error_sq && es.rot <= P.max_wd_error_sq)
+                    success = attitude_error(P, e, Rc, rc_sq) <= P.max_qd_error ? 1 : 0;
+            }
         }
         row[20] = (double)collided;
         row[21] = (double)success;
