@@ -1,11 +1,16 @@
 // rdv_b200.cu -- kernels and C ABI of librdv_b200.so (sm_100a only).
 //
-// Layout in HBM: structure-of-arrays fp64 state [RDV_NF64][ld] + int32 [RDV_NI32][ld]; one
-// thread per environment, so every state load/store is a fully coalesced 256 B warp access.
-// Row-major [n][6] actions are read with 8/16-byte vector loads; the [n][17] float32
-// observation is staged in shared memory and written out as contiguous float4 rows.
-// Per-configuration constants (CW transition matrix, thresholds, reward coefficients,
-// inertia) travel in the __grid_constant__ RdvParams kernel argument, i.e. the constant bank.
+// Layout in HBM: structure-of-arrays fp64 state [RDV_NF64][ld] + int32 [RDV_NI32][ld], so a warp's access to one
+// row is one coalesced 256 B line.  Row-major [n][6] actions are read with 8/16-byte loads; the [n][17] float32
+// observation is staged in shared memory and written out as contiguous rows.  Per-configuration constants (CW
+// transition matrix, thresholds, reward coefficients, inertia) travel in the __grid_constant__ RdvParams kernel
+// argument, i.e. the constant bank.
+//
+// Kernels:
+//   step_kernel     rdv_step     one launch per step, two lanes per env, team-of-8 auto-reset fused in
+//   rollout_kernel  rdv_rollout  K steps per launch, state in registers, one in-phase CTA per SM, in-warp
+//                                resets, actions from a tensor / Philox / the policy on the tensor cores
+//   reset_kernel, observe_kernel, errors_kernel, frame_kernel, policy_kernel, fp64_peak_kernel
 #include <cuda_runtime.h>
 #include <math.h>
 #include <string.h>
@@ -90,9 +95,6 @@ RDV_DEV int pair_swap(int v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 // ~20 doubles per step through warp shuffles.  Finished envs are appended to reset_list (count in
 // reset_list[0]) for the compacted reset kernel below, so the rare reset path never diverges a stepping warp.
 // ---------------------------------------------------------------------------------
-#ifndef RDV_STEP_LAYOUT
-#define RDV_STEP_LAYOUT 2              // 1: thread per env (lock-step or sequential solves); 2: lane pair per env
-#endif
 #ifndef RDV_STEP_MIN_CTAS
 #define RDV_STEP_MIN_CTAS 4          // 4 CTAs x 4 warps = 16 resident warps per SM at <= 128 registers
 #endif
@@ -390,120 +392,10 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 }
 
 // ---------------------------------------------------------------------------------
-// step kernel, layout 1: ONE thread per environment; the chaser and target RK45 solves advance in
-// lock-step inside the thread (rk45_iso_pair), which doubles the instruction-level parallelism of
-// the dependent fp64 chains without the shuffle / duplicated-work overhead of the lane-pair layout.
-// ---------------------------------------------------------------------------------
-#ifndef RDV_STEP1_MIN_CTAS
-#define RDV_STEP1_MIN_CTAS 4
-#endif
-
-#ifndef RDV_TPB1
-#define RDV_TPB1 64
-#endif
-constexpr int TPB1 = RDV_TPB1;
-
-template <bool ISO, bool ACT_F64, bool CLOSED>
-__global__ void __launch_bounds__(TPB1, RDV_STEP1_MIN_CTAS)
-step_kernel_env(const __grid_constant__ RdvParams P, const RdvState S, const RdvStepIO io, const int64_t n,
-                const uint64_t seed, const int64_t env_offset)
-{
-    __shared__ __align__(16) float s_obs[TPB1 * RDV_OBS_DIM];
-    __shared__ double s_stats[TPB1 / 32][RDV_NSTATS];
-    __shared__ double s_team[TPB1 / RDV_TEAM][RDV_TEAM_ROW];  // scratch rows of the reset teams
-    __shared__ int s_reset_idx[TPB1];                         // envs of this CTA whose episode just ended
-    __shared__ int s_reset_n;
-    if (threadIdx.x == 0) s_reset_n = 0;
-    __syncthreads();
-
-    const int64_t base = (int64_t)blockIdx.x * TPB1;
-    const int64_t i = base + threadIdx.x;
-    const bool active = i < n;
-    StepStats st = {};
-
-    if (active) {
-        EnvRegs e;
-        EnvCounters c;
-        load_env(S, i, e);
-        load_counters(S, i, c);
-        ActionTerms t;
-        if (ACT_F64) {
-            const double2 *ap = reinterpret_cast<const double2 *>(static_cast<const double *>(io.actions) + 6 * i);
-            const double2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
-            const double a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
-            ingest_action_f64(P, a, c, t);
-        } else {
-            const float2 *ap = reinterpret_cast<const float2 *>(static_cast<const float *>(io.actions) + 6 * i);
-            const float2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
-            const float a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
-            ingest_action_f32(P, a, c, t);
-        }
-        int rk_acc = 0, rk_rej = 0, fail = 0;
-        env_advance<ISO, CLOSED, (RDV_STEP1_MIN_CTAS <= 4)>(P, e, t, rk_acc, rk_rej, fail);
-        float ov[RDV_OBS_DIM];
-        const StepResult r = env_evaluate(P, e, t.fuel, c, ov);
-        float *o = s_obs + threadIdx.x * RDV_OBS_DIM;
-#pragma unroll
-        for (int k = 0; k < RDV_OBS_DIM; ++k) o[k] = ov[k];
-
-        io.reward[i] = r.rew;
-        io.done[i] = (uint8_t)r.done;
-        if (io.end_reason) io.end_reason[i] = (int8_t)r.reason;
-        st.steps = 1; st.reward = r.rew; st.rk_acc = rk_acc; st.rk_rej = rk_rej; st.fail = fail;
-        if (r.done) {
-            st.episodes = 1; st.succeeded = c.success > 0; st.collided = c.collided;
-            st.end0 = r.reason == 0; st.end1 = r.reason == 1; st.end2 = r.reason == 2; st.end3 = r.reason == 3;
-            st.ep_return = c.ep_ret; st.ep_length = (double)c.step; st.delta_v = c.tdv; st.delta_w = c.tdw;
-            if (io.episode_record) {
-                double *rec = io.episode_record + RDV_EP_NCOL * i;
-                rec[RDV_EP_RETURN] = c.ep_ret; rec[RDV_EP_LENGTH] = (double)c.step;
-                rec[RDV_EP_SUCCESS] = (double)c.success; rec[RDV_EP_COLLIDED] = (double)c.collided;
-                rec[RDV_EP_DELTA_V] = c.tdv; rec[RDV_EP_DELTA_W] = c.tdw;
-            }
-            if (io.terminal_obs) {
-                float *to = io.terminal_obs + RDV_OBS_DIM * i;
-#pragma unroll
-                for (int k = 0; k < RDV_OBS_DIM; ++k) to[k] = ov[k];
-            }
-            if (io.auto_reset) s_reset_idx[atomicAdd(&s_reset_n, 1)] = threadIdx.x;
-        }
-        store_env(S, i, e);
-        store_counters(S, i, c);
-    }
-
-    // ---- auto-reset by teams of 8 lanes (see step_kernel) ----
-    __syncthreads();
-    if (io.auto_reset) {
-        const int count = s_reset_n, team = threadIdx.x / RDV_TEAM;
-        for (int b = 0; b < count; b += TPB1 / RDV_TEAM) {
-            if (b + (team & ~3) >= count) break;
-            const bool valid = b + team < count;
-            const int local = valid ? s_reset_idx[b + team] : 0;
-            const int64_t ie = base + local < n ? base + local : n - 1;
-            team_reset(P, S, seed, env_offset + ie, ie, valid, 1, nullptr, s_team[team], s_obs + local * RDV_OBS_DIM);
-        }
-        __syncthreads();
-    }
-
-    // ---- coalesced observation write-out: the CTA's rows are contiguous in obs[n][17] ----
-    {
-        const int64_t rows = (n - base) < TPB1 ? (n - base) : TPB1;
-        const int total = (int)rows * RDV_OBS_DIM;
-        float *dst = io.obs + base * RDV_OBS_DIM;              // base*17*4 B is a multiple of 16 (TPB1 = 64)
-        const int nvec = total >> 2;
-        const float4 *src4 = reinterpret_cast<const float4 *>(s_obs);
-        float4 *dst4 = reinterpret_cast<float4 *>(dst);
-        for (int k = threadIdx.x; k < nvec; k += TPB1) dst4[k] = src4[k];
-        for (int k = (nvec << 2) + threadIdx.x; k < total; k += TPB1) dst[k] = s_obs[k];
-    }
-    if (io.stats) reduce_stats<TPB1 / 32>(st, io.stats, s_stats);
-}
-
-// ---------------------------------------------------------------------------------
 // Fused rollout: K consecutive steps of every env in ONE launch, state resident in registers.
 //
 // Per step: the action comes from a caller tensor [K][n][6] or from the device Philox stream
-// (philox_actions), the env steps exactly as in step_kernel_env, and finished envs are reset inside the
+// (philox_actions), the env steps through the shared building blocks of rdv_step.cuh, and finished envs are reset inside the
 // warp: the (up to four at a time) finished lanes are handed to the warp's four 8-lane teams
 // (team_reset_core), which leave the new state in a shared scratch row that the owning lane reads back
 // into its registers.  What a per-step launch pays every step -- launch latency, 193 B/env of state
@@ -982,14 +874,8 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
     const bool iso = p->iso_c && p->iso_t;
     const bool closed = p->integrator == RDV_INTEGRATOR_CLOSED_FORM;
     if (io->auto_reset != 0 && io->auto_reset != 1) return RDV_ERR_SIZE;
-#if RDV_STEP_LAYOUT == 1
-    const unsigned grid1 = (unsigned)((n + TPB1 - 1) / TPB1);
-#define RDV_LAUNCH(ISO_, F64_, CL_) \
-    step_kernel_env<ISO_, F64_, CL_><<<grid1, TPB1, 0, st>>>(*p, *s, *io, n, seed, env_offset)
-#else
 #define RDV_LAUNCH(ISO_, F64_, CL_) \
     step_kernel<ISO_, F64_, CL_><<<grid, TPB, 0, st>>>(*p, *s, *io, n, seed, env_offset)
-#endif
     if (closed) { if (io->act_f64) RDV_LAUNCH(true, true, true); else RDV_LAUNCH(true, false, true); }
     else if (iso) { if (io->act_f64) RDV_LAUNCH(true, true, false); else RDV_LAUNCH(true, false, false); }
     else { if (io->act_f64) RDV_LAUNCH(false, true, false); else RDV_LAUNCH(false, false, false); }
