@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 10
+#define RDV_ABI_VERSION 11
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -218,6 +218,11 @@ int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n
  * Weights are row-major [out][in] as in torch.nn.Linear. */
 
 int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
+
+/* Test hook: y[i] = f(x[i]) for the device math helpers the step is built from.  op 0: 1/sqrt(x), 1: 1/x,
+ * 2: sqrt(x), 3: x^-0.1 (fp64 controller), 4: x^-0.1 (float32 controller), 5: acos(round(x, 5))
+ * (angle_between_vectors, utils/general.py:163-181). */
+int rdv_math_probe(const double *x, double *y, int64_t n, int op, void *cuda_stream);
 
 /* Measured-peak helper for the roofline: runs `iters` dependent-chain-free DFMA per thread on
  * every SM and writes one double per thread to `sink` ([blocks*threads]).  flops = 2*iters*16*

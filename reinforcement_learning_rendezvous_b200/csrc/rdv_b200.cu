@@ -697,6 +697,24 @@ __global__ void __launch_bounds__(PTPB) policy_kernel(const RdvPolicy pi, const 
     }
 }
 
+// element-wise evaluation of the device math helpers, for tests/test_gpu_math.py
+__global__ void math_probe_kernel(const double *x, double *y, int64_t n, int op)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r;
+    switch (op) {
+        case 0: r = fast_rsqrt(v); break;
+        case 1: r = fast_rcp(v); break;
+        case 2: r = fast_sqrt(v); break;
+        case 3: r = pow_neg_tenth(v); break;
+        case 4: r = (double)pow_neg_tenth_f32((float)v); break;
+        default: r = rounded_angle_from(v, 1.0, 1.0); break;      // acos(round(v, 5))
+    }
+    y[i] = r;
+}
+
 // DFMA-saturating probe for the measured fp64 peak (16 independent accumulators per thread)
 __global__ void fp64_peak_kernel(double *sink, int iters)
 {
@@ -1023,6 +1041,15 @@ int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, in
         attr_set = true;
     }
     policy_kernel<<<(unsigned)((n + PTPB - 1) / PTPB), PTPB, smem, (cudaStream_t)cuda_stream>>>(*pi, obs, actions, n);
+    return launch_status();
+}
+
+int rdv_math_probe(const double *x, double *y, int64_t n, int op, void *cuda_stream)
+{
+    if (!x || !y) return RDV_ERR_NULL;
+    if (n < 0 || op < 0 || op > 5) return RDV_ERR_SIZE;
+    if (n == 0) return RDV_OK;
+    math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x, y, n, op);
     return launch_status();
 }
 
