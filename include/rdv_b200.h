@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 11
+#define RDV_ABI_VERSION 12
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -164,8 +164,13 @@ typedef struct RdvPolicy {
     const float *w2, *b2;    /* [6][H],  [6] */
     int32_t hidden;          /* H, must be 64 */
     int32_t reserved;
+    const float *log_std;    /* nullable [6]: state-independent log std of the Gaussian head (sampling mode) */
 } RdvPolicy;
-enum { RDV_ACTIONS_F32 = 0, RDV_ACTIONS_F64 = 1, RDV_ACTIONS_PHILOX = 2, RDV_ACTIONS_POLICY = 3 };
+enum { RDV_ACTIONS_F32 = 0, RDV_ACTIONS_F64 = 1, RDV_ACTIONS_PHILOX = 2,
+       RDV_ACTIONS_POLICY = 3,          /* a = clip(actor(obs)): model.predict(deterministic=True)                 */
+       RDV_ACTIONS_POLICY_SAMPLE = 4 }; /* a ~ N(actor(obs), exp(log_std)^2), the env gets clip(a) and actions_out  *
+                                         * the unclipped draw: SB3 collect_rollouts (noise: Philox(action_seed; env  *
+                                         * id, step_base + k), Box-Muller in float32)                               */
 typedef struct RdvRolloutIO {
     int32_t  steps;          /* K                                                                          */
     int32_t  action_source;  /* RDV_ACTIONS_*                                                              */

@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200
 SOURCES = ("rdv_b200.cu",)
 HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh", "rdv_policy.cuh")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -89,6 +89,7 @@ class RdvPolicy(C.Structure):
     _fields_ = [
         ("w0", C.c_void_p), ("b0", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p),
         ("w2", C.c_void_p), ("b2", C.c_void_p), ("hidden", C.c_int32), ("reserved", C.c_int32),
+        ("log_std", C.c_void_p),
     ]
 
 
@@ -101,7 +102,7 @@ class RdvRolloutIO(C.Structure):
     ]
 
 
-ACTIONS_F32, ACTIONS_F64, ACTIONS_PHILOX, ACTIONS_POLICY = 0, 1, 2, 3
+ACTIONS_F32, ACTIONS_F64, ACTIONS_PHILOX, ACTIONS_POLICY, ACTIONS_POLICY_SAMPLE = 0, 1, 2, 3, 4
 
 
 # name -> (restype, argtypes); every symbol include/rdv_b200.h declares

@@ -148,13 +148,16 @@ class BatchedRendezvousEnv:
 
     def rollout(self, steps: int, actions: Optional[torch.Tensor] = None, action_seed: Optional[int] = None,
                 step_base: int = 0, record_rewards: bool = False, record_dones: bool = False,
-                record_obs: bool = False, record_actions: bool = False, policy=None) -> dict:
+                record_obs: bool = False, record_actions: bool = False, policy=None,
+                stochastic: bool = False) -> dict:
         """``steps`` consecutive env steps in ONE kernel launch (state stays in registers, finished envs restart
         in place when ``auto_reset``).  Actions come from ``actions`` ([steps, N, 6] float32/float64 on the device) or,
         when it is None, from the device Philox stream ``(action_seed; global env id, step_base + k)`` as U(-1,1) fp64
         draws -- the "random actions" workload -- or from ``policy`` (an :class:`MlpPolicy`): the deterministic actor
         output ``clip(pi(obs), -1, 1)`` evaluated inside the launch on the tensor cores from the observation the
-        previous step returned (closed loop, float32 actions).  Returns a dict with ``obs`` (final observation, f32 [N,17]) and the
+        previous step returned (closed loop, float32 actions); with ``stochastic`` the action is drawn from the
+        policy's Gaussian head N(pi(obs), exp(log_std)^2) with Philox noise keyed by ``action_seed`` (SB3's
+        collect_rollouts: the env gets the clipped draw, ``actions`` records the unclipped one).  Returns a dict with ``obs`` (final observation, f32 [N,17]) and the
         requested per-step records (``rewards`` f64 [steps,N], ``dones`` u8 [steps,N], ``obs_steps`` f32 [steps,N,17],
         ``actions`` f64 [steps,N,6] for Philox actions).  Asynchronous on the current stream."""
         steps = int(steps)
@@ -172,7 +175,9 @@ class BatchedRendezvousEnv:
         elif policy is not None:
             if policy.device != dev:
                 raise ValueError("policy and env live on different devices")
-            source, esz = N.ACTIONS_POLICY, 0
+            if stochastic and (policy.log_std is None or action_seed is None):
+                raise ValueError("stochastic policy rollouts need policy.log_std and an action_seed")
+            source, esz = (N.ACTIONS_POLICY_SAMPLE if stochastic else N.ACTIONS_POLICY), 0
         else:
             if action_seed is None:
                 raise ValueError("give an actions tensor, an action_seed (device-generated actions) or a policy")

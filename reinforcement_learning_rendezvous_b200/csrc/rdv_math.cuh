@@ -502,7 +502,6 @@ RDV_DEV void rhs_iso(const double *q, const double *hw, double *f)
     f[0] = g0 * r; f[1] = g1 * r; f[2] = g2 * r; f[3] = g3 * r;
 }
 
-template <bool CTA_SYNC>
 RDV_DEV int rk45_iso_pair(double (&ya)[7], double (&yb)[7], const double dt, int &n_rejected)
 {
     double y[2][4], w[2][3], hw[2][3], K0[2][4], h_abs[2], t[2];
@@ -566,13 +565,7 @@ RDV_DEV int rk45_iso_pair(double (&ya)[7], double (&yb)[7], const double dt, int
         }
     }
     // ---- attempted steps (scipy rk.py:111-179), both bodies per pass, predicated commit ----
-    // CTA_SYNC: every warp of the CTA runs the same number of passes, re-converging at a barrier per pass, so
-    // that all resident warps fetch the same ~20 KB of straight-line code at the same time (the step is
-    // instruction-cache bound otherwise); a finished thread's extra passes commit nothing.
-    for (;;) {
-        bool more = !((done[0] || failed[0]) && (done[1] || failed[1]));
-        if (CTA_SYNC) more = __syncthreads_or(more);
-        if (!more) break;
+    while (!((done[0] || failed[0]) && (done[1] || failed[1]))) {
         double h[2], t_new[2], ha[2], ys[2][4];
         bool fail_now[2];
         double K1[2][4], K2[2][4], K3[2][4], K4[2][4], K5[2][4], K6[2][4];

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "rdv_b200.h"
+#include "rdv_math.cuh"
 
 namespace rdv {
 
@@ -32,6 +33,7 @@ struct PolicyShared {
     float w1h[PI_H * PI_S1], w1l[PI_H * PI_S1];
     float w2h[8 * PI_S1], w2l[8 * PI_S1];
     float b0[PI_H], b1[PI_H], b2[8];
+    float std[8];                    // exp(log_std) of the Gaussian head (sampling mode)
 };
 
 __device__ __forceinline__ float tf32_hi(float x)
@@ -89,12 +91,15 @@ __device__ __forceinline__ void policy_load(const RdvPolicy &pi, PolicyShared &s
         s.w2h[idx] = h; s.w2l[idx] = tf32_hi(w - h);
     }
     for (int idx = threadIdx.x; idx < PI_H; idx += blockDim.x) { s.b0[idx] = pi.b0[idx]; s.b1[idx] = pi.b1[idx]; }
-    if (threadIdx.x < 8) s.b2[threadIdx.x] = threadIdx.x < RDV_ACT_DIM ? pi.b2[threadIdx.x] : 0.0f;
+    if (threadIdx.x < 8) {
+        s.b2[threadIdx.x] = threadIdx.x < RDV_ACT_DIM ? pi.b2[threadIdx.x] : 0.0f;
+        s.std[threadIdx.x] = (threadIdx.x < RDV_ACT_DIM && pi.log_std) ? expf(pi.log_std[threadIdx.x]) : 0.0f;
+    }
 }
 
 // Whole warp.  x_stage: the warp's 32 observation rows [32][17] in shared memory (written by the caller, who
 // also owns the __syncwarp before the call); act_stage: warp-private [32][8] floats.  On return lane L holds
-// the clipped deterministic action of its env in act[0..5].
+// the actor's mean action (NOT clipped) of its env in act[0..5].
 __device__ __forceinline__ void policy_forward_warp(const PolicyShared &s, const float *x_stage, float *act_stage,
                                                     float (&act)[RDV_ACT_DIM])
 {
@@ -189,8 +194,27 @@ __device__ __forceinline__ void policy_forward_warp(const PolicyShared &s, const
     }
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < RDV_ACT_DIM; ++j) act[j] = fminf(1.0f, fmaxf(-1.0f, act_stage[lane * 8 + j]));   // np.clip (:128-133)
+    for (int j = 0; j < RDV_ACT_DIM; ++j) act[j] = act_stage[lane * 8 + j];
     __syncwarp();
+}
+
+// Six N(0,1) float32 draws for (noise seed; env id, step index): Philox blocks 0x20000000 | {0,1,2}, one
+// Box-Muller pair per block (the Gaussian head of SB3's DiagGaussianDistribution.sample()).
+__device__ __forceinline__ void philox_normals(uint64_t seed, int64_t env_id, int64_t step_index, float (&z)[6])
+{
+#pragma unroll
+    for (uint32_t blk = 0; blk < 3; ++blk) {
+        uint32_t c[4] = {(uint32_t)env_id, (uint32_t)((uint64_t)env_id >> 32), (uint32_t)step_index,
+                         0x20000000u | blk | (((uint32_t)((uint64_t)step_index >> 32) & 0x00FFFFFFu) << 4)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1)
+        const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float r = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        z[2 * blk] = r * cs;
+        z[2 * blk + 1] = r * sn;
+    }
 }
 
 }  // namespace rdv

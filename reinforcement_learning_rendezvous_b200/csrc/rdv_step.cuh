@@ -49,7 +49,7 @@ RDV_DEV void ingest_action_f32(const RdvParams &P, const float (&a)[6], EnvCount
 // (rk45_iso_pair, 2x ILP, ~240 registers) -- the right choice with <= 2 warps per SM sub-partition; otherwise one
 // solve after the other through a single copy of the solver (128 registers), which wins once 3-4 warps per
 // sub-partition hide the latency instead.
-template <bool ISO, bool CLOSED, bool LOCKSTEP, bool CTA_SYNC = false>
+template <bool ISO, bool CLOSED, bool LOCKSTEP>
 RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, int &rk_acc, int &rk_rej, int &fail)
 {
     {
@@ -76,15 +76,12 @@ RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, i
         bc.I = P.inertia_c; bc.Iinv = P.inv_inertia_c; bc.tau = P.torque_c;
         bt.I = P.inertia_t; bt.Iinv = P.inv_inertia_t; bt.tau = c_zero3;
         if (ISO && LOCKSTEP) {
-            if (CTA_SYNC) __syncthreads();
-            const int k = rk45_iso_pair<CTA_SYNC>(y, z, P.dt, rk_rej);
-            if (CTA_SYNC) __syncthreads();
+            const int k = rk45_iso_pair(y, z, P.dt, rk_rej);
             if (k < 0) fail = 1; else rk_acc += k;
         } else if (ISO) {
             // one solve after the other through a single copy of the solver code (bounded registers)
 #pragma unroll 1
             for (int body = 0; body < 2; ++body) {
-                if (CTA_SYNC) __syncthreads();        // both solves start with the CTA's warps aligned
                 const int k = rk45_attitude<true>(y, P.dt, bc, rk_rej);
                 if (k < 0) fail = 1; else rk_acc += k;
 #pragma unroll

@@ -53,9 +53,12 @@ class MlpPolicy:
                 or tuple(self.w["w2"].shape) != (N.ACT_DIM, hidden):
             raise ValueError("unexpected policy shapes")
         self.hidden = hidden
-        self.log_std = state_dict.get("log_std")
+        ls = state_dict.get("log_std")
+        self.log_std = None if ls is None else torch.as_tensor(np.ascontiguousarray(ls), dtype=torch.float32,
+                                                                device=self.device).contiguous()
         self._c = N.RdvPolicy(self.w["w0"].data_ptr(), self.w["b0"].data_ptr(), self.w["w1"].data_ptr(),
-                              self.w["b1"].data_ptr(), self.w["w2"].data_ptr(), self.w["b2"].data_ptr(), hidden, 0)
+                              self.w["b1"].data_ptr(), self.w["w2"].data_ptr(), self.w["b2"].data_ptr(), hidden, 0,
+                              self.log_std.data_ptr() if self.log_std is not None else None)
         self._h_obs = self._h_act = None
 
     @classmethod

@@ -5,7 +5,11 @@ normalize_advantage``), for the case where SB3 is not installed (it is not part 
 numpy rollout buffer is the bottleneck.  With SB3 present, ``make_vec_env`` + ``stable_baselines3.PPO`` works as
 in the reference; this module keeps every rollout tensor on the GPU instead:
 
-* collection: obs -> actor/critic (torch) -> Gaussian sample -> clip -> ``BatchedRendezvousEnv.step`` (CUDA kernels)
+* collection, fused (default): ONE ``rdv_rollout`` launch per iteration -- the actor runs on the tensor cores inside
+  the kernel, the action is drawn from the Gaussian head with Philox noise, the env steps, finished envs restart;
+  observations / unclipped actions / rewards / dones come back as [n_steps, N, ...] tensors and the critic values
+  and log-probabilities are one batched torch forward afterwards
+* collection, stepwise (``fused=False``): obs -> actor/critic (torch) -> sample -> clip -> ``env.step`` per step
 * GAE(lambda) and the clipped-surrogate update in torch autograd (the optimiser is library code, not the hot path)
 * ``evaluate`` = the callback's deterministic evaluation (custom/custom_callbacks.py:427-475) as ONE fused
   policy rollout (``rollout(policy=...)``), best model kept like ``CustomCallback`` (:477-493).
@@ -77,6 +81,7 @@ class PPOConfig:
     max_grad_norm: float = 0.5
     normalize_advantage: bool = True
     n_evals: int = 50                 # custom_callbacks.py: n_evals
+    fused: bool = True                # collect with the policy-fused rollout kernel
     seed: int = 0
     log: list = field(default_factory=list)
 
@@ -101,6 +106,7 @@ class PPO:
         self.obs = env.reset().clone()
         self.episode_start = torch.ones(n, dtype=torch.bool, device=dev)
         self.num_timesteps = 0
+        self._noise_step = 0
         self.best_eval = -float("inf")
         self.best_state = None
         kw = {k: v for k, v in env.ctor_kwargs.items()}
@@ -109,6 +115,42 @@ class PPO:
     # -- rollout collection (OnPolicyAlgorithm.collect_rollouts) ------------------------------------------------
     @torch.no_grad()
     def collect(self):
+        return self._collect_fused() if self.cfg.fused else self._collect_stepwise()
+
+    def _gae(self, last_value):
+        T = self.cfg.n_steps
+        adv = torch.zeros_like(self.buf_rew)
+        last = torch.zeros(self.env.num_envs, device=self.device)
+        for t in reversed(range(T)):
+            next_value = last_value if t == T - 1 else self.buf_val[t + 1]
+            not_done = (~self.buf_done[t]).float()
+            delta = self.buf_rew[t] + self.cfg.gamma * next_value * not_done - self.buf_val[t]
+            last = delta + self.cfg.gamma * self.cfg.gae_lambda * not_done * last
+            adv[t] = last
+        self.num_timesteps += T * self.env.num_envs
+        return adv, adv + self.buf_val
+
+    def _collect_fused(self):
+        env, T, n = self.env, self.cfg.n_steps, self.env.num_envs
+        actor = self.policy.to_mlp_policy(self.device)
+        out = env.rollout(T, policy=actor, stochastic=True, action_seed=self.cfg.seed + 977,
+                          step_base=self._noise_step, record_obs=True, record_actions=True, record_rewards=True,
+                          record_dones=True)
+        self._noise_step += T
+        self.buf_obs[0] = self.obs
+        self.buf_obs[1:] = out["obs_steps"][:-1]
+        self.buf_act.copy_(out["actions"])
+        self.buf_rew.copy_(out["rewards"])
+        self.buf_done.copy_(out["dones"].bool())
+        mean, value = self.policy(self.buf_obs.reshape(T * n, 17))
+        self.buf_val.copy_(value.reshape(T, n))
+        self.buf_logp.copy_(self.policy.distribution(mean).log_prob(self.buf_act.reshape(T * n, 6)).sum(-1).reshape(T, n))
+        self.obs = out["obs_steps"][-1].clone()
+        self.episode_start = self.buf_done[-1]
+        _, last_value = self.policy(self.obs)
+        return self._gae(last_value)
+
+    def _collect_stepwise(self):
         env, T = self.env, self.cfg.n_steps
         starts = torch.empty((T, env.num_envs), dtype=torch.bool, device=self.device)
         for t in range(T):
@@ -124,16 +166,7 @@ class PPO:
             self.episode_start = done.bool()
         _, last_value = self.policy(self.obs)
         # GAE(lambda) (RolloutBuffer.compute_returns_and_advantage); no time-limit bootstrapping, like the reference
-        adv = torch.zeros_like(self.buf_rew)
-        last = torch.zeros(env.num_envs, device=self.device)
-        for t in reversed(range(T)):
-            next_value = last_value if t == T - 1 else self.buf_val[t + 1]
-            not_done = (~self.buf_done[t]).float()
-            delta = self.buf_rew[t] + self.cfg.gamma * next_value * not_done - self.buf_val[t]
-            last = delta + self.cfg.gamma * self.cfg.gae_lambda * not_done * last
-            adv[t] = last
-        self.num_timesteps += T * env.num_envs
-        return adv, adv + self.buf_val
+        return self._gae(last_value)
 
     # -- clipped-surrogate update (PPO.train) --------------------------------------------------------------------
     def update(self, adv, ret):

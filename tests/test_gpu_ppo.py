@@ -6,12 +6,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_ppo_short_training_run(tmp_path):
+@pytest.mark.parametrize("fused", [True, False])
+def test_ppo_short_training_run(tmp_path, fused):
     import torch
     from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, MlpPolicy
     from reinforcement_learning_rendezvous_b200.ppo import PPO, PPOConfig
     env = BatchedRendezvousEnv(4096, seed=0)
-    cfg = PPOConfig(n_steps=16, batch_size=8192, n_epochs=4, n_evals=64, seed=0)
+    cfg = PPOConfig(n_steps=16, batch_size=8192, n_epochs=4, n_evals=64, seed=0, fused=fused)
     algo = PPO(env, cfg)
     algo.learn(total_timesteps=12 * 16 * 4096, eval_every=4)
     log = cfg.log

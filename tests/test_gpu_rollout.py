@@ -216,3 +216,43 @@ def test_fused_policy_monte_carlo_success_rate():
     assert same_len > 0.985, same_len
     st = env.read_stats()
     assert st["failures"] == 0
+
+
+def test_stochastic_policy_rollout_statistics_and_determinism():
+    """Sampling mode: recorded actions = actor mean + exp(log_std) * N(0,1) draws (moments, independence across
+    envs / steps / components), the env receives the clipped draw, and the launch is reproducible."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    pol = _policy()
+    n, K = 8192, 24
+    runs = []
+    for _ in range(2):
+        env = BatchedRendezvousEnv(n, seed=3)
+        obs0 = env.reset().clone()
+        out = env.rollout(K, policy=pol, stochastic=True, action_seed=42, step_base=1000, record_actions=True,
+                          record_obs=True, record_rewards=True)
+        runs.append((obs0, out, env.get_state().clone()))
+    (obs0, out, state), (_, out2, state2) = runs
+    assert torch.equal(out["actions"], out2["actions"]) and torch.equal(state, state2)
+    prev = torch.cat([obs0[None], out["obs_steps"][:-1]])
+    std = pol.log_std.exp()
+    # actor mean (unclipped) from the fp32 torch weights
+    x = prev.reshape(-1, 17)
+    h = torch.tanh(x @ pol.w["w0"].T + pol.w["b0"])
+    h = torch.tanh(h @ pol.w["w1"].T + pol.w["b1"])
+    mean = (h @ pol.w["w2"].T + pol.w["b2"]).reshape(K, n, 6)
+    z = ((out["actions"] - mean) / std).double()
+    m = z.numel()
+    assert abs(float(z.mean())) < 5 / np.sqrt(m) and abs(float(z.var()) - 1) < 0.01
+    assert abs(float((z ** 3).mean())) < 0.02 and abs(float((z ** 4).mean()) - 3) < 0.05
+    zc = z.reshape(-1, 6)
+    corr = torch.corrcoef(zc.T)
+    assert float((corr - torch.eye(6, device=corr.device, dtype=corr.dtype)).abs().max()) < 0.01
+    assert abs(float(torch.corrcoef(torch.stack([z[0, :, 0], z[1, :, 0]]))[0, 1])) < 0.05
+    # a different step_base / seed gives different noise
+    env = BatchedRendezvousEnv(n, seed=3)
+    env.reset()
+    other = env.rollout(K, policy=pol, stochastic=True, action_seed=43, step_base=1000, record_actions=True)
+    assert not torch.equal(other["actions"][0], out["actions"][0])
+    with pytest.raises(ValueError):
+        env.rollout(2, policy=pol, stochastic=True)
