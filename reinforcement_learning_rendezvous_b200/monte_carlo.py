@@ -134,3 +134,50 @@ def evaluate_batch(policy, initial_states, config=None, reward_kwargs=None, devi
         total_reward=total_reward.cpu().numpy(), total_delta_v=tdv.cpu().numpy(), num_successes=n_suc_np,
         succeeded=(n_suc_np > 0).astype(np.int64), min_dist_from_koz=min_koz.cpu().numpy(),
         pos_error=te[:, 0], vel_error=te[:, 1], att_error=te[:, 2], rot_error=te[:, 3])
+
+
+def evaluate_sweep(policy, param_sets, episodes_per_set=1024, reward_kwargs=None, device="cuda", seed=0,
+                   **common) -> list:
+    """Sensitivity sweep as ONE batch (BASELINE.json configs[4]; the axes of sensitivity_analysis.py:97-134 --
+    ``rc0, wt0, koz_radius, corridor_half_angle, h, dt``): every entry of ``param_sets`` (a dict of ``make_env``
+    config keys) becomes a contiguous block of ``episodes_per_set`` stochastic envs with its own constants; all
+    blocks step together (one launch per block and step) under the deterministic policy and the first episode of
+    every env is scored.  Returns one dict per set: mean return / length, success and collision rates
+    (the metrics of custom_callbacks.py:285-298)."""
+    if episodes_per_set % 32:
+        raise ValueError("episodes_per_set must be a multiple of 32")
+    batches = []
+    for ps in param_sets:
+        kw = config_to_kwargs(dict(common, **ps), stochastic=True)
+        batches.append((episodes_per_set, {k: v for k, v in kw.items() if v is not None}))
+    n = episodes_per_set * len(batches)
+    env = BatchedRendezvousEnv(n, device=device, seed=seed, auto_reset=False, track_stats=False,
+                               reward_kwargs=reward_kwargs, param_batches=batches)
+    dev = env.device
+    obs = env.reset().clone()
+    steps = max(int(g.params.done_steps) for g in env.groups)
+    returns = torch.zeros(n, dtype=torch.float64, device=dev)
+    length = torch.zeros(n, dtype=torch.int64, device=dev)
+    alive = torch.ones(n, dtype=torch.bool, device=dev)
+    success = torch.zeros(n, dtype=torch.bool, device=dev)
+    collided = torch.zeros(n, dtype=torch.bool, device=dev)
+    actions = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    for _ in range(steps):
+        policy.forward(obs, out=actions)
+        obs, rew, done = env.step(actions)
+        returns += torch.where(alive, rew, torch.zeros_like(rew))
+        length += alive.long()
+        finished = alive & done.bool()
+        success |= finished & (env.success > 0)
+        collided |= finished & (env.collided > 0)
+        alive &= ~done.bool()
+        if not bool(alive.any()):
+            break
+    out = []
+    for ps, g in zip(param_sets, env.groups):
+        sl = slice(g.lo, g.hi)
+        out.append(dict(params=dict(ps), episodes=g.n, mean_return=float(returns[sl].mean()),
+                        mean_length_s=float(length[sl].double().mean() * g.params.dt),
+                        success_rate=float(success[sl].double().mean()),
+                        collision_rate=float(collided[sl].double().mean())))
+    return out

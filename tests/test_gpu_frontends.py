@@ -285,3 +285,22 @@ def test_vec_env_step_arrays_matches_step_infos():
             assert info["end_reason"] == ("obs", "time", "bubble", "attitude")[fin["end_reason"][j]]
             seen += 1
     assert seen > n
+
+
+def test_sensitivity_sweep_as_one_batch():
+    """BASELINE.json configs[4]: parameter sets of sensitivity_analysis.py:97-134 evaluated as blocks of one batch;
+    the nominal block reproduces the policy's Monte-Carlo success rate, harder settings do worse."""
+    from reinforcement_learning_rendezvous_b200 import evaluate_sweep
+    pol = _policy()
+    sets = [dict(), dict(h=400e3), dict(wt0=float(np.radians(2.5))), dict(koz_radius=10.0),
+            dict(corridor_half_angle=float(np.radians(15))), dict(rc0=30.0)]
+    res = evaluate_sweep(pol, sets, episodes_per_set=1024, seed=3, dt=1, t_max=60)
+    assert len(res) == len(sets) and all(r["episodes"] == 1024 for r in res)
+    nominal = res[0]
+    assert 0.40 < nominal["success_rate"] < 0.70          # the published experiment: 545 / 1000
+    assert 0.08 < nominal["collision_rate"] < 0.30        # 166 / 1000
+    assert abs(res[1]["success_rate"] - nominal["success_rate"]) < 0.15      # altitude barely matters
+    assert res[4]["collision_rate"] > nominal["collision_rate"]               # a narrower corridor collides more
+    assert res[5]["success_rate"] <= nominal["success_rate"]      # 30 m out: outside what the policy was trained on
+    for r in res:
+        assert np.isfinite(r["mean_return"]) and 0 < r["mean_length_s"] <= 60
