@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 12
+#define RDV_ABI_VERSION 13
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -218,11 +218,12 @@ int rdv_refresh_flags(const RdvParams *p, const RdvState *s, int64_t n, void *cu
 int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n, int transpose,
                         void *cuda_stream);
 
-/* -- fused policy (model.predict of an SB3 MlpPolicy, monte_carlo.py:128-133) ------------------- */
-/* fp32 tanh MLP obs[17] -> hidden -> hidden -> action[6], deterministic mean clipped to [-1,1].
- * Weights are row-major [out][in] as in torch.nn.Linear. */
-
+/* -- stand-alone policy forward (model.predict of an SB3 MlpPolicy, monte_carlo.py:128-133) ----------------
+ * obs [n][17] float32 -> actions [n][6] float32, deterministic mean clipped to [-1,1].
+ * rdv_policy_forward: tcgen05 tensor-core kernel (TMEM accumulators, 3xTF32 = fp32-level accuracy).
+ * rdv_policy_forward_ffma: the same op as plain fp32 FMAs, one thread per env (numerics reference). */
 int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
+int rdv_policy_forward_ffma(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
 
 /* Test hook: y[i] = f(x[i]) for the device math helpers the step is built from.  op 0: 1/sqrt(x), 1: 1/x,
  * 2: sqrt(x), 3: x^-0.1 (fp64 controller), 4: x^-0.1 (float32 controller), 5: acos(round(x, 5))

@@ -21,9 +21,9 @@ CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200.so")   # env: A/B experiments
 SOURCES = ("rdv_b200.cu",)
-HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh", "rdv_policy.cuh")
+HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh", "rdv_policy.cuh", "rdv_policy_tc.cuh")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -124,6 +124,7 @@ PROTOTYPES = {
     "rdv_refresh_flags": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.c_int64, C.c_void_p]),
     "rdv_frame_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "rdv_policy_forward": (C.c_int, [C.POINTER(RdvPolicy), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "rdv_policy_forward_ffma": (C.c_int, [C.POINTER(RdvPolicy), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rdv_math_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "rdv_fp64_peak_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }

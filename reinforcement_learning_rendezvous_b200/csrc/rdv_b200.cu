@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "rdv_step.cuh"
 #include "rdv_policy.cuh"
+#include "rdv_policy_tc.cuh"
 
 namespace rdv {
 
@@ -1041,6 +1042,32 @@ int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n
 }
 
 int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream)
+{
+    if (!pi || !obs || !actions || !pi->w0 || !pi->b0 || !pi->w1 || !pi->b1 || !pi->w2 || !pi->b2) return RDV_ERR_NULL;
+    if (pi->hidden != tc::H) return RDV_ERR_UNSUPPORTED;
+    if (n < 0) return RDV_ERR_SIZE;
+    if (n == 0) return RDV_OK;
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) {
+            sm_count = 0;
+            return RDV_ERR_CUDA;
+        }
+        if (cudaFuncSetAttribute(tc::policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(tc::Smem)) != cudaSuccess) {
+            sm_count = 0;
+            return RDV_ERR_CUDA;
+        }
+    }
+    const int64_t tiles = (n + tc::TM - 1) / tc::TM;
+    const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
+    tc::policy_tc_kernel<<<grid, tc::TM, sizeof(tc::Smem), (cudaStream_t)cuda_stream>>>(*pi, obs, actions, n);
+    return launch_status();
+}
+
+int rdv_policy_forward_ffma(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream)
 {
     if (!pi || !obs || !actions || !pi->w0 || !pi->b0 || !pi->w1 || !pi->b1 || !pi->w2 || !pi->b2) return RDV_ERR_NULL;
     if (pi->hidden != PH) return RDV_ERR_UNSUPPORTED;

@@ -65,16 +65,18 @@ class MlpPolicy:
     def load(cls, path: str, device="cuda") -> "MlpPolicy":
         return cls(load_state_dict(path), device=device)
 
-    def forward(self, obs: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-        """Deterministic clipped actions f32[n,6] for device observations f32[n,17] (asynchronous)."""
+    def forward(self, obs: torch.Tensor, out: torch.Tensor = None, ffma: bool = False) -> torch.Tensor:
+        """Deterministic clipped actions f32[n,6] for device observations f32[n,17] (asynchronous).  Default: the
+        tcgen05 tensor-core kernel; ``ffma=True``: the plain fp32-FMA kernel (numerics reference)."""
         if obs.device != self.device or obs.dtype != torch.float32:
             raise ValueError("obs must be a float32 tensor on the policy's device")
         obs = obs.contiguous()
         n = obs.shape[0]
         out = torch.empty((n, N.ACT_DIM), dtype=torch.float32, device=self.device) if out is None else out
         with torch.cuda.device(self.device):
-            N.check(self.lib.rdv_policy_forward(C.byref(self._c), obs.data_ptr(), out.data_ptr(), n,
-                                                _stream_ptr(self.device)), "rdv_policy_forward")
+            fn = self.lib.rdv_policy_forward_ffma if ffma else self.lib.rdv_policy_forward
+            N.check(fn(C.byref(self._c), obs.data_ptr(), out.data_ptr(), n, _stream_ptr(self.device)),
+                    "rdv_policy_forward")
         return out
 
     def predict(self, observation, state=None, episode_start=None, deterministic=True):

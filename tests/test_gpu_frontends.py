@@ -127,24 +127,38 @@ def test_monte_carlo_batch_reproduces_published_workbook():
 
 # ------------------------------------------------------------------------------------------ policy
 def test_policy_forward_matches_torch_fp32():
+    """rdv_policy_forward (tcgen05 / TMEM, 3xTF32) and rdv_policy_forward_ffma (plain fp32 FMAs) against an fp64
+    evaluation of the same network, at tile-ragged sizes; tolerance = fp32 accumulation error of a 64-wide MLP."""
     import torch
     pol = _policy()
     g = golden("traj_f32.npz")
     obs = np.concatenate([g["obs0"], g["obs"][:, :20].reshape(-1, 17)])
     obs = obs[np.isfinite(obs).all(axis=1)].astype(np.float32)
     w = {k: v.double().cpu() for k, v in pol.w.items()}
-    x = torch.as_tensor(obs).double()
-    h = torch.tanh(x @ w["w0"].T + w["b0"])
-    h = torch.tanh(h @ w["w1"].T + w["b1"])
-    ref = torch.clamp(h @ w["w2"].T + w["b2"], -1, 1).numpy()
-    act = pol.forward(torch.as_tensor(obs, device=pol.device)).cpu().numpy()
-    assert np.abs(act - ref).max() < 5e-6                      # fp32 accumulation vs an fp64 evaluation
+
+    def reference(x):
+        x = torch.as_tensor(x).double()
+        h = torch.tanh(x @ w["w0"].T + w["b0"])
+        h = torch.tanh(h @ w["w1"].T + w["b1"])
+        return torch.clamp(h @ w["w2"].T + w["b2"], -1, 1).numpy()
+
+    ref = reference(obs)
+    dev_obs = torch.as_tensor(obs, device=pol.device)
+    act_tc = pol.forward(dev_obs).cpu().numpy()
+    act_ff = pol.forward(dev_obs, ffma=True).cpu().numpy()
+    assert np.abs(act_ff - ref).max() < 5e-6                    # fp32 accumulation vs an fp64 evaluation
+    assert np.abs(act_tc - ref).max() < 8e-6                    # 3xTF32: fp32-level, not TF32-level (1e-3)
+    rng = np.random.default_rng(0)
+    for n in (1, 31, 127, 128, 129, 300, 4096 + 77):            # partial tiles, several tiles per CTA
+        x = rng.uniform(-1, 1, (n, 17)).astype(np.float32)
+        a = pol.forward(torch.as_tensor(x, device=pol.device)).cpu().numpy()
+        assert a.shape == (n, 6) and np.abs(a - reference(x)).max() < 8e-6, n
     a1, state = pol.predict(obs[0], deterministic=True)
     assert a1.shape == (6,) and a1.dtype == np.float32 and state is None
-    np.testing.assert_array_equal(a1, act[0])
+    np.testing.assert_array_equal(a1, act_tc[0])
     # the reference's own fp32 actions (torch CPU) for the first step of each golden episode
     first = pol.predict(g["obs0"], deterministic=True)[0]
-    assert np.abs(first - g["actions"][:, 0]).max() < 5e-6
+    assert np.abs(first - g["actions"][:, 0]).max() < 8e-6
 
 
 # ------------------------------------------------------------------------------------------ VecEnv
