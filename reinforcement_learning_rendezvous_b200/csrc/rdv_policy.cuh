@@ -60,13 +60,22 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const float (&ah)[4], 
     mma_tf32(c, ah, bh.x, bh.y);
 }
 
-// tanh to fp32 accuracy in absolute terms (the next layer is linear in it): 1 - 2 / (exp(2|x|) + 1)
+// tanh to fp32 accuracy in ABSOLUTE terms (the next layer is linear in it): 1 - 2 / (1 + exp(2x)), five
+// instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA).  exp(2x) -> 0 gives -1, -> inf gives +1; no range split.
 __device__ __forceinline__ float tanh_fast(float x)
 {
-    const float ax = fminf(fabsf(x), 15.0f);
-    const float e = __expf(2.0f * ax);
-    const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
-    return copysignf(t, x);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));      // 2^(2x log2 e) = exp(2x)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
+// x = hi + lo with hi = the TF32 part (mantissa truncated to 10 bits; the tensor core ignores the 13 low bits of
+// an operand, so lo may stay a plain fp32 number)
+__device__ __forceinline__ void tf32_split(float x, float &hi, float &lo)
+{
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = x - hi;
 }
 
 // Whole CTA: split the weights into TF32 hi / lo parts in shared memory (once per launch).
@@ -122,7 +131,7 @@ __device__ __forceinline__ void policy_forward_warp(const PolicyShared &s, const
             const float a[4] = {k0 < RDV_OBS_DIM ? r0[k0] : 0.0f, k0 < RDV_OBS_DIM ? r1[k0] : 0.0f,
                                 k0 + 1 < RDV_OBS_DIM ? r0[k0 + 1] : 0.0f, k0 + 1 < RDV_OBS_DIM ? r1[k0 + 1] : 0.0f};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { ah[mt][j] = tf32_hi(a[j]); al[mt][j] = tf32_hi(a[j] - ah[mt][j]); }
+            for (int j = 0; j < 4; ++j) tf32_split(a[j], ah[mt][j], al[mt][j]);
         }
 #pragma unroll
         for (int jn = 0; jn < 8; ++jn) {
@@ -150,7 +159,7 @@ __device__ __forceinline__ void policy_forward_warp(const PolicyShared &s, const
             const float a[4] = {tanh_fast(h[mt][jk][0]), tanh_fast(h[mt][jk][2]), tanh_fast(h[mt][jk][1]),
                                 tanh_fast(h[mt][jk][3])};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { ah[mt][j] = tf32_hi(a[j]); al[mt][j] = tf32_hi(a[j] - ah[mt][j]); }
+            for (int j = 0; j < 4; ++j) tf32_split(a[j], ah[mt][j], al[mt][j]);
         }
 #pragma unroll
         for (int jn = 0; jn < 8; ++jn) {
@@ -179,7 +188,7 @@ __device__ __forceinline__ void policy_forward_warp(const PolicyShared &s, const
                                 tanh_fast(h2[mt][jk][3])};
             float ah[4], al[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { ah[j] = tf32_hi(a[j]); al[j] = tf32_hi(a[j] - ah[j]); }
+            for (int j = 0; j < 4; ++j) tf32_split(a[j], ah[j], al[j]);
             mma_3xtf32(o[mt], ah, al, bh, bl);
         }
     }
