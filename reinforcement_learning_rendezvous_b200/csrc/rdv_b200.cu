@@ -1061,9 +1061,9 @@ int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, in
             return RDV_ERR_CUDA;
         }
     }
-    const int64_t tiles = (n + tc::TM - 1) / tc::TM;
-    const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
-    tc::policy_tc_kernel<<<grid, tc::TM, sizeof(tc::Smem), (cudaStream_t)cuda_stream>>>(*pi, obs, actions, n);
+    const int64_t pairs = ((n + tc::TM - 1) / tc::TM + tc::GROUPS - 1) / tc::GROUPS;
+    const unsigned grid = (unsigned)(pairs < sm_count ? pairs : sm_count);
+    tc::policy_tc_kernel<<<grid, tc::GROUPS * tc::TM, sizeof(tc::Smem), (cudaStream_t)cuda_stream>>>(*pi, obs, actions, n);
     return launch_status();
 }
 

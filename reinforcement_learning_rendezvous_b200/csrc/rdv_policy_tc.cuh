@@ -11,7 +11,9 @@
 //   layer 3: D3[128x16] = A2 W2^T           8 K-steps x 3 (6 outputs padded to N = 16)
 //   tcgen05.ld D3 -> registers, + bias, clip -> actions
 //
-// A single thread issues the MMAs and commits them to an mbarrier; the 128 threads wait on it, pull their TMEM
+// A CTA runs TWO such 128-thread groups side by side (256 threads, shared weights, private activation tiles,
+// mbarriers, named barriers and TMEM columns), so the tensor-core phase of one tile overlaps the tanh epilogue of
+// the other.  Per group, a single thread issues the MMAs and commits them to an mbarrier; the 128 threads wait on it, pull their TMEM
 // lane with tcgen05.ld (32x32b: thread r of warp w <-> lane 32 w + r) and run the epilogue.  Every product is
 // 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo) so the result has fp32-level accuracy, like the reference's torch
 // policy; weights are split once per CTA.  Shared-memory operands use the canonical no-swizzle K-major UMMA
@@ -31,15 +33,16 @@ constexpr int TM = 128;                 // envs per tile = UMMA M = threads per 
 constexpr int H = 64;                   // hidden width
 constexpr int K0 = 24;                  // 17 inputs padded to 3 K-steps of 8
 constexpr int N3 = 16;                  // 6 outputs padded to the smallest legal UMMA N for M = 128
-constexpr uint32_t TMEM_COLS = 256;     // D1 @ 0..63, D2 @ 64..127, D3 @ 128..143 (power of two >= 144)
+constexpr uint32_t TMEM_COLS = 256;     // per group 128 columns: D1 @ +0..63, D2 @ +64..127, D3 re-uses +0..15
 
+constexpr int GROUPS = 2;               // independent 128-thread tile pipelines per CTA
 struct Smem {
-    float ah[(H / 4) * TM * 4], al[(H / 4) * TM * 4];            // activations, [chunk][row][4]
+    float ah[GROUPS][(H / 4) * TM * 4], al[GROUPS][(H / 4) * TM * 4];   // activations, [group][chunk][row][4]
     float w0h[(K0 / 4) * H * 4], w0l[(K0 / 4) * H * 4];          // [chunk][n][4]
     float w1h[(H / 4) * H * 4], w1l[(H / 4) * H * 4];
     float w2h[(H / 4) * N3 * 4], w2l[(H / 4) * N3 * 4];
     float b0[H], b1[H], b2[N3];
-    uint64_t mbar;
+    uint64_t mbar[GROUPS];
     uint32_t tmem_base;
 };
 
@@ -102,7 +105,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void load_weights(const float *w, int n_valid, int k_valid, int n_pad, int k_pad, float *wh,
                                              float *wl)
 {
-    for (int idx = threadIdx.x; idx < n_pad * k_pad; idx += TM) {
+    for (int idx = threadIdx.x; idx < n_pad * k_pad; idx += GROUPS * TM) {
         const int nn = idx / k_pad, k = idx % k_pad;
         const float x = (nn < n_valid && k < k_valid) ? w[nn * k_valid + k] : 0.0f;
         const float hi = tf32_hi(x);
@@ -113,14 +116,14 @@ __device__ __forceinline__ void load_weights(const float *w, int n_valid, int k_
 }
 
 // one layer: D[128 x n] (TMEM column d_col) = A[128 x 8*ksteps] W^T, 3xTF32, issued by the calling thread
-__device__ __forceinline__ void issue_layer(const Smem &s, uint32_t tmem_d, const float *wh, const float *wl, int n,
-                                            int ksteps, uint64_t *bar)
+__device__ __forceinline__ void issue_layer(const float *ah, const float *al, uint32_t tmem_d, const float *wh,
+                                            const float *wl, int n, int ksteps, uint64_t *bar)
 {
     const uint32_t idesc = umma_idesc(n);
     const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)n * 16;
     for (int kk = 0; kk < ksteps; ++kk) {
-        const uint64_t a_hi = umma_desc(s.ah + (size_t)kk * 2 * TM * 4, lbo_a, 128);
-        const uint64_t a_lo = umma_desc(s.al + (size_t)kk * 2 * TM * 4, lbo_a, 128);
+        const uint64_t a_hi = umma_desc(ah + (size_t)kk * 2 * TM * 4, lbo_a, 128);
+        const uint64_t a_lo = umma_desc(al + (size_t)kk * 2 * TM * 4, lbo_a, 128);
         const uint64_t b_hi = umma_desc(wh + (size_t)kk * 2 * n * 4, lbo_b, 128);
         const uint64_t b_lo = umma_desc(wl + (size_t)kk * 2 * n * 4, lbo_b, 128);
         umma_tf32(tmem_d, a_lo, b_hi, idesc, kk > 0 ? 1u : 0u);
@@ -130,23 +133,27 @@ __device__ __forceinline__ void issue_layer(const Smem &s, uint32_t tmem_d, cons
     umma_commit(bar);
 }
 
-__global__ void __launch_bounds__(TM, 1) policy_tc_kernel(const RdvPolicy pi, const float *obs, float *actions, int64_t n)
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory"); }
+
+__global__ void __launch_bounds__(GROUPS * TM, 1) policy_tc_kernel(const RdvPolicy pi, const float *obs, float *actions, int64_t n)
 {
     extern __shared__ __align__(128) unsigned char raw[];
     Smem &s = *reinterpret_cast<Smem *>(raw);
-    const int r = threadIdx.x, warp = r >> 5;
+    const int g = threadIdx.x / TM, r = threadIdx.x % TM, warp = r >> 5;      // group, row in tile, warp in group
+    float *ah = s.ah[g], *al = s.al[g];
+    uint64_t *mbar = &s.mbar[g];
 
     // ---- one-time set-up: weights (hi / lo), biases, mbarrier, TMEM ----
     load_weights(pi.w0, H, RDV_OBS_DIM, H, K0, s.w0h, s.w0l);
     load_weights(pi.w1, H, H, H, H, s.w1h, s.w1l);
     load_weights(pi.w2, RDV_ACT_DIM, H, N3, H, s.w2h, s.w2l);
-    if (r < H) { s.b0[r] = pi.b0[r]; s.b1[r] = pi.b1[r]; }
-    if (r < N3) s.b2[r] = r < RDV_ACT_DIM ? pi.b2[r] : 0.0f;
+    if (threadIdx.x < H) { s.b0[threadIdx.x] = pi.b0[threadIdx.x]; s.b1[threadIdx.x] = pi.b1[threadIdx.x]; }
+    if (threadIdx.x < N3) s.b2[threadIdx.x] = threadIdx.x < RDV_ACT_DIM ? pi.b2[threadIdx.x] : 0.0f;
     if (r == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s.mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -155,12 +162,13 @@ __global__ void __launch_bounds__(TM, 1) policy_tc_kernel(const RdvPolicy pi, co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = s.tmem_base;
+    const uint32_t tmem_all = s.tmem_base;
+    const uint32_t tmem = tmem_all + (uint32_t)g * 128;                    // this group's columns: D1 / D3 @ +0, D2 @ +64
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);       // this warp's 32 TMEM lanes
     uint32_t phase = 0;
 
     const int64_t tiles = (n + TM - 1) / TM;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + g; tile < tiles; tile += (int64_t)gridDim.x * GROUPS) {
         const int64_t env = tile * TM + r;
         const bool valid = env < n;
         // ---- A0: this thread's observation row, hi / lo, one float4 per 16-byte chunk ----
@@ -173,19 +181,19 @@ __global__ void __launch_bounds__(TM, 1) policy_tc_kernel(const RdvPolicy pi, co
                 float4 hi, lo;
                 hi.x = tf32_hi(x[4 * c]); hi.y = tf32_hi(x[4 * c + 1]); hi.z = tf32_hi(x[4 * c + 2]); hi.w = tf32_hi(x[4 * c + 3]);
                 lo.x = x[4 * c] - hi.x; lo.y = x[4 * c + 1] - hi.y; lo.z = x[4 * c + 2] - hi.z; lo.w = x[4 * c + 3] - hi.w;
-                reinterpret_cast<float4 *>(s.ah)[c * TM + r] = hi;
-                reinterpret_cast<float4 *>(s.al)[c * TM + r] = lo;
+                reinterpret_cast<float4 *>(ah)[c * TM + r] = hi;
+                reinterpret_cast<float4 *>(al)[c * TM + r] = lo;
             }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(g);
         // ---- layer 1 ----
         if (r == 0) {
             tc_fence_after();
-            issue_layer(s, tmem + 0, s.w0h, s.w0l, H, K0 / 8, &s.mbar);
+            issue_layer(ah, al, tmem + 0, s.w0h, s.w0l, H, K0 / 8, mbar);
         }
-        mbar_wait(&s.mbar, phase);
+        mbar_wait(mbar, phase);
         phase ^= 1;
         tc_fence_after();
 #pragma unroll
@@ -199,19 +207,19 @@ __global__ void __launch_bounds__(TM, 1) policy_tc_kernel(const RdvPolicy pi, co
                 float t2 = tanh_fast(v[4 * c + 2] + s.b0[16 * q + 4 * c + 2]), t3 = tanh_fast(v[4 * c + 3] + s.b0[16 * q + 4 * c + 3]);
                 hi.x = tf32_hi(t0); hi.y = tf32_hi(t1); hi.z = tf32_hi(t2); hi.w = tf32_hi(t3);
                 lo.x = t0 - hi.x; lo.y = t1 - hi.y; lo.z = t2 - hi.z; lo.w = t3 - hi.w;
-                reinterpret_cast<float4 *>(s.ah)[(4 * q + c) * TM + r] = hi;
-                reinterpret_cast<float4 *>(s.al)[(4 * q + c) * TM + r] = lo;
+                reinterpret_cast<float4 *>(ah)[(4 * q + c) * TM + r] = hi;
+                reinterpret_cast<float4 *>(al)[(4 * q + c) * TM + r] = lo;
             }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(g);
         // ---- layer 2 ----
         if (r == 0) {
             tc_fence_after();
-            issue_layer(s, tmem + 64, s.w1h, s.w1l, H, H / 8, &s.mbar);
+            issue_layer(ah, al, tmem + 64, s.w1h, s.w1l, H, H / 8, mbar);
         }
-        mbar_wait(&s.mbar, phase);
+        mbar_wait(mbar, phase);
         phase ^= 1;
         tc_fence_after();
 #pragma unroll
@@ -225,24 +233,24 @@ __global__ void __launch_bounds__(TM, 1) policy_tc_kernel(const RdvPolicy pi, co
                 float t2 = tanh_fast(v[4 * c + 2] + s.b1[16 * q + 4 * c + 2]), t3 = tanh_fast(v[4 * c + 3] + s.b1[16 * q + 4 * c + 3]);
                 hi.x = tf32_hi(t0); hi.y = tf32_hi(t1); hi.z = tf32_hi(t2); hi.w = tf32_hi(t3);
                 lo.x = t0 - hi.x; lo.y = t1 - hi.y; lo.z = t2 - hi.z; lo.w = t3 - hi.w;
-                reinterpret_cast<float4 *>(s.ah)[(4 * q + c) * TM + r] = hi;
-                reinterpret_cast<float4 *>(s.al)[(4 * q + c) * TM + r] = lo;
+                reinterpret_cast<float4 *>(ah)[(4 * q + c) * TM + r] = hi;
+                reinterpret_cast<float4 *>(al)[(4 * q + c) * TM + r] = lo;
             }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        // ---- layer 3 ----
+        group_sync(g);
+        // ---- layer 3 (D3 re-uses the columns of D1, which the layer-1 epilogue has drained) ----
         if (r == 0) {
             tc_fence_after();
-            issue_layer(s, tmem + 128, s.w2h, s.w2l, N3, H / 8, &s.mbar);
+            issue_layer(ah, al, tmem + 0, s.w2h, s.w2l, N3, H / 8, mbar);
         }
-        mbar_wait(&s.mbar, phase);
+        mbar_wait(mbar, phase);
         phase ^= 1;
         tc_fence_after();
         {
             float v[16];
-            tmem_ld16(lane_addr + 128, v);
+            tmem_ld16(lane_addr + 0, v);
             if (valid) {
 #pragma unroll
                 for (int j = 0; j < RDV_ACT_DIM; ++j)
@@ -250,12 +258,12 @@ __global__ void __launch_bounds__(TM, 1) policy_tc_kernel(const RdvPolicy pi, co
             }
         }
         tc_fence_before();
-        __syncthreads();                       // A tiles and TMEM columns are reused by the next tile
+        group_sync(g);                         // A tiles and TMEM columns are reused by the group's next tile
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS) : "memory");
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_all), "r"(TMEM_COLS) : "memory");
 }
 
 }  // namespace tc
