@@ -170,15 +170,18 @@ def run_cuda(args):
     # CPU baseline first (rank 0, N = 1 only), before CUDA is initialised in this process
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.subproc_vec_env import time_c_port, time_subproc_baseline
+        from oracle.subproc_vec_env import time_c_port, time_single_process, time_subproc_baseline
         cores = os.cpu_count() or 1
         res = time_subproc_baseline(steps=100000, warmup=2, n_procs=cores, seed=0, max_seconds=args.cpu_seconds)
+        single = time_single_process(seconds=min(3.0, args.cpu_seconds))
         cport = time_c_port(n_envs=4096, steps=10, threads=cores)
         cpu_baseline = {
             "value": res["value"], "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{res['steps']} VecEnv steps x {cores} envs (one per process, SubprocVecEnv protocol), "
                       f"random fp64 actions, numpy restatement of the reference env (bit-exact), "
                       f"{res['seconds']:.1f} s",
+            "single_process_value": single["value"],
+            "single_process_sample": f"one env in-process (DummyVecEnv style, main.py:33-34), {single['steps']} steps",
             "c_port_value": cport["value"],
             "c_port_sample": f"plain-C oracle, {cport['envs']} envs x {cport['steps']} steps on {cores} threads",
         }
@@ -300,6 +303,22 @@ def run_cuda(args):
     ms_flushed = sum(a.elapsed_time(b) for a, b in fe) / F / KL
     del flush
 
+    # ---------------- the same kernel without auto-reset: the first 16 steps after a batch reset ----------------
+    env_nr = BatchedRendezvousEnv(n, device=dev, seed=args.seed, env_offset=rank * n, auto_reset=False,
+                                  track_stats=False, integrator=args.integrator)
+    KN, RN = 16, 16
+    ne = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(RN)]
+    for j in range(RN + 2):
+        env_nr.reset()
+        if j >= 2:
+            ne[j - 2][0].record()
+        env_nr.rollout(KN, action_seed=args.seed + 1, step_base=j * KN)
+        if j >= 2:
+            ne[j - 2][1].record()
+    torch.cuda.synchronize()
+    ms_no_reset = sum(a.elapsed_time(b) for a, b in ne) / RN / KN
+    del env_nr
+
     # ---------------- per-step API (rdv_step, one launch per step, fp64 actions from a device ring) ----------------
     gen = torch.Generator(device=dev)
     gen.manual_seed(1 + rank)
@@ -393,8 +412,11 @@ def run_cuda(args):
                               "(action seed; global env id, step index)",
                    "steps_per_launch": KL,
                    "l2": "state lives in registers for the steps of a launch and is re-read from memory once per "
-                         "launch; ms_per_step_l2_flushed repeats the launches with a 256 MB L2 flush before each",
+                         "launch; ms_per_step_l2_flushed repeats the launches with a 256 MB L2 flush before each; "
+                         "ms_per_step_no_auto_reset = 16-step launches right after a batch reset, auto_reset off "
+                         "(includes 1/16 of a launch latency per step)",
                    "ms_per_step_l2_flushed": ms_flushed,
+                   "ms_per_step_no_auto_reset": ms_no_reset,
                    "parallelism": f"{world} x independent env shards, no data-path collective; one "
                                   "16-double statistics all-reduce per rollout"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": len(launches),

@@ -112,6 +112,24 @@ def time_subproc_baseline(steps, warmup=1, n_procs=None, seed=0, max_seconds=Non
     return dict(value=done_steps * venv.num_envs / dt, cores=venv.num_envs, steps=done_steps, seconds=dt)
 
 
+def time_single_process(seconds=3.0, seed=0, **env_kwargs):
+    """One env stepped in this process (what the reference's ``DummyVecEnv`` of main.py:33-34 does): random fp64
+    actions, reset on done, no IPC.  Returns dict(value=env-steps/s, steps, seconds)."""
+    from oracle.rdv_oracle import OracleEnv
+    env = OracleEnv(integrator=env_kwargs.pop("integrator", "restated"), rng=np.random.RandomState(seed), **env_kwargs)
+    rng = np.random.default_rng(seed)
+    env.reset()
+    steps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        _, _, done, _ = env.step(rng.uniform(-1, 1, 6))
+        if done:
+            env.reset()
+        steps += 1
+    dt = time.perf_counter() - t0
+    return dict(value=steps / dt, steps=steps, seconds=dt)
+
+
 def time_c_port(n_envs=4096, steps=20, threads=None, seed=0):
     """The plain-C oracle (oracle/rdv_oracle.c) on all host threads -- what a compiled CPU port achieves."""
     from oracle import c_oracle as CO

@@ -1,25 +1,32 @@
 // rdv_policy_tc.cuh -- the stand-alone batched actor forward (rdv_policy_forward: model.predict of the SB3
-// MlpPolicy, monte_carlo.py:128-133) on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators.
+// MlpPolicy, monte_carlo.py:128-133) on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators
+// AND TMEM-resident A operands.
 //
-// One CTA of 128 threads owns tiles of 128 environments (UMMA M = 128, one env per thread / TMEM lane):
+// A group of 128 threads owns tiles of 128 environments (UMMA M = 128, one env per thread / TMEM lane):
 //
-//   obs tile -> shared (A operand, K-major, hi / lo TF32 split)
-//   layer 1: D1[128x64] = A0[128x24] W0^T   tcgen05.mma kind::tf32, 3 K-steps x 3 products (3xTF32)
-//   tcgen05.ld D1 -> registers, + bias, tanh, split -> shared A1[128x64]
-//   layer 2: D2[128x64] = A1 W1^T           8 K-steps x 3
-//   tcgen05.ld D2 -> registers, + bias, tanh, split -> shared A2
-//   layer 3: D3[128x16] = A2 W2^T           8 K-steps x 3 (6 outputs padded to N = 16)
-//   tcgen05.ld D3 -> registers, + bias, clip -> actions
+//   obs tile: one 8.7 KB bulk copy (cp.async.bulk, mbarrier complete_tx) into shared memory, prefetched one tile
+//             ahead; every thread splits its row into TF32 hi / lo
+//   layer 1: D[128x64] = A0[128x24] W0^T    3 K-steps x 3 products (3xTF32); the bias rides in a padding column
+//   tcgen05.ld D -> registers, tanh, split -> A1 hi to TMEM (tcgen05.st), A1 lo to shared memory
+//   layer 2: D[128x64] = A1 W1^T            8 K-steps x 3
+//   tcgen05.ld D -> + bias, tanh, split -> A2
+//   layer 3: D[128x16] = A2 W2^T            8 K-steps x 3 (6 outputs padded to N = 16)
+//   tcgen05.ld D -> + bias, clip -> actions
 //
-// A CTA runs TWO such 128-thread groups side by side (256 threads, shared weights, private activation tiles,
-// mbarriers, named barriers and TMEM columns), so the tensor-core phase of one tile overlaps the tanh epilogue of
-// the other.  Per group, a single thread issues the MMAs and commits them to an mbarrier; the 128 threads wait on it, pull their TMEM
-// lane with tcgen05.ld (32x32b: thread r of warp w <-> lane 32 w + r) and run the epilogue.  Every product is
-// 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo) so the result has fp32-level accuracy, like the reference's torch
-// policy; weights are split once per CTA.  Shared-memory operands use the canonical no-swizzle K-major UMMA
-// layout: 8-row x 16-byte core matrices, rows of a core matrix 16 B apart, 8-row groups SBO = 128 B apart, the
-// two 16-byte K-chunks of a K = 8 step LBO = rows*16 B apart, i.e. element (r, k) lives at
-// ((k / 4) * rows + r) * 16 + (k % 4) * 4 bytes.  (Descriptor bit layouts: CUTLASS cute/arch/mma_sm100_desc.hpp.)
+// Every product is 3xTF32 (a_lo b_hi + a_hi b_lo + a_hi b_hi) so the result has fp32-level accuracy, like the
+// reference's torch policy.  The hi part of the activations never leaves the tensor-memory: the two products that
+// use it are issued in the "TS" form of tcgen05.mma (A from TMEM, lane = row, one 32-bit column per K element);
+// only the lo part goes through shared memory (K-major, no swizzle).  That halves the shared-memory footprint of
+// a tile, so a CTA runs FOUR 128-thread groups side by side (512 threads, shared weights; private mbarriers,
+// named barriers, 128 TMEM columns each: D @ +0..63, A hi @ +64..127): while one group waits for its MMAs or its
+// TMEM loads, three others run their tanh epilogues.  Per group a single thread issues the MMAs and commits them
+// to an mbarrier.  exp(2x) = 2^(2 log2(e) x): the factor 2 log2(e) is folded into W0, b0, W1, b1 when the weights
+// are split (once per CTA), so a hidden unit costs MUFU.EX2, a quarter of a MUFU.RCP, a handful of FP32 operations and the split.
+//
+// Shared-memory operands use the canonical no-swizzle K-major UMMA layout: 8-row x 16-byte core matrices, rows of
+// a core matrix 16 B apart, 8-row groups SBO = 128 B apart, the two 16-byte K-chunks of a K = 8 step
+// LBO = rows*16 B apart, i.e. element (r, k) lives at ((k / 4) * rows + r) * 16 + (k % 4) * 4 bytes.
+// (Descriptor bit layouts: CUTLASS cute/arch/mma_sm100_desc.hpp; instruction forms: cute/arch/mma_sm100_umma.hpp.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,20 +36,25 @@
 namespace rdv {
 namespace tc {
 
-constexpr int TM = 128;                 // envs per tile = UMMA M = threads per CTA
+constexpr int TM = 128;                 // envs per tile = UMMA M = threads per group
 constexpr int H = 64;                   // hidden width
-constexpr int K0 = 24;                  // 17 inputs padded to 3 K-steps of 8
+constexpr int K0 = 24;                  // 17 inputs + 1 bias column, padded to 3 K-steps of 8
 constexpr int N3 = 16;                  // 6 outputs padded to the smallest legal UMMA N for M = 128
-constexpr uint32_t TMEM_COLS = 256;     // per group 128 columns: D1 @ +0..63, D2 @ +64..127, D3 re-uses +0..15
+constexpr int GROUPS = 4;               // independent 128-thread tile pipelines per CTA
+constexpr uint32_t GROUP_COLS = 128;    // TMEM columns per group: D @ +0..63 (D3 @ +0..15), A hi @ +64..127
+constexpr uint32_t TMEM_COLS = GROUPS * GROUP_COLS;
+constexpr uint32_t A_COL = 64;
+constexpr int OBS_TILE = TM * RDV_OBS_DIM;              // floats of one observation tile (8704 B, 16 B multiple)
+constexpr float TANH_SCALE = 2.8853900817779268f;       // 2 log2(e)
 
-constexpr int GROUPS = 2;               // independent 128-thread tile pipelines per CTA
 struct Smem {
-    float ah[GROUPS][(H / 4) * TM * 4], al[GROUPS][(H / 4) * TM * 4];   // activations, [group][chunk][row][4]
+    float al[GROUPS][(H / 4) * TM * 4];                          // lo part of the activations, [group][chunk][row][4]
     float w0h[(K0 / 4) * H * 4], w0l[(K0 / 4) * H * 4];          // [chunk][n][4]
     float w1h[(H / 4) * H * 4], w1l[(H / 4) * H * 4];
     float w2h[(H / 4) * N3 * 4], w2l[(H / 4) * N3 * 4];
-    float b0[H], b1[H], b2[N3];
-    uint64_t mbar[GROUPS];
+    float obs[GROUPS][OBS_TILE];                                 // bulk-copy landing zone of the next tile
+    float b1[H], b2[N3];
+    uint64_t mma_bar[GROUPS], obs_bar[GROUPS];
     uint32_t tmem_base;
 };
 
@@ -62,12 +74,21 @@ __device__ __forceinline__ uint32_t umma_idesc(int n)
 {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate)
+// D += A B with A described in shared memory ("SS")
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         :: "r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D += A B with A read from tensor memory ("TS"): 128 lanes x 8 columns at tmem_a
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
@@ -81,77 +102,197 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+// 16 consecutive columns of this thread's TMEM lane -> registers; the registers are valid after tmem_ld_wait
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
 {
-    uint32_t r[16];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    // the registers are only valid after the wait: tie them to it so no use can be scheduled above
+}
+// wait for the outstanding tcgen05.ld; the registers are tied to the wait so no use can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16])
+{
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                  :: "memory");
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// weights [n_valid][k_valid] row-major -> chunked K-major hi / lo (zero padded to n_pad x k_pad)
-__device__ __forceinline__ void load_weights(const float *w, int n_valid, int k_valid, int n_pad, int k_pad, float *wh,
-                                             float *wl)
+// bulk copy global -> shared, completion counted in bytes on an mbarrier (one thread issues both)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
-    for (int idx = threadIdx.x; idx < n_pad * k_pad; idx += GROUPS * TM) {
-        const int nn = idx / k_pad, k = idx % k_pad;
-        const float x = (nn < n_valid && k < k_valid) ? w[nn * k_valid + k] : 0.0f;
-        const float hi = tf32_hi(x);
-        const int o = ((k >> 2) * n_pad + nn) * 4 + (k & 3);
-        wh[o] = hi;
-        wl[o] = x - hi;
-    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// one layer: D[128 x n] (TMEM column d_col) = A[128 x 8*ksteps] W^T, 3xTF32, issued by the calling thread
-__device__ __forceinline__ void issue_layer(const float *ah, const float *al, uint32_t tmem_d, const float *wh,
-                                            const float *wl, int n, int ksteps, uint64_t *bar)
+// weights [N_VALID][K_VALID] row-major (+ optional bias as column K_VALID), times `scale` -> chunked K-major
+// hi / lo, zero padded to N_PAD x K_PAD.  Two phases so that the global loads of all three layers are in flight
+// together before the first value is used.
+template <int N_VALID, int K_VALID, int N_PAD, int K_PAD>
+struct WeightTile {
+    static constexpr int PER = (N_PAD * K_PAD + GROUPS * TM - 1) / (GROUPS * TM);
+    float x[PER];
+    __device__ __forceinline__ void fetch(const float *__restrict__ w, const float *__restrict__ bias_col)
+    {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = threadIdx.x + i * GROUPS * TM;
+            const int nn = idx / K_PAD, k = idx % K_PAD;
+            x[i] = 0.0f;
+            if (idx < N_PAD * K_PAD && nn < N_VALID) {
+                if (k < K_VALID) x[i] = __ldg(w + nn * K_VALID + k);
+                else if (k == K_VALID && bias_col) x[i] = __ldg(bias_col + nn);
+            }
+        }
+    }
+    __device__ __forceinline__ void store(float scale, float *wh, float *wl) const
+    {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = threadIdx.x + i * GROUPS * TM;
+            if (idx < N_PAD * K_PAD) {
+                const int nn = idx / K_PAD, k = idx % K_PAD;
+                const float v = x[i] * scale, hi = tf32_hi(v);
+                const int o = ((k >> 2) * N_PAD + nn) * 4 + (k & 3);
+                wh[o] = hi;
+                wl[o] = v - hi;
+            }
+        }
+    }
+};
+
+// one layer: D[128 x n] (TMEM column d_col) = A[128 x 8*ksteps] W^T, 3xTF32, issued by the calling thread.
+// A hi: TMEM columns a_hi + 8 kk .. + 7; A lo: shared memory.
+__device__ __forceinline__ void issue_layer(uint32_t a_hi, const float *al, uint32_t tmem_d, const float *wh, const float *wl,
+                                            int n, int ksteps, uint64_t *bar)
 {
     const uint32_t idesc = umma_idesc(n);
     const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)n * 16;
     for (int kk = 0; kk < ksteps; ++kk) {
-        const uint64_t a_hi = umma_desc(ah + (size_t)kk * 2 * TM * 4, lbo_a, 128);
         const uint64_t a_lo = umma_desc(al + (size_t)kk * 2 * TM * 4, lbo_a, 128);
         const uint64_t b_hi = umma_desc(wh + (size_t)kk * 2 * n * 4, lbo_b, 128);
         const uint64_t b_lo = umma_desc(wl + (size_t)kk * 2 * n * 4, lbo_b, 128);
-        umma_tf32(tmem_d, a_lo, b_hi, idesc, kk > 0 ? 1u : 0u);
-        umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
-        umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+        umma_ss(tmem_d, a_lo, b_hi, idesc, kk > 0 ? 1u : 0u);
+        umma_ts(tmem_d, a_hi + 8 * kk, b_lo, idesc, 1u);
+        umma_ts(tmem_d, a_hi + 8 * kk, b_hi, idesc, 1u);
     }
     umma_commit(bar);
 }
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory"); }
 
+// exp-form tanh of four pre-scaled arguments z = 2 log2(e) x:  t = 1 - 2 / (1 + 2^z).  The MUFU unit (16 lanes per
+// SM) is the busiest pipe of the epilogue, so the four reciprocals share ONE MUFU.RCP: with a_i = 1 + 2^z_i,
+// 1 / a_0 = a_1 (a_2 a_3) / (a_0 a_1 a_2 a_3) and so on -- nine FMULs on the FMA pipe instead of three RCPs.
+// z is clamped to 31 (tanh already rounds to 1 in fp32 there), so the product of four stays below 2^127.
+__device__ __forceinline__ void tanh_scaled4(const float (&z)[4], float (&t)[4])
+{
+    float a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(z[j], 31.0f)));
+        a[j] = e + 1.0f;
+    }
+    const float p01 = a[0] * a[1], p23 = a[2] * a[3];
+    float rinv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(p01 * p23));
+    const float r01 = rinv * p23, r23 = rinv * p01;             // 1 / (a0 a1), 1 / (a2 a3)
+    t[0] = fmaf(-2.0f, r01 * a[1], 1.0f);
+    t[1] = fmaf(-2.0f, r01 * a[0], 1.0f);
+    t[2] = fmaf(-2.0f, r23 * a[3], 1.0f);
+    t[3] = fmaf(-2.0f, r23 * a[2], 1.0f);
+}
+
+// hidden-layer epilogue: D (64 columns of this thread's lane) -> tanh -> A hi (TMEM) / A lo (shared), the TMEM load
+// of the next 16 columns in flight while the current 16 are processed
+template <bool BIAS>
+__device__ __forceinline__ void hidden_epilogue(uint32_t lane_addr, const float *bias, float *al, int r)
+{
+    uint32_t va[16], vb[16];
+    tmem_ld16_issue(lane_addr, va);
+    tmem_ld_wait(va);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t (&cur)[16] = (q & 1) ? vb : va;
+        uint32_t (&nxt)[16] = (q & 1) ? va : vb;
+        if (q < 3) tmem_ld16_issue(lane_addr + 16 * (q + 1), nxt);
+        uint32_t hi[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float z[4], t[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                z[j] = __uint_as_float(cur[4 * c + j]);
+                if (BIAS) z[j] += bias[16 * q + 4 * c + j];
+            }
+            tanh_scaled4(z, t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hi[4 * c + j] = __float_as_uint(t[j]) & 0xffffe000u;
+                lo[j] = t[j] - __uint_as_float(hi[4 * c + j]);
+            }
+            reinterpret_cast<float4 *>(al)[(4 * q + c) * TM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        tmem_st16(lane_addr + A_COL + 16 * q, hi);
+        if (q < 3) tmem_ld_wait(nxt);
+    }
+    tmem_st_wait();
+}
+
 __global__ void __launch_bounds__(GROUPS * TM, 1) policy_tc_kernel(const RdvPolicy pi, const float *obs, float *actions, int64_t n)
 {
     extern __shared__ __align__(128) unsigned char raw[];
     Smem &s = *reinterpret_cast<Smem *>(raw);
     const int g = threadIdx.x / TM, r = threadIdx.x % TM, warp = r >> 5;      // group, row in tile, warp in group
-    float *ah = s.ah[g], *al = s.al[g];
-    uint64_t *mbar = &s.mbar[g];
+    float *al = s.al[g];
+    uint64_t *mma_bar = &s.mma_bar[g], *obs_bar = &s.obs_bar[g];
+    const int64_t tiles = (n + TM - 1) / TM, stride = (int64_t)gridDim.x * GROUPS;
+    const int64_t first = (int64_t)blockIdx.x * GROUPS + g;
+    const bool bulk_ok = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;        // cp.async.bulk needs 16-byte alignment
 
-    // ---- one-time set-up: weights (hi / lo), biases, mbarrier, TMEM ----
-    load_weights(pi.w0, H, RDV_OBS_DIM, H, K0, s.w0h, s.w0l);
-    load_weights(pi.w1, H, H, H, H, s.w1h, s.w1l);
-    load_weights(pi.w2, RDV_ACT_DIM, H, N3, H, s.w2h, s.w2l);
-    if (threadIdx.x < H) { s.b0[threadIdx.x] = pi.b0[threadIdx.x]; s.b1[threadIdx.x] = pi.b1[threadIdx.x]; }
-    if (threadIdx.x < N3) s.b2[threadIdx.x] = threadIdx.x < RDV_ACT_DIM ? pi.b2[threadIdx.x] : 0.0f;
+    // ---- one-time set-up: mbarriers, first observation tile in flight, weights (hi / lo), biases, TMEM ----
     if (r == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mma_bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(obs_bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (bulk_ok && first < tiles && (first + 1) * TM <= n)
+            bulk_load(s.obs[g], obs + first * OBS_TILE, OBS_TILE * 4, obs_bar);
+    }
+    {
+        WeightTile<H, RDV_OBS_DIM, H, K0> t0;
+        WeightTile<H, H, H, H> t1;
+        WeightTile<RDV_ACT_DIM, H, N3, H> t2;
+        t0.fetch(pi.w0, pi.b0);
+        t1.fetch(pi.w1, nullptr);
+        t2.fetch(pi.w2, nullptr);
+        const float bias1 = threadIdx.x < H ? __ldg(pi.b1 + threadIdx.x) : 0.0f;
+        const float bias2 = threadIdx.x < RDV_ACT_DIM ? __ldg(pi.b2 + threadIdx.x) : 0.0f;
+        t0.store(TANH_SCALE, s.w0h, s.w0l);
+        t1.store(TANH_SCALE, s.w1h, s.w1l);
+        t2.store(1.0f, s.w2h, s.w2l);
+        if (threadIdx.x < H) s.b1[threadIdx.x] = bias1 * TANH_SCALE;
+        if (threadIdx.x < N3) s.b2[threadIdx.x] = bias2;
     }
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -163,102 +304,96 @@ __global__ void __launch_bounds__(GROUPS * TM, 1) policy_tc_kernel(const RdvPoli
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_all = s.tmem_base;
-    const uint32_t tmem = tmem_all + (uint32_t)g * 128;                    // this group's columns: D1 / D3 @ +0, D2 @ +64
+    const uint32_t tmem = tmem_all + (uint32_t)g * GROUP_COLS;             // this group's columns
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);       // this warp's 32 TMEM lanes
-    uint32_t phase = 0;
+    uint32_t mma_phase = 0, obs_phase = 0;
 
-    const int64_t tiles = (n + TM - 1) / TM;
-    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + g; tile < tiles; tile += (int64_t)gridDim.x * GROUPS) {
+    for (int64_t tile = first; tile < tiles; tile += stride) {
         const int64_t env = tile * TM + r;
-        const bool valid = env < n;
-        // ---- A0: this thread's observation row, hi / lo, one float4 per 16-byte chunk ----
+        const bool valid = env < n, staged = bulk_ok && (tile + 1) * TM <= n;
+        // ---- A0: this thread's observation row (+ the constant 1 of the bias column), hi -> TMEM, lo -> shared ----
         {
             float x[K0];
+            if (staged) {
+                mbar_wait(obs_bar, obs_phase);
+                obs_phase ^= 1;
 #pragma unroll
-            for (int k = 0; k < K0; ++k) x[k] = (valid && k < RDV_OBS_DIM) ? obs[env * RDV_OBS_DIM + k] : 0.0f;
+                for (int k = 0; k < RDV_OBS_DIM; ++k) x[k] = s.obs[g][r * RDV_OBS_DIM + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < RDV_OBS_DIM; ++k) x[k] = valid ? obs[env * RDV_OBS_DIM + k] : 0.0f;
+            }
+            x[RDV_OBS_DIM] = 1.0f;
+#pragma unroll
+            for (int k = RDV_OBS_DIM + 1; k < K0; ++k) x[k] = 0.0f;
+            uint32_t hi[K0];
 #pragma unroll
             for (int c = 0; c < K0 / 4; ++c) {
-                float4 hi, lo;
-                hi.x = tf32_hi(x[4 * c]); hi.y = tf32_hi(x[4 * c + 1]); hi.z = tf32_hi(x[4 * c + 2]); hi.w = tf32_hi(x[4 * c + 3]);
-                lo.x = x[4 * c] - hi.x; lo.y = x[4 * c + 1] - hi.y; lo.z = x[4 * c + 2] - hi.z; lo.w = x[4 * c + 3] - hi.w;
-                reinterpret_cast<float4 *>(ah)[c * TM + r] = hi;
-                reinterpret_cast<float4 *>(al)[c * TM + r] = lo;
+                float lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hi[4 * c + j] = __float_as_uint(x[4 * c + j]) & 0xffffe000u;
+                    lo[j] = x[4 * c + j] - __uint_as_float(hi[4 * c + j]);
+                }
+                reinterpret_cast<float4 *>(al)[c * TM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
+            uint32_t h0[16], h1[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h0[j] = hi[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h1[j] = hi[16 + j];
+            tmem_st16(lane_addr + A_COL, h0);
+            tmem_st8(lane_addr + A_COL + 16, h1);
+            tmem_st_wait();
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
-        // ---- layer 1 ----
+        // ---- layer 1 (and the bulk copy of this group's next tile: every thread has consumed the landing zone) ----
         if (r == 0) {
             tc_fence_after();
-            issue_layer(ah, al, tmem + 0, s.w0h, s.w0l, H, K0 / 8, mbar);
+            issue_layer(tmem + A_COL, al, tmem, s.w0h, s.w0l, H, K0 / 8, mma_bar);
+            const int64_t next = tile + stride;
+            if (bulk_ok && next < tiles && (next + 1) * TM <= n) bulk_load(s.obs[g], obs + next * OBS_TILE, OBS_TILE * 4, obs_bar);
         }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1;
         tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {                                  // 64 columns, 16 at a time
-            float v[16];
-            tmem_ld16(lane_addr + 0 + 16 * q, v);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float4 hi, lo;
-                float t0 = tanh_fast(v[4 * c] + s.b0[16 * q + 4 * c]), t1 = tanh_fast(v[4 * c + 1] + s.b0[16 * q + 4 * c + 1]);
-                float t2 = tanh_fast(v[4 * c + 2] + s.b0[16 * q + 4 * c + 2]), t3 = tanh_fast(v[4 * c + 3] + s.b0[16 * q + 4 * c + 3]);
-                hi.x = tf32_hi(t0); hi.y = tf32_hi(t1); hi.z = tf32_hi(t2); hi.w = tf32_hi(t3);
-                lo.x = t0 - hi.x; lo.y = t1 - hi.y; lo.z = t2 - hi.z; lo.w = t3 - hi.w;
-                reinterpret_cast<float4 *>(ah)[(4 * q + c) * TM + r] = hi;
-                reinterpret_cast<float4 *>(al)[(4 * q + c) * TM + r] = lo;
-            }
-        }
+        hidden_epilogue<false>(lane_addr, nullptr, al, r);
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
-        // ---- layer 2 ----
+        // ---- layer 2 (D is reused: the layer-1 epilogue has drained it) ----
         if (r == 0) {
             tc_fence_after();
-            issue_layer(ah, al, tmem + 64, s.w1h, s.w1l, H, H / 8, mbar);
+            issue_layer(tmem + A_COL, al, tmem, s.w1h, s.w1l, H, H / 8, mma_bar);
         }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1;
         tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float v[16];
-            tmem_ld16(lane_addr + 64 + 16 * q, v);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float4 hi, lo;
-                float t0 = tanh_fast(v[4 * c] + s.b1[16 * q + 4 * c]), t1 = tanh_fast(v[4 * c + 1] + s.b1[16 * q + 4 * c + 1]);
-                float t2 = tanh_fast(v[4 * c + 2] + s.b1[16 * q + 4 * c + 2]), t3 = tanh_fast(v[4 * c + 3] + s.b1[16 * q + 4 * c + 3]);
-                hi.x = tf32_hi(t0); hi.y = tf32_hi(t1); hi.z = tf32_hi(t2); hi.w = tf32_hi(t3);
-                lo.x = t0 - hi.x; lo.y = t1 - hi.y; lo.z = t2 - hi.z; lo.w = t3 - hi.w;
-                reinterpret_cast<float4 *>(ah)[(4 * q + c) * TM + r] = hi;
-                reinterpret_cast<float4 *>(al)[(4 * q + c) * TM + r] = lo;
-            }
-        }
+        hidden_epilogue<true>(lane_addr, s.b1, al, r);
         fence_async_smem();
         tc_fence_before();
         group_sync(g);
-        // ---- layer 3 (D3 re-uses the columns of D1, which the layer-1 epilogue has drained) ----
+        // ---- layer 3 ----
         if (r == 0) {
             tc_fence_after();
-            issue_layer(ah, al, tmem + 0, s.w2h, s.w2l, N3, H / 8, mbar);
+            issue_layer(tmem + A_COL, al, tmem, s.w2h, s.w2l, N3, H / 8, mma_bar);
         }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1;
         tc_fence_after();
         {
-            float v[16];
-            tmem_ld16(lane_addr + 0, v);
+            uint32_t v[16];
+            tmem_ld16_issue(lane_addr, v);
+            tmem_ld_wait(v);
             if (valid) {
 #pragma unroll
                 for (int j = 0; j < RDV_ACT_DIM; ++j)
-                    actions[env * RDV_ACT_DIM + j] = fminf(1.0f, fmaxf(-1.0f, v[j] + s.b2[j]));     // np.clip
+                    actions[env * RDV_ACT_DIM + j] = fminf(1.0f, fmaxf(-1.0f, __uint_as_float(v[j]) + s.b2[j]));  // np.clip
             }
         }
-        tc_fence_before();
-        group_sync(g);                         // A tiles and TMEM columns are reused by the group's next tile
+        // the next tile's A0 stores and layer-1 MMAs are ordered after these loads by the fences around its group_sync
     }
     tc_fence_before();
     __syncthreads();
