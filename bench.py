@@ -358,7 +358,7 @@ def run_cuda(args):
         policy_rollout = {"value": world * n * (KP // KL) * KL / (pms * 1e-3), "unit": UNIT,
                           "ms_per_step": pms / ((KP // KL) * KL), "steps": (KP // KL) * KL,
                           "policy": "SB3 MlpPolicy actor 17-64-64-6 tanh (models/mlp_model_best weights), deterministic, "
-                                    "3xTF32 mma.sync inside rollout_kernel"}
+                                    "3xTF32 tcgen05.mma (TMEM-resident activations) inside rollout_kernel"}
 
     # ---------------- end-to-end leg: numpy actions in, numpy results out, through the VecEnv ----------------
     del env

@@ -410,26 +410,28 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 // at a barrier every step: the step is ~60 KB of straight-line code, and warps that drift apart thrash the
 // instruction cache (measured: 58 % hit rate and 3.1 of 6.2 stall cycles per instruction on "no instruction"
 // with four independent 64-thread CTAs per SM; in-phase warps run the same workload 1.7x faster).
-// POLICY: the action of every step is the deterministic output of the SB3 MlpPolicy actor evaluated by the warp on
-// the tensor cores (rdv_policy.cuh) from the observation the previous step produced.
+// POLICY: the action of every step is the output of the SB3 MlpPolicy actor, evaluated on the tensor cores
+// (tcgen05 / TMEM, rdv_policy_tc.cuh: groups of 128 threads = 128 envs = one UMMA tile) from the observation the
+// previous step produced.
 template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false>
 __global__ void __launch_bounds__(TPB_, 1)
 rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __grid_constant__ RdvRolloutIO io,
                const int64_t n, const uint64_t seed, const int64_t env_offset)
 {
     constexpr int NW = TPB_ / 32;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    PolicyShared *ps = reinterpret_cast<PolicyShared *>(dyn_smem);
-    if (POLICY) {
-        policy_load(io.policy, *ps);
-        __syncthreads();
-    }
-    __shared__ __align__(16) float s_obs[NW][32 * RDV_OBS_DIM];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    tc::TileSmem *ts = reinterpret_cast<tc::TileSmem *>(dyn_smem);
+    uint32_t tmem_all = 0, mma_phase = 0;
+    if (POLICY) tmem_all = tc::tile_setup<TPB_>(io.policy, *ts);
+    __shared__ __align__(16) float s_obs[POLICY ? 1 : NW][32 * RDV_OBS_DIM];
     __shared__ double s_stats[NW][RDV_NSTATS];
     __shared__ double s_team[NW][4][RDV_TEAM_ROW];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int src = io.action_source;
+    // the warp's observation staging row; with the fused actor it borrows the group's activation tile, which is
+    // only live between the step barrier and the end of the actor's third layer
+    float *obs_stage = POLICY ? ts->al[warp >> 2] + (warp & 3) * (32 * RDV_OBS_DIM) : s_obs[POLICY ? 0 : warp];
     // this CTA's slice [lo, hi) and its passes
     const int64_t lo = n * (int64_t)blockIdx.x / gridDim.x, hi = n * ((int64_t)blockIdx.x + 1) / gridDim.x;
     const int64_t span = hi - lo;
@@ -461,18 +463,18 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
             ActionTerms t;
             const int64_t row = (int64_t)k * n + i;
             if (POLICY) {
-                float *stage = s_obs[warp];
-#pragma unroll
-                for (int j = 0; j < RDV_OBS_DIM; ++j) stage[lane * RDV_OBS_DIM + j] = ov[j];
-                __syncwarp();
+                // the CTA's threads form groups of 128 (the last one may be smaller); a group runs its tile of envs
+                // through the actor on the tensor cores: thread = row = TMEM lane
                 float a[RDV_ACT_DIM];
-                policy_forward_warp(*ps, stage, stage, a);
+                const int g = threadIdx.x >> 7;
+                tc::tile_forward(*ts, g, threadIdx.x & 127, TPB_ - 128 * g < 128 ? TPB_ - 128 * g : 128, ov,
+                                 tmem_all + (uint32_t)g * tc::GROUP_COLS, mma_phase, a, [] {});
                 const bool sample = src == RDV_ACTIONS_POLICY_SAMPLE;
                 if (sample) {                                     // a ~ N(mean, exp(log_std)^2)
                     float z[RDV_ACT_DIM];
                     philox_normals(io.action_seed, env_id, io.step_base + k, z);
 #pragma unroll
-                    for (int j = 0; j < RDV_ACT_DIM; ++j) a[j] = fmaf(ps->std[j], z[j], a[j]);
+                    for (int j = 0; j < RDV_ACT_DIM; ++j) a[j] = fmaf(ts->std[j], z[j], a[j]);
                 }
                 float ac[RDV_ACT_DIM];
 #pragma unroll
@@ -555,12 +557,12 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
             }
             // ---- per-step observation record (post-reset for finished envs), coalesced via the warp's row ----
             if (io.obs_steps) {
-                float *o = s_obs[warp] + lane * RDV_OBS_DIM;
+                float *o = obs_stage + lane * RDV_OBS_DIM;
 #pragma unroll
                 for (int j = 0; j < RDV_OBS_DIM; ++j) o[j] = ov[j];
                 __syncwarp();
                 float *dst = io.obs_steps + ((int64_t)k * n + warp_base) * RDV_OBS_DIM;
-                for (int j = lane; j < rows_w * RDV_OBS_DIM; j += 32) dst[j] = s_obs[warp][j];
+                for (int j = lane; j < rows_w * RDV_OBS_DIM; j += 32) dst[j] = obs_stage[j];
                 __syncwarp();
             }
         }
@@ -570,15 +572,16 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
             store_env(S, i, e);
             store_counters(S, i, c);
         }
-        float *o = s_obs[warp] + lane * RDV_OBS_DIM;
+        float *o = obs_stage + lane * RDV_OBS_DIM;
 #pragma unroll
         for (int j = 0; j < RDV_OBS_DIM; ++j) o[j] = ov[j];
         __syncwarp();
         float *dst = io.obs + warp_base * RDV_OBS_DIM;
-        for (int j = lane; j < rows_w * RDV_OBS_DIM; j += 32) dst[j] = s_obs[warp][j];
+        for (int j = lane; j < rows_w * RDV_OBS_DIM; j += 32) dst[j] = obs_stage[j];
         __syncwarp();
     }
     if (io.stats) reduce_stats<NW>(st, io.stats, s_stats);
+    if (POLICY) tc::tile_teardown(tmem_all);
 }
 
 // ---------------------------------------------------------------------------------
@@ -964,10 +967,10 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
         static bool attr_done = false;                                                                            \
         if (!attr_done) {                                                                                         \
             if (cudaFuncSetAttribute(rollout_kernel<true, false, T_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)sizeof(PolicyShared)) != cudaSuccess) return RDV_ERR_CUDA;              \
+                                     (int)sizeof(tc::TileSmem)) != cudaSuccess) return RDV_ERR_CUDA;              \
             attr_done = true;                                                                                     \
         }                                                                                                         \
-        rollout_kernel<true, false, T_, true><<<(unsigned)grid, T_, sizeof(PolicyShared), st>>>(*p, *s, *io, n, seed, \
+        rollout_kernel<true, false, T_, true><<<(unsigned)grid, T_, sizeof(tc::TileSmem), st>>>(*p, *s, *io, n, seed, \
                                                                                                 env_offset);      \
     }
     if (policy) {

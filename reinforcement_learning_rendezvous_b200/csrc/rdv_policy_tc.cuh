@@ -47,16 +47,23 @@ constexpr uint32_t A_COL = 64;
 constexpr int OBS_TILE = TM * RDV_OBS_DIM;              // floats of one observation tile (8704 B, 16 B multiple)
 constexpr float TANH_SCALE = 2.8853900817779268f;       // 2 log2(e)
 
-struct Smem {
+// what a tile forward needs: lo activations per group, split weights, biases, MMA mbarriers, the TMEM base
+struct TileSmem {
     float al[GROUPS][(H / 4) * TM * 4];                          // lo part of the activations, [group][chunk][row][4]
     float w0h[(K0 / 4) * H * 4], w0l[(K0 / 4) * H * 4];          // [chunk][n][4]
     float w1h[(H / 4) * H * 4], w1l[(H / 4) * H * 4];
     float w2h[(H / 4) * N3 * 4], w2l[(H / 4) * N3 * 4];
-    float obs[GROUPS][OBS_TILE];                                 // bulk-copy landing zone of the next tile
-    float b1[H], b2[N3];
-    uint64_t mma_bar[GROUPS], obs_bar[GROUPS];
-    uint32_t tmem_base;
+    float b1[H], b2[N3], std[8];                                 // std = exp(log_std) (0 without a Gaussian head)
+    uint64_t mma_bar[GROUPS];
+    uint32_t tmem_base, pad[3];
 };
+// the stand-alone kernel adds the bulk-copy landing zone of the next observation tile
+struct Smem {
+    TileSmem t;
+    float obs[GROUPS][OBS_TILE];
+    uint64_t obs_bar[GROUPS];
+};
+static_assert(sizeof(TileSmem) % 16 == 0, "observation landing zone must stay 16-byte aligned");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -148,15 +155,15 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
 // weights [N_VALID][K_VALID] row-major (+ optional bias as column K_VALID), times `scale` -> chunked K-major
 // hi / lo, zero padded to N_PAD x K_PAD.  Two phases so that the global loads of all three layers are in flight
 // together before the first value is used.
-template <int N_VALID, int K_VALID, int N_PAD, int K_PAD>
+template <int NT, int N_VALID, int K_VALID, int N_PAD, int K_PAD>
 struct WeightTile {
-    static constexpr int PER = (N_PAD * K_PAD + GROUPS * TM - 1) / (GROUPS * TM);
+    static constexpr int PER = (N_PAD * K_PAD + NT - 1) / NT;
     float x[PER];
     __device__ __forceinline__ void fetch(const float *__restrict__ w, const float *__restrict__ bias_col)
     {
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            const int idx = threadIdx.x + i * GROUPS * TM;
+            const int idx = threadIdx.x + i * NT;
             const int nn = idx / K_PAD, k = idx % K_PAD;
             x[i] = 0.0f;
             if (idx < N_PAD * K_PAD && nn < N_VALID) {
@@ -169,7 +176,7 @@ struct WeightTile {
     {
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            const int idx = threadIdx.x + i * GROUPS * TM;
+            const int idx = threadIdx.x + i * NT;
             if (idx < N_PAD * K_PAD) {
                 const int nn = idx / K_PAD, k = idx % K_PAD;
                 const float v = x[i] * scale, hi = tf32_hi(v);
@@ -199,7 +206,11 @@ __device__ __forceinline__ void issue_layer(uint32_t a_hi, const float *al, uint
     umma_commit(bar);
 }
 
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory"); }
+// named barrier of group g (`threads` = 128, or fewer in the last group of a CTA that is not a multiple of 128)
+__device__ __forceinline__ void group_sync(int g, int threads)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "r"(threads) : "memory");
+}
 
 // exp-form tanh of four pre-scaled arguments z = 2 log2(e) x:  t = 1 - 2 / (1 + 2^z).  The MUFU unit (16 lanes per
 // SM) is the busiest pipe of the epilogue, so the four reciprocals share ONE MUFU.RCP: with a_i = 1 + 2^z_i,
@@ -260,39 +271,33 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t lane_addr, const float 
     tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(GROUPS * TM, 1) policy_tc_kernel(const RdvPolicy pi, const float *obs, float *actions, int64_t n)
+// Whole CTA of NT threads, once per launch: weights (hi / lo, tanh factor folded in), biases, the groups' MMA
+// mbarriers, 512 TMEM columns.  Ends with a __syncthreads; returns the TMEM base address.
+template <int NT>
+__device__ __forceinline__ uint32_t tile_setup(const RdvPolicy &pi, TileSmem &s)
 {
-    extern __shared__ __align__(128) unsigned char raw[];
-    Smem &s = *reinterpret_cast<Smem *>(raw);
-    const int g = threadIdx.x / TM, r = threadIdx.x % TM, warp = r >> 5;      // group, row in tile, warp in group
-    float *al = s.al[g];
-    uint64_t *mma_bar = &s.mma_bar[g], *obs_bar = &s.obs_bar[g];
-    const int64_t tiles = (n + TM - 1) / TM, stride = (int64_t)gridDim.x * GROUPS;
-    const int64_t first = (int64_t)blockIdx.x * GROUPS + g;
-    const bool bulk_ok = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;        // cp.async.bulk needs 16-byte alignment
-
-    // ---- one-time set-up: mbarriers, first observation tile in flight, weights (hi / lo), biases, TMEM ----
-    if (r == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mma_bar)) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(obs_bar)) : "memory");
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s.mma_bar[g])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (bulk_ok && first < tiles && (first + 1) * TM <= n)
-            bulk_load(s.obs[g], obs + first * OBS_TILE, OBS_TILE * 4, obs_bar);
     }
     {
-        WeightTile<H, RDV_OBS_DIM, H, K0> t0;
-        WeightTile<H, H, H, H> t1;
-        WeightTile<RDV_ACT_DIM, H, N3, H> t2;
+        WeightTile<NT, H, RDV_OBS_DIM, H, K0> t0;
+        WeightTile<NT, H, H, H, H> t1;
+        WeightTile<NT, RDV_ACT_DIM, H, N3, H> t2;
         t0.fetch(pi.w0, pi.b0);
         t1.fetch(pi.w1, nullptr);
         t2.fetch(pi.w2, nullptr);
         const float bias1 = threadIdx.x < H ? __ldg(pi.b1 + threadIdx.x) : 0.0f;
         const float bias2 = threadIdx.x < RDV_ACT_DIM ? __ldg(pi.b2 + threadIdx.x) : 0.0f;
+        const float lstd = (threadIdx.x < RDV_ACT_DIM && pi.log_std) ? __ldg(pi.log_std + threadIdx.x) : 0.0f;
         t0.store(TANH_SCALE, s.w0h, s.w0l);
         t1.store(TANH_SCALE, s.w1h, s.w1l);
         t2.store(1.0f, s.w2h, s.w2l);
         if (threadIdx.x < H) s.b1[threadIdx.x] = bias1 * TANH_SCALE;
         if (threadIdx.x < N3) s.b2[threadIdx.x] = bias2;
+        if (threadIdx.x < 8) s.std[threadIdx.x] = (threadIdx.x < RDV_ACT_DIM && pi.log_std) ? expf(lstd) : 0.0f;
     }
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -303,102 +308,144 @@ __global__ void __launch_bounds__(GROUPS * TM, 1) policy_tc_kernel(const RdvPoli
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_all = s.tmem_base;
+    return s.tmem_base;
+}
+// Whole CTA, after the last tile_forward.
+__device__ __forceinline__ void tile_teardown(uint32_t tmem_all)
+{
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_all), "r"(TMEM_COLS) : "memory");
+}
+
+// One tile through the actor, called by all `threads` threads of group g (thread r owns row r = its TMEM lane).
+// x: the row's 17 observations; out: the actor's mean action, NOT clipped.  `after_issue` runs on the issuing
+// thread right after the layer-1 MMAs are queued (every thread of the group is past its use of shared staging).
+template <class F>
+__device__ __forceinline__ void tile_forward(TileSmem &s, int g, int r, int threads, const float (&x)[RDV_OBS_DIM],
+                                             uint32_t tmem, uint32_t &phase, float (&out)[RDV_ACT_DIM], F &&after_issue)
+{
+    float *al = s.al[g];
+    uint64_t *bar = &s.mma_bar[g];
+    const uint32_t lane_addr = tmem + ((uint32_t)(r & ~31) << 16);         // this warp's 32 TMEM lanes
+    // ---- A0: the observation row and the constant 1 of the bias column, hi -> TMEM, lo -> shared ----
+    {
+        uint32_t hi[K0];
+#pragma unroll
+        for (int c = 0; c < K0 / 4; ++c) {
+            float lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * c + j;
+                const float v = k < RDV_OBS_DIM ? x[k < RDV_OBS_DIM ? k : 0] : (k == RDV_OBS_DIM ? 1.0f : 0.0f);
+                hi[k] = __float_as_uint(v) & 0xffffe000u;
+                lo[j] = v - __uint_as_float(hi[k]);
+            }
+            reinterpret_cast<float4 *>(al)[c * TM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        uint32_t h0[16], h1[8];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h0[j] = hi[j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h1[j] = hi[16 + j];
+        tmem_st16(lane_addr + A_COL, h0);
+        tmem_st8(lane_addr + A_COL + 16, h1);
+        tmem_st_wait();
+    }
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(g, threads);
+    // ---- layer 1 ----
+    if (r == 0) {
+        tc_fence_after();
+        issue_layer(tmem + A_COL, al, tmem, s.w0h, s.w0l, H, K0 / 8, bar);
+        after_issue();
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    hidden_epilogue<false>(lane_addr, nullptr, al, r);
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(g, threads);
+    // ---- layer 2 (D is reused: the layer-1 epilogue has drained it) ----
+    if (r == 0) {
+        tc_fence_after();
+        issue_layer(tmem + A_COL, al, tmem, s.w1h, s.w1l, H, H / 8, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    hidden_epilogue<true>(lane_addr, s.b1, al, r);
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(g, threads);
+    // ---- layer 3 ----
+    if (r == 0) {
+        tc_fence_after();
+        issue_layer(tmem + A_COL, al, tmem, s.w2h, s.w2l, N3, H / 8, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+        uint32_t v[16];
+        tmem_ld16_issue(lane_addr, v);
+        tmem_ld_wait(v);
+#pragma unroll
+        for (int j = 0; j < RDV_ACT_DIM; ++j) out[j] = __uint_as_float(v[j]) + s.b2[j];
+    }
+    // the next tile's A0 stores and layer-1 MMAs are ordered after these loads by the fences around its first
+    // group_sync
+    tc_fence_before();
+}
+
+__global__ void __launch_bounds__(GROUPS * TM, 1) policy_tc_kernel(const RdvPolicy pi, const float *obs, float *actions, int64_t n)
+{
+    extern __shared__ __align__(128) unsigned char raw[];
+    Smem &s = *reinterpret_cast<Smem *>(raw);
+    const int g = threadIdx.x / TM, r = threadIdx.x % TM;                  // group, row in tile
+    uint64_t *obs_bar = &s.obs_bar[g];
+    const int64_t tiles = (n + TM - 1) / TM, stride = (int64_t)gridDim.x * GROUPS;
+    const int64_t first = (int64_t)blockIdx.x * GROUPS + g;
+    const bool bulk_ok = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;        // cp.async.bulk needs 16-byte alignment
+
+    // the first observation tile is in flight while the weights are split
+    if (r == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(obs_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (bulk_ok && first < tiles && (first + 1) * TM <= n)
+            bulk_load(s.obs[g], obs + first * OBS_TILE, OBS_TILE * 4, obs_bar);
+    }
+    const uint32_t tmem_all = tile_setup<GROUPS * TM>(pi, s.t);
     const uint32_t tmem = tmem_all + (uint32_t)g * GROUP_COLS;             // this group's columns
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);       // this warp's 32 TMEM lanes
     uint32_t mma_phase = 0, obs_phase = 0;
 
     for (int64_t tile = first; tile < tiles; tile += stride) {
         const int64_t env = tile * TM + r;
         const bool valid = env < n, staged = bulk_ok && (tile + 1) * TM <= n;
-        // ---- A0: this thread's observation row (+ the constant 1 of the bias column), hi -> TMEM, lo -> shared ----
-        {
-            float x[K0];
-            if (staged) {
-                mbar_wait(obs_bar, obs_phase);
-                obs_phase ^= 1;
+        float x[RDV_OBS_DIM], a[RDV_ACT_DIM];
+        if (staged) {
+            mbar_wait(obs_bar, obs_phase);
+            obs_phase ^= 1;
 #pragma unroll
-                for (int k = 0; k < RDV_OBS_DIM; ++k) x[k] = s.obs[g][r * RDV_OBS_DIM + k];
-            } else {
+            for (int k = 0; k < RDV_OBS_DIM; ++k) x[k] = s.obs[g][r * RDV_OBS_DIM + k];
+        } else {
 #pragma unroll
-                for (int k = 0; k < RDV_OBS_DIM; ++k) x[k] = valid ? obs[env * RDV_OBS_DIM + k] : 0.0f;
-            }
-            x[RDV_OBS_DIM] = 1.0f;
-#pragma unroll
-            for (int k = RDV_OBS_DIM + 1; k < K0; ++k) x[k] = 0.0f;
-            uint32_t hi[K0];
-#pragma unroll
-            for (int c = 0; c < K0 / 4; ++c) {
-                float lo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    hi[4 * c + j] = __float_as_uint(x[4 * c + j]) & 0xffffe000u;
-                    lo[j] = x[4 * c + j] - __uint_as_float(hi[4 * c + j]);
-                }
-                reinterpret_cast<float4 *>(al)[c * TM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            uint32_t h0[16], h1[8];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) h0[j] = hi[j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) h1[j] = hi[16 + j];
-            tmem_st16(lane_addr + A_COL, h0);
-            tmem_st8(lane_addr + A_COL + 16, h1);
-            tmem_st_wait();
+            for (int k = 0; k < RDV_OBS_DIM; ++k) x[k] = valid ? obs[env * RDV_OBS_DIM + k] : 0.0f;
         }
-        fence_async_smem();
-        tc_fence_before();
-        group_sync(g);
-        // ---- layer 1 (and the bulk copy of this group's next tile: every thread has consumed the landing zone) ----
-        if (r == 0) {
-            tc_fence_after();
-            issue_layer(tmem + A_COL, al, tmem, s.w0h, s.w0l, H, K0 / 8, mma_bar);
+        tile_forward(s.t, g, r, TM, x, tmem, mma_phase, a, [&] {
+            // bulk copy of this group's next tile: every thread has consumed the landing zone
             const int64_t next = tile + stride;
             if (bulk_ok && next < tiles && (next + 1) * TM <= n) bulk_load(s.obs[g], obs + next * OBS_TILE, OBS_TILE * 4, obs_bar);
-        }
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1;
-        tc_fence_after();
-        hidden_epilogue<false>(lane_addr, nullptr, al, r);
-        fence_async_smem();
-        tc_fence_before();
-        group_sync(g);
-        // ---- layer 2 (D is reused: the layer-1 epilogue has drained it) ----
-        if (r == 0) {
-            tc_fence_after();
-            issue_layer(tmem + A_COL, al, tmem, s.w1h, s.w1l, H, H / 8, mma_bar);
-        }
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1;
-        tc_fence_after();
-        hidden_epilogue<true>(lane_addr, s.b1, al, r);
-        fence_async_smem();
-        tc_fence_before();
-        group_sync(g);
-        // ---- layer 3 ----
-        if (r == 0) {
-            tc_fence_after();
-            issue_layer(tmem + A_COL, al, tmem, s.w2h, s.w2l, N3, H / 8, mma_bar);
-        }
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1;
-        tc_fence_after();
-        {
-            uint32_t v[16];
-            tmem_ld16_issue(lane_addr, v);
-            tmem_ld_wait(v);
-            if (valid) {
+        });
+        if (valid) {
 #pragma unroll
-                for (int j = 0; j < RDV_ACT_DIM; ++j)
-                    actions[env * RDV_ACT_DIM + j] = fminf(1.0f, fmaxf(-1.0f, __uint_as_float(v[j]) + s.b2[j]));  // np.clip
-            }
+            for (int j = 0; j < RDV_ACT_DIM; ++j) actions[env * RDV_ACT_DIM + j] = fminf(1.0f, fmaxf(-1.0f, a[j]));   // np.clip
         }
-        // the next tile's A0 stores and layer-1 MMAs are ordered after these loads by the fences around its group_sync
     }
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_all), "r"(TMEM_COLS) : "memory");
+    tile_teardown(tmem_all);
 }
 
 }  // namespace tc

@@ -26,4 +26,4 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 pol.forward(obs); e0.record()
 for _ in range(20): pol.forward(obs)
 e1.record(); torch.cuda.synchronize()
-print(f"stand-alone fp32 FFMA policy kernel, n={obs.shape[0]}: {1e3 * e0.elapsed_time(e1) / 20:.1f} us")
+print(f"stand-alone tcgen05 policy kernel, n={obs.shape[0]}: {1e3 * e0.elapsed_time(e1) / 20:.1f} us")
