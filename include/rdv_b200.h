@@ -175,7 +175,7 @@ typedef struct RdvRolloutIO {
     int32_t  steps;          /* K                                                                          */
     int32_t  action_source;  /* RDV_ACTIONS_*                                                              */
     int32_t  auto_reset;     /* 1: VecEnv semantics (finished envs restart inside the launch)              */
-    int32_t  reserved;
+    int32_t  reserved;       /* set to 0 (the library passes its reset-prefetch period to the kernel here)   */
     const void *actions;     /* [K][n][6] float32 / float64 for the tensor sources                         */
     uint64_t action_seed;    /* RDV_ACTIONS_PHILOX: U(-1,1) fp64 actions from Philox(action_seed; global   */
     int64_t  step_base;      /*   env id, step_base + k): 6 draws per env-step                             */

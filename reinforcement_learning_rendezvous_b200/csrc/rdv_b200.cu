@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 // POLICY: the action of every step is the output of the SB3 MlpPolicy actor, evaluated on the tensor cores
 // (tcgen05 / TMEM, rdv_policy_tc.cuh: groups of 128 threads = 128 envs = one UMMA tile) from the observation the
 // previous step produced.
+constexpr int RDV_NEXT_ROW = 22;          // doubles per prefetched reset row: state[20], collided, success
 template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false>
 __global__ void __launch_bounds__(TPB_, 1)
 rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __grid_constant__ RdvRolloutIO io,
@@ -429,6 +430,13 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int src = io.action_source;
+    // Reset prefetch (variants without the actor, launches of >= 2 refill periods): the reset state of
+    // (env, episode + 1) does not depend on the trajectory, so every lane keeps its NEXT reset row ready in shared
+    // memory.  A finished lane just reads its row; the rows are recomputed for all lanes that used theirs every
+    // `refill` steps, four per pass of the warp's 8-lane teams with every team busy, instead of one pass with
+    // 1.6 of 4 teams busy on 80 % of the steps.  A lane that finishes twice between refills gets its row at once.
+    const int refill = (!POLICY && io.auto_reset && io.reserved > 0 && io.steps >= 2 * io.reserved) ? io.reserved : 0;
+    double *next_rows = reinterpret_cast<double *>(dyn_smem) + (size_t)warp * 32 * RDV_NEXT_ROW;
     // the warp's observation staging row; with the fused actor it borrows the group's activation tile, which is
     // only live between the step barrier and the end of the actor's third layer
     float *obs_stage = POLICY ? ts->al[warp >> 2] + (warp & 3) * (32 * RDV_OBS_DIM) : s_obs[POLICY ? 0 : warp];
@@ -454,6 +462,8 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
         load_counters(S, i, c);
         float ov[RDV_OBS_DIM];
         make_obs(e, obs_scale(P), ov);
+        unsigned fresh = 0;                                    // lanes whose next reset row is ready
+        int countdown = refill;                                // steps until the next refill of the rows
 
         for (int k = 0; k < io.steps; ++k) {
             // Keep the CTA's warps in the same code region (instruction-cache locality).  Measured alternatives:
@@ -527,8 +537,48 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
                     st.ep_return += c.ep_ret; st.ep_length += (double)c.step; st.delta_v += c.tdv; st.delta_w += c.tdw;
                 }
             }
-            // ---- auto-reset inside the warp: four finished lanes per pass, one 8-lane team each ----
-            if (io.auto_reset) {
+            // ---- auto-reset inside the warp ----
+            if (!POLICY && io.auto_reset && refill) {
+                // prefetched rows: compute what is missing right now (rare), consume, refill periodically
+                const unsigned m = __ballot_sync(full, done);
+                // rows for the lanes of `todo`, four per pass
+                auto fill_rows = [&](unsigned todo) {
+                    while (todo) {
+                        const int team = lane >> 3;
+                        const unsigned src_bit = __fns(todo, 0, team + 1);        // team-th lane of the set, or ~0u
+                        const int src_lane = src_bit < 32 ? (int)src_bit : lane;
+                        const int64_t r_env = __shfl_sync(full, env_id, src_lane);
+                        const int r_episode = __shfl_sync(full, c.episode, src_lane) + 1;
+                        team_reset_core(P, seed, r_env, r_episode, nullptr,
+                                        src_bit < 32 ? next_rows + src_lane * RDV_NEXT_ROW : s_team[warp][team]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) todo &= todo - 1;              // drop the four handled lanes
+                    }
+                };
+                const unsigned need = m & ~fresh;
+                if (need) fill_rows(need);
+                if (done) {
+                    const double *rw = next_rows + lane * RDV_NEXT_ROW;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { e.rc[j] = rw[RDV_RCX + j]; e.vc[j] = rw[RDV_VCX + j]; }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { e.qc[j] = rw[RDV_QCW + j]; e.qt[j] = rw[RDV_QTW + j]; }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { e.wc[j] = rw[RDV_WCX + j]; e.wt[j] = rw[RDV_WTX + j]; }
+                    c.collided = (int)rw[20]; c.success = (int)rw[21];
+                    c.step = 0; c.episode += 1; c.tdv = c.tdw = c.ep_ret = 0.0;
+                    make_obs(e, obs_scale(P), ov);                             // post-reset observation
+                }
+                fresh = (fresh | need) & ~m;
+                __syncwarp();
+                if (--countdown == 0 && k + 1 < io.steps) {
+                    countdown = refill;
+                    const unsigned todo = __ballot_sync(full, active) & ~fresh;
+                    fill_rows(todo);                  // (serving only full passes of four measured no faster)
+                    fresh |= todo;
+                }
+            } else if (io.auto_reset) {
+                // four finished lanes per pass, one 8-lane team each
                 unsigned m = __ballot_sync(full, done);
                 while (m) {
                     const int team = lane >> 3;
@@ -956,12 +1006,30 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     const int64_t max_tpb = force_tpb > 0 ? force_tpb : 512;
     const int64_t passes = (per_cta + max_tpb - 1) / max_tpb;
     const int64_t chunk = force_tpb > 0 ? force_tpb : (per_cta + passes - 1) / passes;
-#define RDV_LAUNCH_R(ISO_, CL_, T_) rollout_kernel<ISO_, CL_, T_><<<(unsigned)grid, T_, 0, st>>>(*p, *s, *io, n, seed, env_offset)
-#define RDV_PICK_R(ISO_, CL_)                                  \
-    if (chunk <= 256) RDV_LAUNCH_R(ISO_, CL_, 256);            \
-    else if (chunk <= 384) RDV_LAUNCH_R(ISO_, CL_, 384);       \
-    else if (chunk <= 448) RDV_LAUNCH_R(ISO_, CL_, 448);       \
-    else RDV_LAUNCH_R(ISO_, CL_, 512);
+    // reset prefetch period (steps between refills of the per-lane reset rows; 0 = reset on demand only).
+    // RDV_RESET_REFILL overrides it (development / tests).
+    RdvRolloutIO io_k = *io;
+    {
+        const char *rf = getenv("RDV_RESET_REFILL");
+        io_k.reserved = rf ? atoi(rf) : 8;
+        if (io_k.reserved < 0 || io_k.reserved > 64) io_k.reserved = 0;
+    }
+#define RDV_LAUNCH_R(ISO_, CL_, T_)                                                                               \
+    {                                                                                                             \
+        constexpr size_t smem_ = (size_t)(T_ / 32) * 32 * RDV_NEXT_ROW * sizeof(double);                          \
+        static bool attr_done = false;                                                                            \
+        if (!attr_done) {                                                                                         \
+            if (cudaFuncSetAttribute(rollout_kernel<ISO_, CL_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     (int)smem_) != cudaSuccess) return RDV_ERR_CUDA;                             \
+            attr_done = true;                                                                                     \
+        }                                                                                                         \
+        rollout_kernel<ISO_, CL_, T_><<<(unsigned)grid, T_, smem_, st>>>(*p, *s, io_k, n, seed, env_offset);      \
+    }
+#define RDV_PICK_R(ISO_, CL_)                                 \
+    if (chunk <= 256) RDV_LAUNCH_R(ISO_, CL_, 256)            \
+    else if (chunk <= 384) RDV_LAUNCH_R(ISO_, CL_, 384)       \
+    else if (chunk <= 448) RDV_LAUNCH_R(ISO_, CL_, 448)       \
+    else RDV_LAUNCH_R(ISO_, CL_, 512)
 #define RDV_LAUNCH_P(T_)                                                                                          \
     {                                                                                                             \
         static bool attr_done = false;                                                                            \
@@ -970,7 +1038,7 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
                                      (int)sizeof(tc::TileSmem)) != cudaSuccess) return RDV_ERR_CUDA;              \
             attr_done = true;                                                                                     \
         }                                                                                                         \
-        rollout_kernel<true, false, T_, true><<<(unsigned)grid, T_, sizeof(tc::TileSmem), st>>>(*p, *s, *io, n, seed, \
+        rollout_kernel<true, false, T_, true><<<(unsigned)grid, T_, sizeof(tc::TileSmem), st>>>(*p, *s, io_k, n, seed, \
                                                                                                 env_offset);      \
     }
     if (policy) {
@@ -982,7 +1050,7 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     }
     else if (closed) { RDV_PICK_R(true, true) }
     else if (iso) { RDV_PICK_R(true, false) }
-    else RDV_LAUNCH_R(false, false, 256);
+    else RDV_LAUNCH_R(false, false, 256)
 #undef RDV_LAUNCH_P
 #undef RDV_PICK_R
 #undef RDV_LAUNCH_R

@@ -133,6 +133,33 @@ def test_rollout_launch_shapes_are_bit_identical(monkeypatch):
         assert stats[0]["rk_accepted"] == stats[k]["rk_accepted"] and stats[0]["episodes"] == stats[k]["episodes"]
 
 
+def test_reset_prefetch_is_bit_identical(monkeypatch):
+    """The rollout keeps every env's NEXT reset state ready in shared memory and refills the used rows every few
+    steps (the reset of (env, episode) does not depend on the trajectory).  On-demand resets (period 0), short and
+    long refill periods and short episodes (t_max = 3: envs finish again before the next refill) give the same bits."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    for kw in (dict(t_max=25), dict(t_max=3)):
+        ref = None
+        for period in ("0", "2", "3", "8", "16"):
+            monkeypatch.setenv("RDV_RESET_REFILL", period)
+            env = BatchedRendezvousEnv(2500, seed=5, **kw)
+            env.reset()
+            out = env.rollout(70, action_seed=3, record_rewards=True, record_dones=True)
+            env.rollout(33, action_seed=3, step_base=70)               # a second launch starts without rows
+            got = (env.get_state().clone(), out["rewards"].clone(), out["dones"].clone(), env.episode_index.clone(),
+                   env.read_stats())
+            if ref is None:
+                ref = got
+                assert int(out["dones"].sum()) > 2500                  # resets really happened
+                continue
+            for a, b in zip(ref[:4], got[:4]):
+                assert torch.equal(a, b), (kw, period)
+            for key, v in ref[4].items():      # counters exact; the fp64 sums are atomically reduced over CTAs in any order
+                assert got[4][key] == v if float(v).is_integer() else abs(got[4][key] - v) <= 1e-12 * abs(v), key
+    monkeypatch.delenv("RDV_RESET_REFILL")
+
+
 def _policy():
     import os
     from helpers import GOLDEN
