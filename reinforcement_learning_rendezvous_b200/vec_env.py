@@ -151,24 +151,26 @@ class RendezvousVecEnv(_Base):
         obs, rew, done, idx = self._launch_and_fetch()
         infos: List[dict] = [_EMPTY_INFO] * self.num_envs
         if idx.size:
-            # bulk numpy work first, then one small dict per finished env
+            # bulk numpy work first, then one small dict per finished env, built by comprehensions over zipped
+            # columns (row views of ONE gathered array) -- about half the cost of an indexed Python loop
             rec = self._h_rec.numpy()[idx]
-            term = self._h_term.numpy()[idx]                       # one gather; rows below are views of it
+            term = list(self._h_term.numpy()[idx])                 # one gather; a list of row views of it
             elapsed = round(time.time() - self._t_start, 6)
             rets = np.round(rec[:, N.EP_RETURN], 6).tolist()
             lens = rec[:, N.EP_LENGTH].astype(np.int64).tolist()
+            episodes = [{"r": r, "l": l, "t": elapsed} for r, l in zip(rets, lens)]
             if self.rich_infos:
-                reason = self._h_reason.numpy()[idx].tolist()
+                reason = [N.END_REASONS[j] for j in self._h_reason.numpy()[idx].tolist()]
                 succ = (rec[:, N.EP_SUCCESS] > 0).tolist()
                 coll = (rec[:, N.EP_COLLIDED] > 0).tolist()
                 dv, dw = rec[:, N.EP_DELTA_V].tolist(), rec[:, N.EP_DELTA_W].tolist()
-                for j, i in enumerate(idx.tolist()):
-                    infos[i] = {"terminal_observation": term[j], "episode": {"r": rets[j], "l": lens[j], "t": elapsed},
-                                "is_success": succ[j], "collided": coll[j], "total_delta_v": dv[j],
-                                "total_delta_w": dw[j], "end_reason": N.END_REASONS[reason[j]]}
+                new = [{"terminal_observation": t, "episode": e, "is_success": s, "collided": c, "total_delta_v": v,
+                        "total_delta_w": w, "end_reason": r}
+                       for t, e, s, c, v, w, r in zip(term, episodes, succ, coll, dv, dw, reason)]
             else:
-                for j, i in enumerate(idx.tolist()):
-                    infos[i] = {"terminal_observation": term[j], "episode": {"r": rets[j], "l": lens[j], "t": elapsed}}
+                new = [{"terminal_observation": t, "episode": e} for t, e in zip(term, episodes)]
+            for i, d in zip(idx.tolist(), new):
+                infos[i] = d
         if self.copy_outputs:
             return obs.copy(), rew.copy(), done.copy(), infos
         return obs, rew, done, infos
