@@ -370,6 +370,7 @@ def run_cuda(args):
     for k in range(max(3, min(W, 10))):
         venv.step(host_ring[k % RING])
     checksum = 0.0
+    d2h_before = venv.d2h_bytes_total
     barrier()
     t0 = time.perf_counter()
     e0.record()
@@ -380,9 +381,10 @@ def run_cuda(args):
     barrier()
     wall = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall))
+    d2h_e2e = (venv.d2h_bytes_total - d2h_before) // KE       # obs + reward + done of every env, rows of finished ones
     e2e = {"value": world * n * KE / (e2e_ms * 1e-3), "unit": UNIT, "steps": KE,
            "ms_per_step": e2e_ms / KE, "h2d_bytes_per_step": venv.h2d_bytes_per_step,
-           "d2h_bytes_per_step": venv.d2h_bytes_per_step,
+           "d2h_bytes_per_step": d2h_e2e,
            "api": "RendezvousVecEnv.step(np.float32[N,6]) -> (obs, rewards, dones, infos) numpy, pinned staging"}
 
     # the same loop through the array-returning variant (no per-env Python objects)

@@ -84,10 +84,16 @@ class RendezvousVecEnv(_Base):
         self._h_term = torch.zeros((n, N.OBS_DIM), dtype=torch.float32).pin_memory()
         self._h_rec = torch.zeros((n, N.EP_NCOL), dtype=torch.float64).pin_memory()
         self._h_reason = torch.zeros(n, dtype=torch.int8).pin_memory()
+        self._h_idx = torch.zeros(n, dtype=torch.int64).pin_memory()
         self._pending = None
         self._t_start = time.time()
         self.h2d_bytes_per_step = n * N.ACT_DIM * 4
-        self.d2h_bytes_per_step = n * (N.OBS_DIM * 4 + 4 + 1 + N.OBS_DIM * 4 + N.EP_NCOL * 8 + 1)
+        # device -> host per step: obs, reward, done for every env, plus the compacted rows of the finished ones
+        self._d2h_fixed = n * (N.OBS_DIM * 4 + 4 + 1)
+        self._d2h_row = N.OBS_DIM * 4 + N.EP_NCOL * 8 + 1 + 8
+        self.d2h_bytes_per_step = self._d2h_fixed          # + _d2h_row per finished env; see d2h_bytes_last_step
+        self.d2h_bytes_last_step = self._d2h_fixed
+        self.d2h_bytes_total = 0
 
     # ------------------------------------------------------------------ VecEnv API
     def reset(self):
@@ -120,13 +126,20 @@ class RendezvousVecEnv(_Base):
         self._h_obs.copy_(env.obs, non_blocking=True)
         self._h_rew.copy_(self._d_rew32, non_blocking=True)
         self._h_done.copy_(env.done, non_blocking=True)
-        self._h_term.copy_(env.terminal_obs, non_blocking=True)
-        self._h_rec.copy_(env.episode_record, non_blocking=True)
-        self._h_reason.copy_(env.end_reason, non_blocking=True)
+        # finished envs: compact their rows on the device (ascending env index) and copy only those
+        idx_d = torch.nonzero(env.done).squeeze(1)
+        m = int(idx_d.numel())
+        if m:
+            self._h_idx[:m].copy_(idx_d, non_blocking=True)
+            self._h_term[:m].copy_(env.terminal_obs.index_select(0, idx_d), non_blocking=True)
+            self._h_rec[:m].copy_(env.episode_record.index_select(0, idx_d), non_blocking=True)
+            self._h_reason[:m].copy_(env.end_reason.index_select(0, idx_d), non_blocking=True)
         torch.cuda.current_stream(env.device).synchronize()
+        self.d2h_bytes_last_step = self._d2h_fixed + m * self._d2h_row
+        self.d2h_bytes_total += self.d2h_bytes_last_step
         obs, rew = self._h_obs.numpy(), self._h_rew.numpy()
         done = self._h_done.numpy().view(np.bool_)
-        return obs, rew, done, np.flatnonzero(done)
+        return obs, rew, done, self._h_idx.numpy()[:m].copy()
 
     def step_arrays(self, actions):
         """``step`` without per-env Python objects: returns ``(obs, rewards, dones, finished)`` where ``finished`` is
@@ -135,13 +148,14 @@ class RendezvousVecEnv(_Base):
         ``end_reason`` (0 obs, 1 time, 2 bubble, 3 attitude).  Same data as the ``infos`` of ``step``."""
         self.step_async(actions)
         obs, rew, done, idx = self._launch_and_fetch()
-        rec = self._h_rec.numpy()[idx]
+        m = idx.size
+        rec = self._h_rec.numpy()[:m].copy()
         finished = {
-            "index": idx, "terminal_observation": self._h_term.numpy()[idx],
+            "index": idx, "terminal_observation": self._h_term.numpy()[:m].copy(),
             "episode_return": rec[:, N.EP_RETURN], "episode_length": rec[:, N.EP_LENGTH].astype(np.int64),
             "is_success": rec[:, N.EP_SUCCESS] > 0, "collided": rec[:, N.EP_COLLIDED] > 0,
             "total_delta_v": rec[:, N.EP_DELTA_V], "total_delta_w": rec[:, N.EP_DELTA_W],
-            "end_reason": self._h_reason.numpy()[idx],
+            "end_reason": self._h_reason.numpy()[:m].copy(),
         }
         if self.copy_outputs:
             return obs.copy(), rew.copy(), done.copy(), finished
@@ -153,14 +167,15 @@ class RendezvousVecEnv(_Base):
         if idx.size:
             # bulk numpy work first, then one small dict per finished env, built by comprehensions over zipped
             # columns (row views of ONE gathered array) -- about half the cost of an indexed Python loop
-            rec = self._h_rec.numpy()[idx]
-            term = list(self._h_term.numpy()[idx])                 # one gather; a list of row views of it
+            m = idx.size
+            rec = self._h_rec.numpy()[:m]                          # rows of the finished envs, compacted on the device
+            term = list(self._h_term.numpy()[:m].copy())           # one copy; a list of row views of it
             elapsed = round(time.time() - self._t_start, 6)
             rets = np.round(rec[:, N.EP_RETURN], 6).tolist()
             lens = rec[:, N.EP_LENGTH].astype(np.int64).tolist()
             episodes = [{"r": r, "l": l, "t": elapsed} for r, l in zip(rets, lens)]
             if self.rich_infos:
-                reason = [N.END_REASONS[j] for j in self._h_reason.numpy()[idx].tolist()]
+                reason = [N.END_REASONS[j] for j in self._h_reason.numpy()[:m].tolist()]
                 succ = (rec[:, N.EP_SUCCESS] > 0).tolist()
                 coll = (rec[:, N.EP_COLLIDED] > 0).tolist()
                 dv, dw = rec[:, N.EP_DELTA_V].tolist(), rec[:, N.EP_DELTA_W].tolist()
