@@ -17,6 +17,7 @@ overwritten by the next ``step_wait``; SB3 copies them into its rollout buffer i
 """
 from __future__ import annotations
 
+import gc
 import time
 from typing import Any, List, Optional, Sequence
 
@@ -163,6 +164,22 @@ class RendezvousVecEnv(_Base):
 
     def step_wait(self):
         obs, rew, done, idx = self._launch_and_fetch()
+        # The cyclic garbage collector is paused while the per-env objects are created: a step at 65,536 envs
+        # allocates a 65,536-slot list and ~6,500 small dicts, none of them cyclic, and the generation-0 passes
+        # they trigger (each one walking the new list) cost more than building them (3.9 -> 1.6 ms per step).
+        paused = gc.isenabled()
+        if paused:
+            gc.disable()
+        try:
+            infos = self._build_infos(idx)
+        finally:
+            if paused:
+                gc.enable()
+        if self.copy_outputs:
+            return obs.copy(), rew.copy(), done.copy(), infos
+        return obs, rew, done, infos
+
+    def _build_infos(self, idx) -> List[dict]:
         infos: List[dict] = [_EMPTY_INFO] * self.num_envs
         if idx.size:
             # bulk numpy work first, then one small dict per finished env, built by comprehensions over zipped
@@ -186,9 +203,7 @@ class RendezvousVecEnv(_Base):
                 new = [{"terminal_observation": t, "episode": e} for t, e in zip(term, episodes)]
             for i, d in zip(idx.tolist(), new):
                 infos[i] = d
-        if self.copy_outputs:
-            return obs.copy(), rew.copy(), done.copy(), infos
-        return obs, rew, done, infos
+        return infos
 
     def close(self):
         return None
