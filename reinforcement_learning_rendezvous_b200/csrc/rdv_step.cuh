@@ -6,6 +6,10 @@
 #pragma once
 #include "rdv_env.cuh"
 
+#ifndef RDV_ISO_PLANE
+#define RDV_ISO_PLANE 1        /* 1: isotropic bodies are integrated in the invariant plane (rk45_iso_plane) */
+#endif
+
 namespace rdv {
 
 __constant__ double c_zero3[3] = {0.0, 0.0, 0.0};     // the target carries no torque (rendezvous_env.py:585)
@@ -75,14 +79,14 @@ RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, i
         BodyConst bc, bt;
         bc.I = P.inertia_c; bc.Iinv = P.inv_inertia_c; bc.tau = P.torque_c;
         bt.I = P.inertia_t; bt.Iinv = P.inv_inertia_t; bt.tau = c_zero3;
-        if (ISO && LOCKSTEP) {
+        if (ISO && LOCKSTEP && RDV_ISO_PLANE == 0) {
             const int k = rk45_iso_pair(y, z, P.dt, rk_rej);
             if (k < 0) fail = 1; else rk_acc += k;
         } else if (ISO) {
             // one solve after the other through a single copy of the solver code (bounded registers)
 #pragma unroll 1
             for (int body = 0; body < 2; ++body) {
-                const int k = rk45_attitude<true>(y, P.dt, bc, rk_rej);
+                const int k = RDV_ISO_PLANE ? rk45_iso_plane(y, P.dt, rk_rej) : rk45_attitude<true>(y, P.dt, bc, rk_rej);
                 if (k < 0) fail = 1; else rk_acc += k;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) { const double tmp = y[j]; y[j] = z[j]; z[j] = tmp; }
