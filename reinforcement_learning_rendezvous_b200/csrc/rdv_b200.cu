@@ -413,6 +413,9 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 // POLICY: the action of every step is the output of the SB3 MlpPolicy actor, evaluated on the tensor cores
 // (tcgen05 / TMEM, rdv_policy_tc.cuh: groups of 128 threads = 128 envs = one UMMA tile) from the observation the
 // previous step produced.
+#ifndef RDV_LOCKSTEP_MAX_TPB
+#define RDV_LOCKSTEP_MAX_TPB 256      /* CTAs up to this size interleave the two attitude solves (rk45_iso_plane_pair) */
+#endif
 constexpr int RDV_NEXT_ROW = 22;          // doubles per prefetched reset row: state[20], collided, success
 template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false>
 __global__ void __launch_bounds__(TPB_, 1)
@@ -523,7 +526,7 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
             }
             // ---- step ----
             int rk_acc = 0, rk_rej = 0, fail = 0;
-            env_advance<ISO, CLOSED, (TPB_ <= 256)>(P, e, t, rk_acc, rk_rej, fail);
+            env_advance<ISO, CLOSED, (TPB_ <= RDV_LOCKSTEP_MAX_TPB)>(P, e, t, rk_acc, rk_rej, fail);
             const StepResult r = env_evaluate(P, e, t.fuel, c, ov);
             const bool done = r.done && active;
             if (active) {

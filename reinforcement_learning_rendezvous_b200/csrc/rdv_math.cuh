@@ -651,6 +651,179 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
     }
 }
 
+// Lock-step form of rk45_iso_plane for TWO bodies in one thread (chaser and target of one env): the control flow of
+// scipy's _step_impl (accept / reject, the factor clamps, the rejected-step rule, TOO_SMALL_STEP) is written as
+// predicated updates, a body that has reached t = dt keeps stepping in the shadow without committing anything, and
+// the two bodies are interleaved stage by stage in the source, so that two independent slope chains (norm ->
+// rsqrt -> scale) sit next to each other in every basic block.  Arithmetic per body is that of rk45_iso_plane,
+// operation for operation (tests/test_gpu_rollout.py compares the bits).
+RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double dt, int &n_rejected)
+{
+    double q0[2][4], p[2][4], yc[2][4], om2[2], inv_n0[2], a[2], b[2], ka0[2], kb0[2], h_abs[2], t[2];
+    int accepted[2] = {0, 0};
+    bool done[2] = {false, false}, rejected[2] = {false, false}, failed[2] = {false, false};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { q0[0][i] = ya[i]; q0[1][i] = yb[i]; }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const double *w = c ? yb + 4 : ya + 4;
+        const double hw[3] = {0.5 * w[0], 0.5 * w[1], 0.5 * w[2]};
+        p[c][0] = -fma(hw[2], q0[c][3], fma(hw[1], q0[c][2], hw[0] * q0[c][1]));
+        p[c][1] = fma(-hw[1], q0[c][3], fma(hw[2], q0[c][2], hw[0] * q0[c][0]));
+        p[c][2] = fma(hw[0], q0[c][3], fma(-hw[2], q0[c][1], hw[1] * q0[c][0]));
+        p[c][3] = fma(-hw[0], q0[c][2], fma(hw[1], q0[c][1], hw[2] * q0[c][0]));
+        om2[c] = fma(hw[2], hw[2], fma(hw[1], hw[1], hw[0] * hw[0]));
+        inv_n0[c] = fast_rsqrt(dot4(q0[c], q0[c]));
+        a[c] = 1.0; b[c] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) yc[c][i] = q0[c][i];
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) rhs_plane(a[c], b[c], om2[c], inv_n0[c], ka0[c], kb0[c]);
+    // ---- select_initial_step for both bodies, expression for expression the one of rk45_iso_plane ----
+    {
+        float inv_sc[2][7], d1s[2];
+        double h0[2], ka1[2], kb1[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const double *y = c ? yb : ya;
+            float d0s = 0.0f;
+            d1s[c] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const float yi = (float)y[i];
+                inv_sc[c][i] = __frcp_rn(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
+                const float v = yi * inv_sc[c][i];
+                d0s = fmaf(v, v, d0s);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = (float)(kb0[c] * p[c][i]) * inv_sc[c][i];
+                d1s[c] = fmaf(v, v, d1s[c]);
+            }
+            d0s *= (1.0f / 7.0f);
+            d1s[c] *= (1.0f / 7.0f);
+            float h0f;
+            if (d0s < 1e-10f || d1s[c] < 1e-10f) h0f = 1e-6f;
+            else h0f = 0.01f * sqrtf(__fdividef(d0s, d1s[c]));
+            h0[c] = fmin((double)h0f, dt);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            rhs_plane(fma(h0[c], ka0[c], a[c]), fma(h0[c], kb0[c], b[c]), om2[c], inv_n0[c], ka1[c], kb1[c]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const double da = ka1[c] - ka0[c], db = kb1[c] - kb0[c];
+            float d2s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = (float)fma(db, p[c][i], da * q0[c][i]) * inv_sc[c][i];
+                d2s = fmaf(v, v, d2s);
+            }
+            const float inv_h0 = __frcp_rn((float)h0[c]);
+            d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
+            float h1;
+            if (d1s[c] <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0[c] * 1e-3f);
+            else h1 = pow_neg_tenth_f32(fminf(fmaxf(d1s[c], d2s), 1e30f) * 1e4f);
+            h_abs[c] = fmin(fmin(100.0 * h0[c], (double)h1), dt);
+            t[c] = 0.0;
+        }
+    }
+    // ---- attempted steps, both bodies per pass, predicated commit ----
+    while (!((done[0] || failed[0]) && (done[1] || failed[1]))) {
+        double h[2], t_new[2], ha[2], as[2], bs[2];
+        bool fail_now[2];
+        double ka1[2], kb1[2], ka2[2], kb2[2], ka3[2], kb3[2], ka4[2], kb4[2], ka5[2], kb5[2], ka6[2], kb6[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t[c]) + 1) - t[c]);
+            fail_now[c] = rejected[c] && h_abs[c] < min_step;
+            ha[c] = rejected[c] ? h_abs[c] : fmax(h_abs[c], min_step);
+            t_new[c] = t[c] + ha[c];
+            if (t_new[c] - dt > 0.0) t_new[c] = dt;
+            h[c] = t_new[c] - t[c];
+            ha[c] = fabs(h[c]);
+        }
+#define RDV_PSTAGE(KA, KB, EA, EB)                                                       \
+        _Pragma("unroll") for (int c = 0; c < 2; ++c) { as[c] = (EA); bs[c] = (EB); }    \
+        _Pragma("unroll") for (int c = 0; c < 2; ++c) rhs_plane(as[c], bs[c], om2[c], inv_n0[c], KA[c], KB[c]);
+        RDV_PSTAGE(ka1, kb1, fma(ka0[c] * RK_A21, h[c], a[c]), fma(kb0[c] * RK_A21, h[c], b[c]))
+        RDV_PSTAGE(ka2, kb2, fma(fma(ka1[c], RK_A32, ka0[c] * RK_A31), h[c], a[c]),
+                   fma(fma(kb1[c], RK_A32, kb0[c] * RK_A31), h[c], b[c]))
+        RDV_PSTAGE(ka3, kb3, fma(fma(ka2[c], RK_A43, fma(ka1[c], RK_A42, ka0[c] * RK_A41)), h[c], a[c]),
+                   fma(fma(kb2[c], RK_A43, fma(kb1[c], RK_A42, kb0[c] * RK_A41)), h[c], b[c]))
+        RDV_PSTAGE(ka4, kb4,
+                   fma(fma(ka3[c], RK_A54, fma(ka2[c], RK_A53, fma(ka1[c], RK_A52, ka0[c] * RK_A51))), h[c], a[c]),
+                   fma(fma(kb3[c], RK_A54, fma(kb2[c], RK_A53, fma(kb1[c], RK_A52, kb0[c] * RK_A51))), h[c], b[c]))
+        RDV_PSTAGE(ka5, kb5,
+                   fma(fma(ka4[c], RK_A65, fma(ka3[c], RK_A64, fma(ka2[c], RK_A63, fma(ka1[c], RK_A62, ka0[c] * RK_A61)))),
+                       h[c], a[c]),
+                   fma(fma(kb4[c], RK_A65, fma(kb3[c], RK_A64, fma(kb2[c], RK_A63, fma(kb1[c], RK_A62, kb0[c] * RK_A61)))),
+                       h[c], b[c]))
+        RDV_PSTAGE(ka6, kb6,
+                   fma(h[c], fma(ka5[c], RK_B6, fma(ka4[c], RK_B5, fma(ka3[c], RK_B4, fma(ka2[c], RK_B3, ka0[c] * RK_B1)))),
+                       a[c]),
+                   fma(h[c], fma(kb5[c], RK_B6, fma(kb4[c], RK_B5, fma(kb3[c], RK_B4, fma(kb2[c], RK_B3, kb0[c] * RK_B1)))),
+                       b[c]))
+#undef RDV_PSTAGE
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            // as / bs hold (a_new, b_new) of the attempted step
+            const double ea = h[c] * fma(ka6[c], RK_E7, fma(ka5[c], RK_E6, fma(ka4[c], RK_E5, fma(ka3[c], RK_E4,
+                                     fma(ka2[c], RK_E3, ka0[c] * RK_E1)))));
+            const double eb = h[c] * fma(kb6[c], RK_E7, fma(kb5[c], RK_E6, fma(kb4[c], RK_E5, fma(kb3[c], RK_E4,
+                                     fma(kb2[c], RK_E3, kb0[c] * RK_E1)))));
+            double eh[4], y_new[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                y_new[i] = fma(bs[c], p[c][i], as[c] * q0[c][i]);
+                eh[i] = fma(eb, p[c][i], ea * q0[c][i]);
+            }
+            float esf = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float m = (float)fmax(fabs(yc[c][i]), fabs(y_new[i]));
+                const float q = __fdividef((float)eh[i], fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
+                esf = fmaf(q, q, esf);
+            }
+            esf *= (1.0f / 7.0f);
+            const bool live = !done[c] && !failed[c];
+            const bool bad = fail_now[c] || !(esf < 1.0e30f);
+            bool accept = esf < 1.0f;
+            if (fabsf(esf - 1.0f) < 1.0e-3f) {         // threshold region: decide with the fp64 norm
+                double es = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double e = eh[i] * fast_rcp(fma(fmax(fabs(yc[c][i]), fabs(y_new[i])), RK_RTOL, RK_ATOL));
+                    es = fma(e, e, es);
+                }
+                accept = es * (1.0 / 7.0) < 1.0;
+            }
+            const float pf = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
+            float factor = accept ? fminf(10.0f, pf) : fmaxf(0.2f, pf);
+            if (accept && rejected[c]) factor = fminf(1.0f, factor);
+            const bool commit = live && !bad && accept;
+            if (live) {
+                failed[c] = bad;
+                h_abs[c] = bad ? h_abs[c] : ha[c] * (double)factor;
+                rejected[c] = !accept;
+                n_rejected += (!bad && !accept) ? 1 : 0;
+            }
+            if (commit) {
+                a[c] = as[c]; b[c] = bs[c]; ka0[c] = ka6[c]; kb0[c] = kb6[c];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) yc[c][i] = y_new[i];
+                t[c] = t_new[c];
+                accepted[c] += 1;
+                done[c] = t_new[c] - dt >= 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ya[i] = yc[0][i]; yb[i] = yc[1][i]; }
+    return (failed[0] || failed[1]) ? -1 : accepted[0] + accepted[1];
+}
+
 // ---------------------------------------------------------------------------------
 // Lock-step form of the same solver for TWO bodies in one thread (chaser and target of one env), for the
 // isotropic, torque-free case (the reference env: w is constant, only q moves).

@@ -79,8 +79,8 @@ RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, i
         BodyConst bc, bt;
         bc.I = P.inertia_c; bc.Iinv = P.inv_inertia_c; bc.tau = P.torque_c;
         bt.I = P.inertia_t; bt.Iinv = P.inv_inertia_t; bt.tau = c_zero3;
-        if (ISO && LOCKSTEP && RDV_ISO_PLANE == 0) {
-            const int k = rk45_iso_pair(y, z, P.dt, rk_rej);
+        if (ISO && LOCKSTEP) {
+            const int k = RDV_ISO_PLANE ? rk45_iso_plane_pair(y, z, P.dt, rk_rej) : rk45_iso_pair(y, z, P.dt, rk_rej);
             if (k < 0) fail = 1; else rk_acc += k;
         } else if (ISO) {
             // one solve after the other through a single copy of the solver code (bounded registers)
