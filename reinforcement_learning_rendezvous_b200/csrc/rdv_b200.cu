@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
         bc.I = body ? P.inertia_t : P.inertia_c;
         bc.Iinv = body ? P.inv_inertia_t : P.inv_inertia_c;
         bc.tau = body ? c_zero3 : P.torque_c;
-        const int k = (ISO && RDV_ISO_PLANE) ? rk45_iso_plane(y, P.dt, rk_rej) : rk45_attitude<ISO>(y, P.dt, bc, rk_rej);
+        const int k = ISO ? rk45_iso_plane(y, P.dt, rk_rej) : rk45_attitude<ISO>(y, P.dt, bc, rk_rej);
         if (k < 0) fail = 1; else rk_acc = k;
     }
     {

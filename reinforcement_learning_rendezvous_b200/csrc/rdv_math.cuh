@@ -261,7 +261,12 @@ __constant__ double c_rk[26] = {
 // cancellation) stays fp64.  The accept test err < 1 is re-evaluated in full fp64 whenever the float32
 // value lies within 1e-3 of the threshold, so accept / reject decisions are those of the fp64 controller.
 // ---------------------------------------------------------------------------------
-RDV_DEV float pow_neg_tenth_f32(float x) { return exp2f(-0.1f * __log2f(x)); }
+// float32 helpers of the controller: single MUFU instructions without the denormal-range fix-ups of
+// __fdividef / __log2f / exp2f (every argument here is a normal number: scales >= atol = 1e-6, clamped norms)
+RDV_DEV float rcp_f32(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RDV_DEV float lg2_f32(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RDV_DEV float ex2_f32(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RDV_DEV float pow_neg_tenth_f32(float x) { return ex2_f32(-0.1f * lg2_f32(x)); }
 
 #ifndef RDV_RK_INLINE
 #define RDV_RK_INLINE 1
@@ -287,7 +292,7 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             const float yi = (float)y[i];
-            inv_sc[i] = __frcp_rn(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
+            inv_sc[i] = rcp_f32(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
             const float a = yi * inv_sc[i];
             d0s = fmaf(a, a, d0s);
         }
@@ -300,7 +305,7 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
         d1s *= (1.0f / 7.0f);                                // squares of the rms norms d0, d1
         float h0f;
         if (d0s < 1e-10f || d1s < 1e-10f) h0f = 1e-6f;
-        else h0f = 0.01f * sqrtf(__fdividef(d0s, d1s));
+        else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s));
         const double h0 = fmin((double)h0f, dt);
         double y1[7], f1[NA];
 #pragma unroll
@@ -314,7 +319,7 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
             const float a = (float)(f1[i] - K[0][i]) * inv_sc[i];
             d2s = fmaf(a, a, d2s);
         }
-        const float inv_h0 = __frcp_rn((float)h0);
+        const float inv_h0 = rcp_f32((float)h0);
         d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
         float h1;
         if (d1s <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0 * 1e-3f);
@@ -422,7 +427,7 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 #pragma unroll
             for (int i = 0; i < NA; ++i) {
                 const float m = (float)fmax(fabs(y[i]), fabs(y_new[i]));
-                const float q = __fdividef((float)eh[i], fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
+                const float q = (float)eh[i] * rcp_f32(fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
                 esf = fmaf(q, q, esf);
             }
             esf *= (1.0f / 7.0f);                      // err_norm^2
@@ -527,7 +532,7 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             const float yi = (float)y[i];
-            inv_sc[i] = __frcp_rn(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
+            inv_sc[i] = rcp_f32(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
             const float v = yi * inv_sc[i];
             d0s = fmaf(v, v, d0s);
         }
@@ -540,7 +545,7 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
         d1s *= (1.0f / 7.0f);                                // squares of the rms norms d0, d1
         float h0f;
         if (d0s < 1e-10f || d1s < 1e-10f) h0f = 1e-6f;
-        else h0f = 0.01f * sqrtf(__fdividef(d0s, d1s));
+        else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s));
         const double h0 = fmin((double)h0f, dt);
         double ka1, kb1;
         rhs_plane(fma(h0, ka[0], a), fma(h0, kb[0], b), om2, inv_n0, ka1, kb1);
@@ -551,7 +556,7 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
             const float v = (float)fma(db, p[i], da * q0[i]) * inv_sc[i];
             d2s = fmaf(v, v, d2s);
         }
-        const float inv_h0 = __frcp_rn((float)h0);
+        const float inv_h0 = rcp_f32((float)h0);
         d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
         float h1;
         if (d1s <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0 * 1e-3f);
@@ -610,7 +615,7 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float m = (float)fmax(fabs(yc[i]), fabs(y_new[i]));
-                const float q = __fdividef((float)eh[i], fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
+                const float q = (float)eh[i] * rcp_f32(fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
                 esf = fmaf(q, q, esf);
             }
             esf *= (1.0f / 7.0f);                      // err_norm^2 (the three rate components contribute 0)
@@ -692,7 +697,7 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
                 const float yi = (float)y[i];
-                inv_sc[c][i] = __frcp_rn(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
+                inv_sc[c][i] = rcp_f32(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
                 const float v = yi * inv_sc[c][i];
                 d0s = fmaf(v, v, d0s);
             }
@@ -705,7 +710,7 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
             d1s[c] *= (1.0f / 7.0f);
             float h0f;
             if (d0s < 1e-10f || d1s[c] < 1e-10f) h0f = 1e-6f;
-            else h0f = 0.01f * sqrtf(__fdividef(d0s, d1s[c]));
+            else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s[c]));
             h0[c] = fmin((double)h0f, dt);
         }
 #pragma unroll
@@ -720,7 +725,7 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
                 const float v = (float)fma(db, p[c][i], da * q0[c][i]) * inv_sc[c][i];
                 d2s = fmaf(v, v, d2s);
             }
-            const float inv_h0 = __frcp_rn((float)h0[c]);
+            const float inv_h0 = rcp_f32((float)h0[c]);
             d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
             float h1;
             if (d1s[c] <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0[c] * 1e-3f);
@@ -783,7 +788,7 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float m = (float)fmax(fabs(yc[c][i]), fabs(y_new[i]));
-                const float q = __fdividef((float)eh[i], fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
+                const float q = (float)eh[i] * rcp_f32(fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
                 esf = fmaf(q, q, esf);
             }
             esf *= (1.0f / 7.0f);
@@ -821,174 +826,6 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) { ya[i] = yc[0][i]; yb[i] = yc[1][i]; }
-    return (failed[0] || failed[1]) ? -1 : accepted[0] + accepted[1];
-}
-
-// ---------------------------------------------------------------------------------
-// Lock-step form of the same solver for TWO bodies in one thread (chaser and target of one env), for the
-// isotropic, torque-free case (the reference env: w is constant, only q moves).
-//
-// rk45_attitude above is a chain of dependent fp64 operations with at most 4-way instruction-level
-// parallelism (dependent DFMA latency ~12 cycles); with <= 2 warps per SM sub-partition one thread keeps
-// only a fraction of the fp64 pipe busy with it.  Here the control flow of scipy's _step_impl (accept /
-// reject, the factor clamps, the rejected-step rule, TOO_SMALL_STEP) is written as predicated updates, a body
-// that has reached t = dt keeps stepping in the shadow without committing anything, and the two bodies are
-// interleaved STAGE BY STAGE in the source: "stage vector of body 0, stage vector of body 1,
-// right-hand side of body 0, right-hand side of body 1".  The two right-hand sides are independent
-// ~30-instruction dependency chains (dot product -> rsqrt -> Omega q) that sit next to each other in one
-// basic block, so the scheduler overlaps them; written as two whole solves one after the other the compiler
-// serialises them.  Arithmetic per body is identical to rk45_attitude<true>, operation for operation.
-// ---------------------------------------------------------------------------------
-RDV_DEV void rhs_iso(const double *q, const double *hw, double *f)
-{
-    const double r = fast_rsqrt(dot4(q, q));
-    const double g0 = -fma(hw[2], q[3], fma(hw[1], q[2], hw[0] * q[1]));
-    const double g1 = fma(-hw[1], q[3], fma(hw[2], q[2], hw[0] * q[0]));
-    const double g2 = fma(hw[0], q[3], fma(-hw[2], q[1], hw[1] * q[0]));
-    const double g3 = fma(-hw[0], q[2], fma(hw[1], q[1], hw[2] * q[0]));
-    f[0] = g0 * r; f[1] = g1 * r; f[2] = g2 * r; f[3] = g3 * r;
-}
-
-RDV_DEV int rk45_iso_pair(double (&ya)[7], double (&yb)[7], const double dt, int &n_rejected)
-{
-    double y[2][4], w[2][3], hw[2][3], K0[2][4], h_abs[2], t[2];
-    int accepted[2] = {0, 0};
-    bool done[2] = {false, false}, rejected[2] = {false, false}, failed[2] = {false, false};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { y[0][i] = ya[i]; y[1][i] = yb[i]; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        w[0][i] = ya[4 + i]; w[1][i] = yb[4 + i];
-        hw[0][i] = 0.5 * w[0][i]; hw[1][i] = 0.5 * w[1][i];
-    }
-    // ---- select_initial_step (scipy common.py:68-134) for both bodies; float32 controller arithmetic,
-    //      expression for expression the one of rk45_attitude (bit-identical step sizes) ----
-    {
-        float inv_sc[2][7], d0s[2], d1s[2];
-        double h0[2], y1[2][4], f1[2][4];
-#pragma unroll
-        for (int b = 0; b < 2; ++b) rhs_iso(y[b], hw[b], K0[b]);
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            d0s[b] = 0.0f; d1s[b] = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const float yi = (float)(i < 4 ? y[b][i < 4 ? i : 0] : w[b][i < 4 ? 0 : i - 4]);
-                inv_sc[b][i] = __frcp_rn(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
-                const float a = yi * inv_sc[b][i];
-                d0s[b] = fmaf(a, a, d0s[b]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float a = (float)K0[b][i] * inv_sc[b][i];
-                d1s[b] = fmaf(a, a, d1s[b]);
-            }
-            d0s[b] *= (1.0f / 7.0f);
-            d1s[b] *= (1.0f / 7.0f);
-            float h0f;
-            if (d0s[b] < 1e-10f || d1s[b] < 1e-10f) h0f = 1e-6f;
-            else h0f = 0.01f * sqrtf(__fdividef(d0s[b], d1s[b]));
-            h0[b] = fmin((double)h0f, dt);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) y1[b][i] = fma(h0[b], K0[b][i], y[b][i]);
-        }
-#pragma unroll
-        for (int b = 0; b < 2; ++b) rhs_iso(y1[b], hw[b], f1[b]);
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            float d2s = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float a = (float)(f1[b][i] - K0[b][i]) * inv_sc[b][i];
-                d2s = fmaf(a, a, d2s);
-            }
-            const float inv_h0 = __frcp_rn((float)h0[b]);
-            d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
-            float h1;
-            if (d1s[b] <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0[b] * 1e-3f);
-            else h1 = pow_neg_tenth_f32(fminf(fmaxf(d1s[b], d2s), 1e30f) * 1e4f);
-            h_abs[b] = fmin(fmin(100.0 * h0[b], (double)h1), dt);
-            t[b] = 0.0;
-        }
-    }
-    // ---- attempted steps (scipy rk.py:111-179), both bodies per pass, predicated commit ----
-    while (!((done[0] || failed[0]) && (done[1] || failed[1]))) {
-        double h[2], t_new[2], ha[2], ys[2][4];
-        bool fail_now[2];
-        double K1[2][4], K2[2][4], K3[2][4], K4[2][4], K5[2][4], K6[2][4];
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t[b]) + 1) - t[b]);
-            fail_now[b] = rejected[b] && h_abs[b] < min_step;
-            ha[b] = rejected[b] ? h_abs[b] : fmax(h_abs[b], min_step);
-            t_new[b] = t[b] + ha[b];
-            if (t_new[b] - dt > 0.0) t_new[b] = dt;
-            h[b] = t_new[b] - t[b];
-            ha[b] = fabs(h[b]);
-        }
-#define RDV_STAGE(KOUT, EXPR)                                                      \
-        _Pragma("unroll") for (int b = 0; b < 2; ++b) {                            \
-            _Pragma("unroll") for (int i = 0; i < 4; ++i) ys[b][i] = (EXPR);       \
-        }                                                                          \
-        _Pragma("unroll") for (int b = 0; b < 2; ++b) rhs_iso(ys[b], hw[b], KOUT[b]);
-        RDV_STAGE(K1, fma(K0[b][i] * RK_A21, h[b], y[b][i]))
-        RDV_STAGE(K2, fma(fma(K1[b][i], RK_A32, K0[b][i] * RK_A31), h[b], y[b][i]))
-        RDV_STAGE(K3, fma(fma(K2[b][i], RK_A43, fma(K1[b][i], RK_A42, K0[b][i] * RK_A41)), h[b], y[b][i]))
-        RDV_STAGE(K4, fma(fma(K3[b][i], RK_A54, fma(K2[b][i], RK_A53, fma(K1[b][i], RK_A52, K0[b][i] * RK_A51))),
-                          h[b], y[b][i]))
-        RDV_STAGE(K5, fma(fma(K4[b][i], RK_A65, fma(K3[b][i], RK_A64, fma(K2[b][i], RK_A63,
-                          fma(K1[b][i], RK_A62, K0[b][i] * RK_A61)))), h[b], y[b][i]))
-        RDV_STAGE(K6, fma(h[b], fma(K5[b][i], RK_B6, fma(K4[b][i], RK_B5, fma(K3[b][i], RK_B4,
-                          fma(K2[b][i], RK_B3, K0[b][i] * RK_B1)))), y[b][i]))
-#undef RDV_STAGE
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            double eh[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                eh[i] = h[b] * fma(K6[b][i], RK_E7, fma(K5[b][i], RK_E6, fma(K4[b][i], RK_E5, fma(K3[b][i], RK_E4,
-                                   fma(K2[b][i], RK_E3, K0[b][i] * RK_E1)))));
-            float esf = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float m = (float)fmax(fabs(y[b][i]), fabs(ys[b][i]));
-                const float q = __fdividef((float)eh[i], fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
-                esf = fmaf(q, q, esf);
-            }
-            esf *= (1.0f / 7.0f);
-            const bool live = !done[b] && !failed[b];
-            const bool bad = fail_now[b] || !(esf < 1.0e30f);
-            bool accept = esf < 1.0f;
-            if (fabsf(esf - 1.0f) < 1.0e-3f) {         // threshold region: decide with the fp64 norm
-                double es = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double e = eh[i] * fast_rcp(fma(fmax(fabs(y[b][i]), fabs(ys[b][i])), RK_RTOL, RK_ATOL));
-                    es = fma(e, e, es);
-                }
-                accept = es * (1.0 / 7.0) < 1.0;
-            }
-            const float p = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
-            float factor = accept ? fminf(10.0f, p) : fmaxf(0.2f, p);
-            if (accept && rejected[b]) factor = fminf(1.0f, factor);
-            const bool commit = live && !bad && accept;
-            if (live) {
-                failed[b] = bad;
-                h_abs[b] = bad ? h_abs[b] : ha[b] * (double)factor;
-                rejected[b] = !accept;
-                n_rejected += (!bad && !accept) ? 1 : 0;
-            }
-            if (commit) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { y[b][i] = ys[b][i]; K0[b][i] = K6[b][i]; }
-                t[b] = t_new[b];
-                accepted[b] += 1;
-                done[b] = t_new[b] - dt >= 0.0;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { ya[i] = y[0][i]; yb[i] = y[1][i]; }
     return (failed[0] || failed[1]) ? -1 : accepted[0] + accepted[1];
 }
 

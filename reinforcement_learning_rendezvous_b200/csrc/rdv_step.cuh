@@ -6,10 +6,6 @@
 #pragma once
 #include "rdv_env.cuh"
 
-#ifndef RDV_ISO_PLANE
-#define RDV_ISO_PLANE 1        /* 1: isotropic bodies are integrated in the invariant plane (rk45_iso_plane) */
-#endif
-
 namespace rdv {
 
 __constant__ double c_zero3[3] = {0.0, 0.0, 0.0};     // the target carries no torque (rendezvous_env.py:585)
@@ -50,8 +46,8 @@ RDV_DEV void ingest_action_f32(const RdvParams &P, const float (&a)[6], EnvCount
 
 // Translation (impulse rotated by the OLD chaser attitude, then the CW transition; dynamics.py:24-55) and the
 // two attitude propagations (:552-604).  LOCKSTEP: the two isotropic solves advance interleaved stage by stage
-// (rk45_iso_pair, 2x ILP, ~240 registers) -- the right choice with <= 2 warps per SM sub-partition; otherwise one
-// solve after the other through a single copy of the solver (128 registers), which wins once 3-4 warps per
+// (rk45_iso_plane_pair, 2x ILP) -- the right choice with <= 2 warps per SM sub-partition; otherwise one solve after
+// the other through a single copy of the solver (rk45_iso_plane, 128 registers), which wins once 3-4 warps per
 // sub-partition hide the latency instead.
 template <bool ISO, bool CLOSED, bool LOCKSTEP>
 RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, int &rk_acc, int &rk_rej, int &fail)
@@ -80,13 +76,13 @@ RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, i
         bc.I = P.inertia_c; bc.Iinv = P.inv_inertia_c; bc.tau = P.torque_c;
         bt.I = P.inertia_t; bt.Iinv = P.inv_inertia_t; bt.tau = c_zero3;
         if (ISO && LOCKSTEP) {
-            const int k = RDV_ISO_PLANE ? rk45_iso_plane_pair(y, z, P.dt, rk_rej) : rk45_iso_pair(y, z, P.dt, rk_rej);
+            const int k = rk45_iso_plane_pair(y, z, P.dt, rk_rej);
             if (k < 0) fail = 1; else rk_acc += k;
         } else if (ISO) {
             // one solve after the other through a single copy of the solver code (bounded registers)
 #pragma unroll 1
             for (int body = 0; body < 2; ++body) {
-                const int k = RDV_ISO_PLANE ? rk45_iso_plane(y, P.dt, rk_rej) : rk45_attitude<true>(y, P.dt, bc, rk_rej);
+                const int k = rk45_iso_plane(y, P.dt, rk_rej);
                 if (k < 0) fail = 1; else rk_acc += k;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) { const double tmp = y[j]; y[j] = z[j]; z[j] = tmp; }
