@@ -509,6 +509,81 @@ RDV_DEV void rhs_plane(const double a, const double b, const double om2, const d
     kb = a * g;
 }
 
+// What the controller sees of one attempted step, in float32 (RDV_CTRL_F32 rationale above): the candidate state
+// y_new = a_new q0 + b_new p and the error estimate e = ea q0 + eb p in quaternion components, and
+// err^2 = mean((e_i / (atol + rtol max(|y_i|, |y_new,i|)))^2) over the reference's seven components (the three
+// rate components contribute 0).  q0 is orthogonal to p, so sum e_i^2 = ea^2 |q0|^2 + eb^2 |p|^2 and cancellation
+// inside single components cannot amplify the float32 rounding of the norm beyond ~2e-7 relative.
+RDV_DEV float plane_err2_f32(const double ea, const double eb, const double a_new, const double b_new,
+                             const float (&q0f)[4], const float (&pf)[4], const float (&ycf)[4], float (&ynf)[4])
+{
+    const float eaf = (float)ea, ebf = (float)eb, anf = (float)a_new, bnf = (float)b_new;
+    float esf = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ynf[i] = fmaf(bnf, pf[i], anf * q0f[i]);
+        const float e = fmaf(ebf, pf[i], eaf * q0f[i]);
+        const float m = fmaxf(fabsf(ycf[i]), fabsf(ynf[i]));
+        const float q = e * rcp_f32(fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
+        esf = fmaf(q, q, esf);
+    }
+    return esf * (1.0f / 7.0f);
+}
+// the same quantity in fp64, for the accept decision when the float32 value lies within 1e-3 of the threshold
+RDV_DEV double plane_err2_f64(const double ea, const double eb, const double a, const double b, const double a_new,
+                              const double b_new, const double (&q0)[4], const double (&p)[4])
+{
+    double es = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double yc = fma(b, p[i], a * q0[i]), yn = fma(b_new, p[i], a_new * q0[i]);
+        const double e = fma(eb, p[i], ea * q0[i]) * fast_rcp(fma(fmax(fabs(yc), fabs(yn)), RK_RTOL, RK_ATOL));
+        es = fma(e, e, es);
+    }
+    return es * (1.0 / 7.0);
+}
+// select_initial_step (scipy common.py:68-134, order 4) from the first slope (0, kb0) at (a, b) = (1, 0)
+RDV_DEV double plane_initial_step(const double (&y)[7], const float (&q0f)[4], const float (&pf)[4], const double kb0,
+                                  const double om2, const double inv_n0, const double dt)
+{
+    float inv_sc[4], d0s = 0.0f, d1s = 0.0f;
+    const float kb0f = (float)kb0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        inv_sc[i] = rcp_f32(fmaf(fabsf(q0f[i]), (float)RK_RTOL, (float)RK_ATOL));
+        const float v = q0f[i] * inv_sc[i], f = kb0f * pf[i] * inv_sc[i];       // y0 / scale, f0 / scale
+        d0s = fmaf(v, v, d0s);
+        d1s = fmaf(f, f, d1s);
+    }
+#pragma unroll
+    for (int i = 4; i < 7; ++i) {                                                // the rate components: f0 = 0
+        const float yi = (float)y[i];
+        const float v = yi * rcp_f32(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
+        d0s = fmaf(v, v, d0s);
+    }
+    d0s *= (1.0f / 7.0f);
+    d1s *= (1.0f / 7.0f);                                    // squares of the rms norms d0, d1
+    float h0f;
+    if (d0s < 1e-10f || d1s < 1e-10f) h0f = 1e-6f;
+    else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s));
+    const double h0 = fmin((double)h0f, dt);
+    double ka1, kb1;
+    rhs_plane(1.0, h0 * kb0, om2, inv_n0, ka1, kb1);         // y1 = y0 + h0 f0
+    const float daf = (float)ka1, dbf = (float)(kb1 - kb0);  // f1 - f0 in plane coordinates (ka0 = 0)
+    float d2s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float v = fmaf(dbf, pf[i], daf * q0f[i]) * inv_sc[i];
+        d2s = fmaf(v, v, d2s);
+    }
+    const float inv_h0 = rcp_f32((float)h0);
+    d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
+    float h1;
+    if (d1s <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0 * 1e-3f);
+    else h1 = pow_neg_tenth_f32(fminf(fmaxf(d1s, d2s), 1e30f) * 1e4f);   // (0.01/max(d1,d2))**(1/5)
+    return fmin(fmin(100.0 * h0, (double)h1), dt);
+}
+
 RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
 {
     const double hw[3] = {0.5 * y[4], 0.5 * y[5], 0.5 * y[6]};
@@ -520,49 +595,13 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
                          fma(-hw[0], q0[2], fma(hw[1], q0[1], hw[2] * q0[0]))};
     const double om2 = fma(hw[2], hw[2], fma(hw[1], hw[1], hw[0] * hw[0]));
     const double inv_n0 = fast_rsqrt(dot4(q0, q0));
+    float q0f[4], pf[4], ycf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { q0f[i] = (float)q0[i]; pf[i] = (float)p[i]; ycf[i] = q0f[i]; }
     double a = 1.0, b = 0.0;                    // y = a q0 + b p
     double ka[7], kb[7];                        // slopes in plane coordinates
     rhs_plane(a, b, om2, inv_n0, ka[0], kb[0]);
-    double yc[4] = {q0[0], q0[1], q0[2], q0[3]};            // current state, quaternion components
-
-    // ---- select_initial_step (order 4); float32 arithmetic on the reference's seven components ----
-    double h_abs;
-    {
-        float inv_sc[7], d0s = 0.0f, d1s = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const float yi = (float)y[i];
-            inv_sc[i] = rcp_f32(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
-            const float v = yi * inv_sc[i];
-            d0s = fmaf(v, v, d0s);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float v = (float)(kb[0] * p[i]) * inv_sc[i];          // f0 = ka q0 + kb p with ka = 0
-            d1s = fmaf(v, v, d1s);
-        }
-        d0s *= (1.0f / 7.0f);
-        d1s *= (1.0f / 7.0f);                                // squares of the rms norms d0, d1
-        float h0f;
-        if (d0s < 1e-10f || d1s < 1e-10f) h0f = 1e-6f;
-        else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s));
-        const double h0 = fmin((double)h0f, dt);
-        double ka1, kb1;
-        rhs_plane(fma(h0, ka[0], a), fma(h0, kb[0], b), om2, inv_n0, ka1, kb1);
-        const double da = ka1 - ka[0], db = kb1 - kb[0];
-        float d2s = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float v = (float)fma(db, p[i], da * q0[i]) * inv_sc[i];
-            d2s = fmaf(v, v, d2s);
-        }
-        const float inv_h0 = rcp_f32((float)h0);
-        d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
-        float h1;
-        if (d1s <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0 * 1e-3f);
-        else h1 = pow_neg_tenth_f32(fminf(fmaxf(d1s, d2s), 1e30f) * 1e4f);   // (0.01/max(d1,d2))**(1/5)
-        h_abs = fmin(fmin(100.0 * h0, (double)h1), dt);
-    }
+    double h_abs = plane_initial_step(y, q0f, pf, kb[0], om2, inv_n0, dt);
 
     double t = 0.0;
     int accepted = 0;
@@ -572,7 +611,7 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
         if (h_abs < min_step) h_abs = min_step;
         bool rejected = false;
         double t_new, h, a_new, b_new;
-        double y_new[4];
+        float ynf[4];
         for (;;) {
             if (h_abs < min_step) return -1;
             t_new = t + h_abs;
@@ -599,46 +638,25 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
             a_new = fma(h, fma(ka[5], RK_B6, fma(ka[4], RK_B5, fma(ka[3], RK_B4, fma(ka[2], RK_B3, ka[0] * RK_B1)))), a);
             b_new = fma(h, fma(kb[5], RK_B6, fma(kb[4], RK_B5, fma(kb[3], RK_B4, fma(kb[2], RK_B3, kb[0] * RK_B1)))), b);
             rhs_plane(a_new, b_new, om2, inv_n0, ka[6], kb[6]);
-            // ---- error estimate (K^T E) h in the plane, then everything the controller sees in quaternion
-            //      components: scale = atol + max(|y|, |y_new|) rtol, err = rms(e / scale) ----
+            // ---- error estimate (K^T E) h in the plane; the controller's norm in quaternion components ----
             const double ea = h * fma(ka[6], RK_E7, fma(ka[5], RK_E6, fma(ka[4], RK_E5, fma(ka[3], RK_E4,
                                   fma(ka[2], RK_E3, ka[0] * RK_E1)))));
             const double eb = h * fma(kb[6], RK_E7, fma(kb[5], RK_E6, fma(kb[4], RK_E5, fma(kb[3], RK_E4,
                                   fma(kb[2], RK_E3, kb[0] * RK_E1)))));
-            double eh[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                y_new[i] = fma(b_new, p[i], a_new * q0[i]);
-                eh[i] = fma(eb, p[i], ea * q0[i]);
-            }
-            float esf = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float m = (float)fmax(fabs(yc[i]), fabs(y_new[i]));
-                const float q = (float)eh[i] * rcp_f32(fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
-                esf = fmaf(q, q, esf);
-            }
-            esf *= (1.0f / 7.0f);                      // err_norm^2 (the three rate components contribute 0)
+            const float esf = plane_err2_f32(ea, eb, a_new, b_new, q0f, pf, ycf, ynf);
             if (!(esf < 1.0e30f)) return -1;           // NaN / inf: the reference shrinks h to failure
             bool accept = esf < 1.0f;
-            if (fabsf(esf - 1.0f) < 1.0e-3f) {         // threshold region: decide with the fp64 norm
-                double es = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double e = eh[i] * fast_rcp(fma(fmax(fabs(yc[i]), fabs(y_new[i])), RK_RTOL, RK_ATOL));
-                    es = fma(e, e, es);
-                }
-                accept = es * (1.0 / 7.0) < 1.0;
-            }
+            if (fabsf(esf - 1.0f) < 1.0e-3f)           // threshold region: decide with the fp64 norm
+                accept = plane_err2_f64(ea, eb, a, b, a_new, b_new, q0, p) < 1.0;
             // 0.9 err^-0.2, clamped where the controller's min / max saturate anyway
-            const float pf = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
+            const float pw = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
             if (accept) {
-                float factor = fminf(10.0f, pf);
+                float factor = fminf(10.0f, pw);
                 if (rejected) factor = fminf(1.0f, factor);
                 h_abs *= (double)factor;
                 break;
             }
-            h_abs *= (double)fmaxf(0.2f, pf);
+            h_abs *= (double)fmaxf(0.2f, pw);
             rejected = true;
             ++n_rejected;
         }
@@ -647,10 +665,10 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
         a = a_new; b = b_new;
         ka[0] = ka[6]; kb[0] = kb[6];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) yc[i] = y_new[i];
+        for (int i = 0; i < 4; ++i) ycf[i] = ynf[i];
         if (t - dt >= 0.0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) y[i] = yc[i];
+            for (int i = 0; i < 4; ++i) y[i] = fma(b, p[i], a * q0[i]);
             return accepted;
         }
     }
@@ -664,7 +682,8 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
 // operation for operation (tests/test_gpu_rollout.py compares the bits).
 RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double dt, int &n_rejected)
 {
-    double q0[2][4], p[2][4], yc[2][4], om2[2], inv_n0[2], a[2], b[2], ka0[2], kb0[2], h_abs[2], t[2];
+    double q0[2][4], p[2][4], om2[2], inv_n0[2], a[2], b[2], ka0[2], kb0[2], h_abs[2], t[2];
+    float q0f[2][4], pf[2][4], ycf[2][4];
     int accepted[2] = {0, 0};
     bool done[2] = {false, false}, rejected[2] = {false, false}, failed[2] = {false, false};
 #pragma unroll
@@ -681,59 +700,13 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
         inv_n0[c] = fast_rsqrt(dot4(q0[c], q0[c]));
         a[c] = 1.0; b[c] = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) yc[c][i] = q0[c][i];
+        for (int i = 0; i < 4; ++i) { q0f[c][i] = (float)q0[c][i]; pf[c][i] = (float)p[c][i]; ycf[c][i] = q0f[c][i]; }
     }
 #pragma unroll
     for (int c = 0; c < 2; ++c) rhs_plane(a[c], b[c], om2[c], inv_n0[c], ka0[c], kb0[c]);
-    // ---- select_initial_step for both bodies, expression for expression the one of rk45_iso_plane ----
-    {
-        float inv_sc[2][7], d1s[2];
-        double h0[2], ka1[2], kb1[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const double *y = c ? yb : ya;
-            float d0s = 0.0f;
-            d1s[c] = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const float yi = (float)y[i];
-                inv_sc[c][i] = rcp_f32(fmaf(fabsf(yi), (float)RK_RTOL, (float)RK_ATOL));
-                const float v = yi * inv_sc[c][i];
-                d0s = fmaf(v, v, d0s);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float v = (float)(kb0[c] * p[c][i]) * inv_sc[c][i];
-                d1s[c] = fmaf(v, v, d1s[c]);
-            }
-            d0s *= (1.0f / 7.0f);
-            d1s[c] *= (1.0f / 7.0f);
-            float h0f;
-            if (d0s < 1e-10f || d1s[c] < 1e-10f) h0f = 1e-6f;
-            else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s[c]));
-            h0[c] = fmin((double)h0f, dt);
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-            rhs_plane(fma(h0[c], ka0[c], a[c]), fma(h0[c], kb0[c], b[c]), om2[c], inv_n0[c], ka1[c], kb1[c]);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const double da = ka1[c] - ka0[c], db = kb1[c] - kb0[c];
-            float d2s = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float v = (float)fma(db, p[c][i], da * q0[c][i]) * inv_sc[c][i];
-                d2s = fmaf(v, v, d2s);
-            }
-            const float inv_h0 = rcp_f32((float)h0[c]);
-            d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
-            float h1;
-            if (d1s[c] <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0[c] * 1e-3f);
-            else h1 = pow_neg_tenth_f32(fminf(fmaxf(d1s[c], d2s), 1e30f) * 1e4f);
-            h_abs[c] = fmin(fmin(100.0 * h0[c], (double)h1), dt);
-            t[c] = 0.0;
-        }
-    }
+    h_abs[0] = plane_initial_step(ya, q0f[0], pf[0], kb0[0], om2[0], inv_n0[0], dt);
+    h_abs[1] = plane_initial_step(yb, q0f[1], pf[1], kb0[1], om2[1], inv_n0[1], dt);
+    t[0] = t[1] = 0.0;
     // ---- attempted steps, both bodies per pass, predicated commit ----
     while (!((done[0] || failed[0]) && (done[1] || failed[1]))) {
         double h[2], t_new[2], ha[2], as[2], bs[2];
@@ -778,34 +751,15 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
                                      fma(ka2[c], RK_E3, ka0[c] * RK_E1)))));
             const double eb = h[c] * fma(kb6[c], RK_E7, fma(kb5[c], RK_E6, fma(kb4[c], RK_E5, fma(kb3[c], RK_E4,
                                      fma(kb2[c], RK_E3, kb0[c] * RK_E1)))));
-            double eh[4], y_new[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                y_new[i] = fma(bs[c], p[c][i], as[c] * q0[c][i]);
-                eh[i] = fma(eb, p[c][i], ea * q0[c][i]);
-            }
-            float esf = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float m = (float)fmax(fabs(yc[c][i]), fabs(y_new[i]));
-                const float q = (float)eh[i] * rcp_f32(fmaf(m, (float)RK_RTOL, (float)RK_ATOL));
-                esf = fmaf(q, q, esf);
-            }
-            esf *= (1.0f / 7.0f);
+            float ynf[4];
+            const float esf = plane_err2_f32(ea, eb, as[c], bs[c], q0f[c], pf[c], ycf[c], ynf);
             const bool live = !done[c] && !failed[c];
             const bool bad = fail_now[c] || !(esf < 1.0e30f);
             bool accept = esf < 1.0f;
-            if (fabsf(esf - 1.0f) < 1.0e-3f) {         // threshold region: decide with the fp64 norm
-                double es = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double e = eh[i] * fast_rcp(fma(fmax(fabs(yc[c][i]), fabs(y_new[i])), RK_RTOL, RK_ATOL));
-                    es = fma(e, e, es);
-                }
-                accept = es * (1.0 / 7.0) < 1.0;
-            }
-            const float pf = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
-            float factor = accept ? fminf(10.0f, pf) : fmaxf(0.2f, pf);
+            if (fabsf(esf - 1.0f) < 1.0e-3f)           // threshold region: decide with the fp64 norm
+                accept = plane_err2_f64(ea, eb, a[c], b[c], as[c], bs[c], q0[c], p[c]) < 1.0;
+            const float pw = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
+            float factor = accept ? fminf(10.0f, pw) : fmaxf(0.2f, pw);
             if (accept && rejected[c]) factor = fminf(1.0f, factor);
             const bool commit = live && !bad && accept;
             if (live) {
@@ -817,7 +771,7 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
             if (commit) {
                 a[c] = as[c]; b[c] = bs[c]; ka0[c] = ka6[c]; kb0[c] = kb6[c];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) yc[c][i] = y_new[i];
+                for (int i = 0; i < 4; ++i) ycf[c][i] = ynf[i];
                 t[c] = t_new[c];
                 accepted[c] += 1;
                 done[c] = t_new[c] - dt >= 0.0;
@@ -825,7 +779,10 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { ya[i] = yc[0][i]; yb[i] = yc[1][i]; }
+    for (int i = 0; i < 4; ++i) {
+        ya[i] = fma(b[0], p[0][i], a[0] * q0[0][i]);
+        yb[i] = fma(b[1], p[1][i], a[1] * q0[1][i]);
+    }
     return (failed[0] || failed[1]) ? -1 : accepted[0] + accepted[1];
 }
 
