@@ -490,8 +490,7 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 // Every vector the Runge-Kutta scheme ever forms -- stage vectors, slopes, y_new, the error estimate -- is a
 // linear combination of q0 (the state at the start of the solve) and p = M q0:  for y = a q0 + b p,
 //
-//     M y = a p - b omega^2 q0,     |y|^2 = |q0|^2 (a^2 + omega^2 b^2)      (p is orthogonal to q0, |p| = omega |q0|;
-//                                                                          q0 is scaled to a unit vector),
+//     M y = a p - b omega^2 q0,     |y|^2 = |q0|^2 (a^2 + omega^2 b^2)      (p is orthogonal to q0, |p| = omega |q0|),
 //
 // so the scheme is advanced on the coordinates (a, b): a slope costs 11 fp64 operations instead of 25 and the
 // stage sums, the 5th-order solution and the embedded error run on 2 components instead of 4.  What the
@@ -502,10 +501,10 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 // exact arithmetic) at 159 instead of 307 fp64 operations per attempted step.  No division by omega occurs:
 // w = 0 gives p = 0 and a constant quaternion.
 // ---------------------------------------------------------------------------------
-RDV_DEV void rhs_plane(const double a, const double b, const double om2, double &ka, double &kb)
+RDV_DEV void rhs_plane(const double a, const double b, const double om2, const double inv_n0, double &ka, double &kb)
 {
     const double t = om2 * b;
-    const double g = fast_rsqrt(fma(t, b, a * a));                // 1 / |y| (the basis vector q0 / |q0| is a unit vector)
+    const double g = fast_rsqrt(fma(t, b, a * a)) * inv_n0;       // 1 / |y|
     ka = -(t * g);
     kb = a * g;
 }
@@ -543,16 +542,16 @@ RDV_DEV double plane_err2_f64(const double ea, const double eb, const double a, 
     }
     return es * (1.0 / 7.0);
 }
-// select_initial_step (scipy common.py:68-134, order 4) from the first slope (0, kb0) at (a, b) = (a0, 0)
-RDV_DEV double plane_initial_step(const double (&y)[7], const float (&ycf)[4], const float (&q0f)[4], const float (&pf)[4], const double a0,
-                                  const double kb0, const double om2, const double dt)
+// select_initial_step (scipy common.py:68-134, order 4) from the first slope (0, kb0) at (a, b) = (1, 0)
+RDV_DEV double plane_initial_step(const double (&y)[7], const float (&q0f)[4], const float (&pf)[4], const double kb0,
+                                  const double om2, const double inv_n0, const double dt)
 {
     float inv_sc[4], d0s = 0.0f, d1s = 0.0f;
     const float kb0f = (float)kb0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        inv_sc[i] = rcp_f32(fmaf(fabsf(ycf[i]), (float)RK_RTOL, (float)RK_ATOL));
-        const float v = ycf[i] * inv_sc[i], f = kb0f * pf[i] * inv_sc[i];        // y0 / scale, f0 / scale
+        inv_sc[i] = rcp_f32(fmaf(fabsf(q0f[i]), (float)RK_RTOL, (float)RK_ATOL));
+        const float v = q0f[i] * inv_sc[i], f = kb0f * pf[i] * inv_sc[i];       // y0 / scale, f0 / scale
         d0s = fmaf(v, v, d0s);
         d1s = fmaf(f, f, d1s);
     }
@@ -569,7 +568,7 @@ RDV_DEV double plane_initial_step(const double (&y)[7], const float (&ycf)[4], c
     else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s));
     const double h0 = fmin((double)h0f, dt);
     double ka1, kb1;
-    rhs_plane(a0, h0 * kb0, om2, ka1, kb1);          // y1 = y0 + h0 f0
+    rhs_plane(1.0, h0 * kb0, om2, inv_n0, ka1, kb1);         // y1 = y0 + h0 f0
     const float daf = (float)ka1, dbf = (float)(kb1 - kb0);  // f1 - f0 in plane coordinates (ka0 = 0)
     float d2s = 0.0f;
 #pragma unroll
@@ -588,22 +587,21 @@ RDV_DEV double plane_initial_step(const double (&y)[7], const float (&ycf)[4], c
 RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
 {
     const double hw[3] = {0.5 * y[4], 0.5 * y[5], 0.5 * y[6]};
-    // basis of the plane: q0 = y / |y| (a unit vector) and p = M q0 = 0.5 Omega(w) q0 (dynamics.py:137-150);
-    // the state starts at (a, b) = (|y|, 0)
-    const double n0sq = dot4(y, y), inv_n0 = fast_rsqrt(n0sq);
-    const double q0[4] = {y[0] * inv_n0, y[1] * inv_n0, y[2] * inv_n0, y[3] * inv_n0};
+    const double q0[4] = {y[0], y[1], y[2], y[3]};
+    // p = M q0 = 0.5 Omega(w) q0 (dynamics.py:137-150)
     const double p[4] = {-fma(hw[2], q0[3], fma(hw[1], q0[2], hw[0] * q0[1])),
                          fma(-hw[1], q0[3], fma(hw[2], q0[2], hw[0] * q0[0])),
                          fma(hw[0], q0[3], fma(-hw[2], q0[1], hw[1] * q0[0])),
                          fma(-hw[0], q0[2], fma(hw[1], q0[1], hw[2] * q0[0]))};
     const double om2 = fma(hw[2], hw[2], fma(hw[1], hw[1], hw[0] * hw[0]));
-    double a = n0sq * inv_n0, b = 0.0;          // y = a q0 + b p
+    const double inv_n0 = fast_rsqrt(dot4(q0, q0));
     float q0f[4], pf[4], ycf[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { q0f[i] = (float)q0[i]; pf[i] = (float)p[i]; ycf[i] = (float)y[i]; }
+    for (int i = 0; i < 4; ++i) { q0f[i] = (float)q0[i]; pf[i] = (float)p[i]; ycf[i] = q0f[i]; }
+    double a = 1.0, b = 0.0;                    // y = a q0 + b p
     double ka[7], kb[7];                        // slopes in plane coordinates
-    rhs_plane(a, b, om2, ka[0], kb[0]);
-    double h_abs = plane_initial_step(y, ycf, q0f, pf, a, kb[0], om2, dt);
+    rhs_plane(a, b, om2, inv_n0, ka[0], kb[0]);
+    double h_abs = plane_initial_step(y, q0f, pf, kb[0], om2, inv_n0, dt);
 
     double t = 0.0;
     int accepted = 0;
@@ -624,22 +622,22 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
             double as, bs;
             as = fma(ka[0] * RK_A21, h, a);
             bs = fma(kb[0] * RK_A21, h, b);
-            rhs_plane(as, bs, om2, ka[1], kb[1]);
+            rhs_plane(as, bs, om2, inv_n0, ka[1], kb[1]);
             as = fma(fma(ka[1], RK_A32, ka[0] * RK_A31), h, a);
             bs = fma(fma(kb[1], RK_A32, kb[0] * RK_A31), h, b);
-            rhs_plane(as, bs, om2, ka[2], kb[2]);
+            rhs_plane(as, bs, om2, inv_n0, ka[2], kb[2]);
             as = fma(fma(ka[2], RK_A43, fma(ka[1], RK_A42, ka[0] * RK_A41)), h, a);
             bs = fma(fma(kb[2], RK_A43, fma(kb[1], RK_A42, kb[0] * RK_A41)), h, b);
-            rhs_plane(as, bs, om2, ka[3], kb[3]);
+            rhs_plane(as, bs, om2, inv_n0, ka[3], kb[3]);
             as = fma(fma(ka[3], RK_A54, fma(ka[2], RK_A53, fma(ka[1], RK_A52, ka[0] * RK_A51))), h, a);
             bs = fma(fma(kb[3], RK_A54, fma(kb[2], RK_A53, fma(kb[1], RK_A52, kb[0] * RK_A51))), h, b);
-            rhs_plane(as, bs, om2, ka[4], kb[4]);
+            rhs_plane(as, bs, om2, inv_n0, ka[4], kb[4]);
             as = fma(fma(ka[4], RK_A65, fma(ka[3], RK_A64, fma(ka[2], RK_A63, fma(ka[1], RK_A62, ka[0] * RK_A61)))), h, a);
             bs = fma(fma(kb[4], RK_A65, fma(kb[3], RK_A64, fma(kb[2], RK_A63, fma(kb[1], RK_A62, kb[0] * RK_A61)))), h, b);
-            rhs_plane(as, bs, om2, ka[5], kb[5]);
+            rhs_plane(as, bs, om2, inv_n0, ka[5], kb[5]);
             a_new = fma(h, fma(ka[5], RK_B6, fma(ka[4], RK_B5, fma(ka[3], RK_B4, fma(ka[2], RK_B3, ka[0] * RK_B1)))), a);
             b_new = fma(h, fma(kb[5], RK_B6, fma(kb[4], RK_B5, fma(kb[3], RK_B4, fma(kb[2], RK_B3, kb[0] * RK_B1)))), b);
-            rhs_plane(a_new, b_new, om2, ka[6], kb[6]);
+            rhs_plane(a_new, b_new, om2, inv_n0, ka[6], kb[6]);
             // ---- error estimate (K^T E) h in the plane; the controller's norm in quaternion components ----
             const double ea = h * fma(ka[6], RK_E7, fma(ka[5], RK_E6, fma(ka[4], RK_E5, fma(ka[3], RK_E4,
                                   fma(ka[2], RK_E3, ka[0] * RK_E1)))));
@@ -684,31 +682,30 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
 // operation for operation (tests/test_gpu_rollout.py compares the bits).
 RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double dt, int &n_rejected)
 {
-    double q0[2][4], p[2][4], om2[2], a[2], b[2], ka0[2], kb0[2], h_abs[2], t[2];
+    double q0[2][4], p[2][4], om2[2], inv_n0[2], a[2], b[2], ka0[2], kb0[2], h_abs[2], t[2];
     float q0f[2][4], pf[2][4], ycf[2][4];
     int accepted[2] = {0, 0};
     bool done[2] = {false, false}, rejected[2] = {false, false}, failed[2] = {false, false};
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const double *yy = c ? yb : ya, *w = yy + 4;
-        const double hw[3] = {0.5 * w[0], 0.5 * w[1], 0.5 * w[2]};
-        const double yq[4] = {yy[0], yy[1], yy[2], yy[3]};
-        const double n0sq = dot4(yq, yq), inv_n0 = fast_rsqrt(n0sq);
+    for (int i = 0; i < 4; ++i) { q0[0][i] = ya[i]; q0[1][i] = yb[i]; }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) q0[c][i] = yq[i] * inv_n0;
+    for (int c = 0; c < 2; ++c) {
+        const double *w = c ? yb + 4 : ya + 4;
+        const double hw[3] = {0.5 * w[0], 0.5 * w[1], 0.5 * w[2]};
         p[c][0] = -fma(hw[2], q0[c][3], fma(hw[1], q0[c][2], hw[0] * q0[c][1]));
         p[c][1] = fma(-hw[1], q0[c][3], fma(hw[2], q0[c][2], hw[0] * q0[c][0]));
         p[c][2] = fma(hw[0], q0[c][3], fma(-hw[2], q0[c][1], hw[1] * q0[c][0]));
         p[c][3] = fma(-hw[0], q0[c][2], fma(hw[1], q0[c][1], hw[2] * q0[c][0]));
         om2[c] = fma(hw[2], hw[2], fma(hw[1], hw[1], hw[0] * hw[0]));
-        a[c] = n0sq * inv_n0; b[c] = 0.0;
+        inv_n0[c] = fast_rsqrt(dot4(q0[c], q0[c]));
+        a[c] = 1.0; b[c] = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { q0f[c][i] = (float)q0[c][i]; pf[c][i] = (float)p[c][i]; ycf[c][i] = (float)yq[i]; }
+        for (int i = 0; i < 4; ++i) { q0f[c][i] = (float)q0[c][i]; pf[c][i] = (float)p[c][i]; ycf[c][i] = q0f[c][i]; }
     }
 #pragma unroll
-    for (int c = 0; c < 2; ++c) rhs_plane(a[c], b[c], om2[c], ka0[c], kb0[c]);
-    h_abs[0] = plane_initial_step(ya, ycf[0], q0f[0], pf[0], a[0], kb0[0], om2[0], dt);
-    h_abs[1] = plane_initial_step(yb, ycf[1], q0f[1], pf[1], a[1], kb0[1], om2[1], dt);
+    for (int c = 0; c < 2; ++c) rhs_plane(a[c], b[c], om2[c], inv_n0[c], ka0[c], kb0[c]);
+    h_abs[0] = plane_initial_step(ya, q0f[0], pf[0], kb0[0], om2[0], inv_n0[0], dt);
+    h_abs[1] = plane_initial_step(yb, q0f[1], pf[1], kb0[1], om2[1], inv_n0[1], dt);
     t[0] = t[1] = 0.0;
     // ---- attempted steps, both bodies per pass, predicated commit ----
     while (!((done[0] || failed[0]) && (done[1] || failed[1]))) {
@@ -727,7 +724,7 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
         }
 #define RDV_PSTAGE(KA, KB, EA, EB)                                                       \
         _Pragma("unroll") for (int c = 0; c < 2; ++c) { as[c] = (EA); bs[c] = (EB); }    \
-        _Pragma("unroll") for (int c = 0; c < 2; ++c) rhs_plane(as[c], bs[c], om2[c], KA[c], KB[c]);
+        _Pragma("unroll") for (int c = 0; c < 2; ++c) rhs_plane(as[c], bs[c], om2[c], inv_n0[c], KA[c], KB[c]);
         RDV_PSTAGE(ka1, kb1, fma(ka0[c] * RK_A21, h[c], a[c]), fma(kb0[c] * RK_A21, h[c], b[c]))
         RDV_PSTAGE(ka2, kb2, fma(fma(ka1[c], RK_A32, ka0[c] * RK_A31), h[c], a[c]),
                    fma(fma(kb1[c], RK_A32, kb0[c] * RK_A31), h[c], b[c]))
