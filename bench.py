@@ -269,12 +269,13 @@ def run_cuda(args):
     b_step = (386.0 + 68.0) / KL                       # state load + store and the final observation, once per launch
     ach_tf = f_step * n / (t_step * 1e-3) / 1e12
     ach_gbs = b_step * n / (t_step * 1e-3) / 1e9
-    traffic = None
+    traffic, f_exec = None, None
     try:                                # dram bytes of one launch from the committed ncu capture (K-independent:
         with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:      # state in + out, final obs)
             tr = json.load(f)
         if tr.get("envs") == n:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            f_exec = tr.get("fp64_flop_per_env_step_executed")
     except Exception:
         pass
     roofline = {
@@ -284,6 +285,13 @@ def run_cuda(args):
         "peak_source": "rdv_fp64_peak_probe (DFMA microbenchmark, this run; MEASURED_PEAKS.json has no fp64 entry; "
                        "nominal 37 TFLOP/s)",
         "flop_per_env_step": f_step, "rk45_steps_per_solve": rk_mean, "steps_per_launch": KL,
+        # `achieved` counts the reference's formulation (4-component quaternion RK45, 6.65 kflop per
+        # env-step).  The kernel integrates the same equation in the invariant plane of the motion (2 components,
+        # same step sizes and results) and executes fewer operations; that figure comes from the ncu source page.
+        "executed": (None if closed or f_exec is None else
+                     {"flop_per_env_step": f_exec, "achieved": f_exec * n / (t_step * 1e-3) / 1e12, "unit": "TFLOP/s",
+                      "frac": f_exec * n / (t_step * 1e-3) / 1e12 / fp64_peak,
+                      "source": "profiles/r01_rollout_kernel.md (ncu source page: DFMA x 2 + DMUL + DADD per thread)"}),
         "launch_ms": t_launch, "launch_ms_min": min(full), "launches_timed": len(full),
         "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                 "bytes_per_env_step": b_step, "peak_source": peak_src},
