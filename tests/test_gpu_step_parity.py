@@ -167,6 +167,49 @@ def test_random_batch_vs_c_oracle_with_auto_reset(act_dtype):
     assert st["steps"] == n * steps and st["episodes"] == total_done and st["failures"] == 0
 
 
+def test_plane_solver_edge_states_vs_c_oracle():
+    """The isotropic bodies are integrated in the invariant plane span{q0, M q0} (rk45_iso_plane).  States at the
+    edges of that construction -- zero rates (M q0 = 0), rates at the observation bound, injected quaternions that
+    are not unit vectors -- must follow the C oracle (the 4-component restatement of scipy's RK45) like any other,
+    through both kernels (per-step pair kernel and fused rollout)."""
+    import torch
+    from oracle import c_oracle as CO
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    n = 512
+    rng = np.random.default_rng(11)
+    st = np.zeros((n, 20))
+    st[:, 0:3] = [0.0, -10.0, 0.0] + rng.normal(0, 0.5, (n, 3))
+    st[:, 3:6] = rng.normal(0, 0.05, (n, 3))
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    qt = rng.normal(size=(n, 4)); qt /= np.linalg.norm(qt, axis=1, keepdims=True)
+    st[:, 6:10], st[:, 13:17] = q, qt
+    st[:, 10:13] = rng.uniform(-0.17, 0.17, (n, 3))               # up to ~10 deg/s, the observation bound
+    st[:, 17:20] = rng.uniform(-0.05, 0.05, (n, 3))
+    st[0:64, 10:13] = 0.0                                        # chaser at rest
+    st[32:128, 17:20] = 0.0                                      # target at rest (both at rest for 32..63)
+    st[128:192, 6:10] *= 1.7                                     # injected non-unit quaternions
+    st[160:256, 13:17] *= 0.3
+    a = rng.uniform(-1, 1, (3, n, 6))
+    a[:, 0:32, 3:6] = 0.0                                        # no torque impulse either: w stays exactly 0
+    for fused in (False, True):
+        env = BatchedRendezvousEnv(n, seed=1, auto_reset=False, t_max=100)
+        env.reset()
+        env.set_state(st)
+        orc = CO.COracleBatch(CO.make_params(t_max=100), n)
+        orc.set_state(st, recompute_flags=True)
+        env.refresh_flags()
+        for k in range(3):
+            if fused:
+                out = env.rollout(1, actions=torch.as_tensor(a[k:k + 1], device=env.device), record_rewards=True)
+                rew = out["rewards"][0]
+            else:
+                _, rew, _ = env.step(torch.as_tensor(a[k], device=env.device))
+            _, o_rew, _ = orc.step(a[k], threads=4)
+            assert rel_err(env.get_state().cpu().numpy(), orc.state) <= REL_TOL, (fused, k)
+            assert rel_err(rew.cpu().numpy(), o_rew.copy()) <= REL_TOL, (fused, k)
+        assert env.read_stats()["failures"] == 0
+
+
 def test_closed_form_fast_path_within_tolerance():
     """The opt-in closed-form attitude propagation (exact for the env's isotropic, torque-free bodies) stays
     within the parity tolerance of the reference's RK45 at the default dt = 1 s."""
