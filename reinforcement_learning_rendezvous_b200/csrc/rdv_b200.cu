@@ -413,6 +413,9 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 // POLICY: the action of every step is the output of the SB3 MlpPolicy actor, evaluated on the tensor cores
 // (tcgen05 / TMEM, rdv_policy_tc.cuh: groups of 128 threads = 128 envs = one UMMA tile) from the observation the
 // previous step produced.
+#ifndef RDV_SYNC_PERIOD
+#define RDV_SYNC_PERIOD 8             /* steps between the CTA barriers that keep the warps in one code region */
+#endif
 #ifndef RDV_LOCKSTEP_MAX_TPB
 #define RDV_LOCKSTEP_MAX_TPB 256      /* CTAs up to this size interleave the two attitude solves (rk45_iso_plane_pair) */
 #endif
@@ -469,9 +472,18 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
         int countdown = refill;                                // steps until the next refill of the rows
 
         for (int k = 0; k < io.steps; ++k) {
-            // Keep the CTA's warps in the same code region (instruction-cache locality).  Measured alternatives:
-            // a barrier every 2 / 4 steps 1 % / 8 % slower, extra barriers before each solve 4 % slower.
+            // Keep the CTA's warps in the same code region (instruction-cache locality).  With the first, ~60 KB
+            // step a barrier every step was best (every 2 / 4 steps: 1 % / 8 % slower); the plane solver's step is
+            // smaller and tolerates drift: every step 12.06, every 4-8 steps 11.66, every 32 steps 11.77, never
+            // 12.1-12.2 us per step.  The fused actor keeps the barrier of every step (its staging rows alias the
+            // activation tiles of the next step's actor).
+#if RDV_SYNC_PERIOD == 1
             __syncthreads();
+#elif RDV_SYNC_PERIOD > 1
+            if (POLICY || (k % RDV_SYNC_PERIOD) == 0) __syncthreads();
+#else
+            if (POLICY) __syncthreads();
+#endif
             // ---- action ----
             ActionTerms t;
             const int64_t row = (int64_t)k * n + i;
