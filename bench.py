@@ -288,6 +288,9 @@ def run_cuda(args):
         # `achieved` counts the reference's formulation (4-component quaternion RK45, 6.65 kflop per
         # env-step).  The kernel integrates the same equation in the invariant plane of the motion (2 components,
         # same step sizes and results) and executes fewer operations; that figure comes from the ncu source page.
+        "note": "achieved counts the flops of the reference's formulation (SURVEY.md 8d), as the contract defines "
+                "it; the kernel reaches the same results with fewer executed operations (see `executed`), so frac "
+                "measures delivered reference arithmetic per second against the fp64 peak and can exceed 1",
         "executed": (None if closed or f_exec is None else
                      {"flop_per_env_step": f_exec, "achieved": f_exec * n / (t_step * 1e-3) / 1e12, "unit": "TFLOP/s",
                       "frac": f_exec * n / (t_step * 1e-3) / 1e12 / fp64_peak,
