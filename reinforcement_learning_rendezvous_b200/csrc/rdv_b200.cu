@@ -8,8 +8,8 @@
 //
 // Kernels:
 //   step_kernel     rdv_step     one launch per step, two lanes per env, team-of-8 auto-reset fused in
-//   rollout_kernel  rdv_rollout  K steps per launch, state in registers, one in-phase CTA per SM, in-warp
-//                                resets, actions from a tensor / Philox / the policy on the tensor cores
+//   rollout_kernel  rdv_rollout  K steps per launch, state in registers, one CTA per SM, prefetched in-warp
+//                                resets, actions from a tensor / Philox / the actor on the tensor cores (tcgen05)
 //   reset_kernel, observe_kernel, errors_kernel, frame_kernel, policy_kernel, fp64_peak_kernel
 #include <cuda_runtime.h>
 #include <math.h>
@@ -395,21 +395,20 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 // ---------------------------------------------------------------------------------
 // Fused rollout: K consecutive steps of every env in ONE launch, state resident in registers.
 //
-// Per step: the action comes from a caller tensor [K][n][6] or from the device Philox stream
-// (philox_actions), the env steps through the shared building blocks of rdv_step.cuh, and finished envs are reset inside the
-// warp: the (up to four at a time) finished lanes are handed to the warp's four 8-lane teams
-// (team_reset_core), which leave the new state in a shared scratch row that the owning lane reads back
-// into its registers.  What a per-step launch pays every step -- launch latency, 193 B/env of state
-// load + store, the phase alignment of all warps (everybody in the fp64-heavy RK45 at the same time,
-// everybody in the latency-bound epilogue at the same time) -- is paid once per K steps; the warps drift
-// apart after a few steps and the fp64 pipe sees a steady mix.  Statistics are accumulated in registers
-// and reduced once.
+// Per step: the action comes from a caller tensor [K][n][6], from the device Philox stream (philox_actions) or
+// from the actor evaluated in the launch; the env steps through the shared building blocks of rdv_step.cuh, and
+// finished envs restart inside the warp: the warp's four 8-lane teams (team_reset_core) compute reset states into
+// shared-memory rows -- ahead of time, one row per lane, refilled every few steps (the reset state of (env,
+// episode) does not depend on the trajectory), or on demand with the fused actor.  What a per-step launch pays
+// every step -- launch latency, 193 B/env of state load + store -- is paid once per K steps.  Statistics are
+// accumulated in registers and reduced once.
 // ---------------------------------------------------------------------------------
 // Launch shape: ONE CTA per SM, every CTA owns an equal contiguous slice of the batch and walks it in
 // passes of at most TPB environments, all K steps of a pass before the next pass.  The CTA's warps re-converge
-// at a barrier every step: the step is ~60 KB of straight-line code, and warps that drift apart thrash the
-// instruction cache (measured: 58 % hit rate and 3.1 of 6.2 stall cycles per instruction on "no instruction"
-// with four independent 64-thread CTAs per SM; in-phase warps run the same workload 1.7x faster).
+// at a barrier every RDV_SYNC_PERIOD steps: the step is tens of KB of straight-line code, and warps that drift far
+// apart thrash the instruction cache (measured with the first, ~60 KB step: 58 % hit rate and 3.1 of 6.2 stall
+// cycles per instruction on "no instruction" with four independent 64-thread CTAs per SM; in-phase warps ran the
+// same workload 1.7x faster).
 // POLICY: the action of every step is the output of the SB3 MlpPolicy actor, evaluated on the tensor cores
 // (tcgen05 / TMEM, rdv_policy_tc.cuh: groups of 128 threads = 128 envs = one UMMA tile) from the observation the
 // previous step produced.
