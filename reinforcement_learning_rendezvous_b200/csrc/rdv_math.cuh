@@ -555,6 +555,7 @@ RDV_DEV double plane_initial_step(const double (&y)[7], const float (&q0f)[4], c
         d0s = fmaf(v, v, d0s);
         d1s = fmaf(f, f, d1s);
     }
+    const float d0q = d0s * (1.0f / 7.0f);                                       // the quaternion part of d0^2
 #pragma unroll
     for (int i = 4; i < 7; ++i) {                                                // the rate components: f0 = 0
         const float yi = (float)y[i];
@@ -567,20 +568,31 @@ RDV_DEV double plane_initial_step(const double (&y)[7], const float (&q0f)[4], c
     if (d0s < 1e-10f || d1s < 1e-10f) h0f = 1e-6f;
     else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s));
     const double h0 = fmin((double)h0f, dt);
-    double ka1, kb1;
-    rhs_plane(1.0, h0 * kb0, om2, inv_n0, ka1, kb1);         // y1 = y0 + h0 f0
-    const float daf = (float)ka1, dbf = (float)(kb1 - kb0);  // f1 - f0 in plane coordinates (ka0 = 0)
-    float d2s = 0.0f;
+    // d2 = rms((f(y0 + h0 f0) - f0) / scale) / h0 only enters through max(d1, d2).  In plane coordinates
+    // f1 - f0 = da q0 + db p with |da| <= omega^2 h0 kb0^2 and |db| <= omega^2 h0^2 kb0^3 / 2, hence
+    // d2 <= omega^2 kb0^2 (rms(q0 / scale) + h0 d1 / 2): of the order omega d1, i.e. below d1 unless the body
+    // spins at ~1 rad/s.  When this bound (with 5 % slack for the float32 arithmetic) is below d1 the second slope
+    // is not evaluated at all; otherwise d2 is formed exactly as scipy does.
+    const float h0c = (float)h0;
+    const float ub = (float)om2 * kb0f * kb0f * fmaf(0.5f * h0c, sqrtf(d1s), sqrtf(d0q));
+    float dmax = d1s;
+    if (!(ub * ub * 1.05f <= d1s)) {
+        double ka1, kb1;
+        rhs_plane(1.0, h0 * kb0, om2, inv_n0, ka1, kb1);         // y1 = y0 + h0 f0
+        const float daf = (float)ka1, dbf = (float)(kb1 - kb0);  // f1 - f0 in plane coordinates (ka0 = 0)
+        float d2s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float v = fmaf(dbf, pf[i], daf * q0f[i]) * inv_sc[i];
-        d2s = fmaf(v, v, d2s);
+        for (int i = 0; i < 4; ++i) {
+            const float v = fmaf(dbf, pf[i], daf * q0f[i]) * inv_sc[i];
+            d2s = fmaf(v, v, d2s);
+        }
+        const float inv_h0 = rcp_f32(h0c);
+        d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
+        dmax = fmaxf(d1s, d2s);
     }
-    const float inv_h0 = rcp_f32((float)h0);
-    d2s = d2s * (1.0f / 7.0f) * inv_h0 * inv_h0;
     float h1;
-    if (d1s <= 1e-30f && d2s <= 1e-30f) h1 = fmaxf(1e-6f, (float)h0 * 1e-3f);
-    else h1 = pow_neg_tenth_f32(fminf(fmaxf(d1s, d2s), 1e30f) * 1e4f);   // (0.01/max(d1,d2))**(1/5)
+    if (dmax <= 1e-30f) h1 = fmaxf(1e-6f, h0c * 1e-3f);     // d1 <= 1e-15 and d2 <= 1e-15
+    else h1 = pow_neg_tenth_f32(fminf(dmax, 1e30f) * 1e4f);  // (0.01/max(d1,d2))**(1/5)
     return fmin(fmin(100.0 * h0, (double)h1), dt);
 }
 
