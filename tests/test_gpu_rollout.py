@@ -38,6 +38,44 @@ def test_rollout_equals_repeated_step(dtype):
     assert sa["episodes"] > n and abs(sa["reward_sum"] - sb["reward_sum"]) <= 1e-9 * abs(sb["reward_sum"])
 
 
+@pytest.mark.parametrize("cfg", [dict(dt=0.25, t_max=10), dict(dt=0.5, t_max=15), dict(dt=2, t_max=40),
+                                 dict(dt=4, t_max=60), dict(h=400e3, koz_radius=10.0), dict(rc0=30, wt0=0.0436),
+                                 dict(corridor_half_angle=0.2618, h=2000e3)])
+def test_sensitivity_axes_step_and_rollout_vs_c_oracle(cfg):
+    """The axes of sensitivity_analysis.py:97-134 (dt, h, koz_radius, rc0, wt0, corridor_half_angle): 12 steps of
+    512 envs through rdv_step and through rdv_rollout against the C oracle -- other step lengths change how the
+    adaptive solver splits the interval (more or fewer RK steps, the clipped last step)."""
+    import torch
+    from oracle import c_oracle as CO
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    from reinforcement_learning_rendezvous_b200.environment_utils import config_to_kwargs
+    n, K, seed = 512, 12, 21
+    kw = {k: v for k, v in config_to_kwargs(cfg, stochastic=True).items() if v is not None}
+    rng = np.random.default_rng(2)
+    acts = rng.uniform(-1, 1, (K, n, 6))
+    ids, episode = np.arange(n), np.ones(n, dtype=np.int32)
+    orc = CO.COracleBatch(CO.make_params(**kw), n)
+    orc.reset_from_uniforms(CO.philox_uniforms(seed, ids, episode))
+    ref_state, ref_rew = [], []
+    for k in range(K):
+        _, r, _ = orc.step(acts[k], threads=4)
+        ref_state.append(orc.state.copy()); ref_rew.append(r.copy())
+    for fused in (False, True):
+        env = BatchedRendezvousEnv(n, seed=seed, auto_reset=False, **kw)
+        env.reset()
+        if fused:
+            out = env.rollout(K, actions=torch.as_tensor(acts, device=env.device), record_rewards=True)
+            assert rel_err(out["rewards"].cpu().numpy(), np.array(ref_rew)) <= REL_TOL, (cfg, fused)
+            assert rel_err(env.get_state().cpu().numpy(), ref_state[-1]) <= REL_TOL, (cfg, fused)
+        else:
+            for k in range(K):
+                _, rew, _ = env.step(torch.as_tensor(acts[k], device=env.device))
+                assert rel_err(env.get_state().cpu().numpy(), ref_state[k]) <= REL_TOL, (cfg, k)
+                assert rel_err(rew.cpu().numpy(), ref_rew[k]) <= REL_TOL, (cfg, k)
+        st = env.read_stats()
+        assert st["failures"] == 0 and st["steps"] == n * K
+
+
 def test_rollout_philox_actions_vs_c_oracle():
     """Device-generated actions + in-warp resets over 60 steps vs the C oracle driven by the same streams."""
     import torch
