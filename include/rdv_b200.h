@@ -121,9 +121,7 @@ typedef struct RdvState {
 typedef struct RdvStepIO {
     const void *actions;     /* [n][6] row-major, float32 (act_f64 = 0) or float64 (act_f64 = 1)  */
     int32_t  act_f64;
-    int32_t  auto_reset;     /* 0: off.  1: envs that finish are reset by the same call (VecEnv semantics).
-                              * 2: finished envs are only queued in reset_scratch; the caller runs
-                              *    rdv_auto_reset afterwards (lets a profiler time the two kernels apart) */
+    int32_t  auto_reset;     /* 0: off.  1: envs that finish are reset by the same call (VecEnv semantics)  */
     float   *obs;            /* [n][17] observation after the step (after the reset if auto-reset) */
     double  *reward;         /* [n]                                                                */
     uint8_t *done;           /* [n]                                                                */
