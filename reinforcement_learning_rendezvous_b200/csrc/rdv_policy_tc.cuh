@@ -1,6 +1,8 @@
-// rdv_policy_tc.cuh -- the stand-alone batched actor forward (rdv_policy_forward: model.predict of the SB3
-// MlpPolicy, monte_carlo.py:128-133) on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators
-// AND TMEM-resident A operands.
+// rdv_policy_tc.cuh -- the actor forward (model.predict of the SB3 MlpPolicy, monte_carlo.py:128-133) on the
+// 5th-generation tensor cores: tcgen05.mma with TMEM accumulators AND TMEM-resident A operands.  tile_setup /
+// tile_forward / tile_teardown are used by two kernels: policy_tc_kernel below (rdv_policy_forward, stand-alone,
+// observations from HBM) and rollout_kernel in rdv_b200.cu (the actor of every step of a fused rollout,
+// observations from the env state in registers).
 //
 // A group of 128 threads owns tiles of 128 environments (UMMA M = 128, one env per thread / TMEM lane):
 //
@@ -21,7 +23,8 @@
 // named barriers, 128 TMEM columns each: D @ +0..63, A hi @ +64..127): while one group waits for its MMAs or its
 // TMEM loads, three others run their tanh epilogues.  Per group a single thread issues the MMAs and commits them
 // to an mbarrier.  exp(2x) = 2^(2 log2(e) x): the factor 2 log2(e) is folded into W0, b0, W1, b1 when the weights
-// are split (once per CTA), so a hidden unit costs MUFU.EX2, a quarter of a MUFU.RCP, a handful of FP32 operations and the split.
+// are split (once per CTA), so a hidden unit costs MUFU.EX2, a quarter of a MUFU.RCP, a handful of FP32 operations
+// and the split.
 //
 // Shared-memory operands use the canonical no-swizzle K-major UMMA layout: 8-row x 16-byte core matrices, rows of
 // a core matrix 16 B apart, 8-row groups SBO = 128 B apart, the two 16-byte K-chunks of a K = 8 step
