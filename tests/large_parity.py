@@ -1,8 +1,8 @@
 """Large parity run: the benchmark workload itself (65,536 envs, Philox actions, in-kernel resets, 250-step launches
 with the reset prefetch) checked step by step against the C oracle driven by the same action / reset streams
-(development tool; the tests do the same at sizes that finish in seconds).
+(a checker script, not collected by pytest; the tests do the same at sizes that finish in seconds).
 
-usage: python tools/large_parity.py [envs] [launches] [steps_per_launch]
+usage (from the repo root): python tests/large_parity.py [envs] [launches] [steps_per_launch]
 """
 import sys, time, json
 import numpy as np
