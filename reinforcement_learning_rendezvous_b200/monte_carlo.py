@@ -39,6 +39,32 @@ def _terminal_errors(errors, limits):
     return (pos[index:].mean(), vel[index:].mean(), np.degrees(att[index:].mean()), np.degrees(rot[index:].mean()))
 
 
+def _terminal_errors_batch(errors, lengths, limits):
+    """``_terminal_errors`` for M episodes at once.  errors [T, M, 4] (rows >= lengths[i] + 1 of episode i are
+    ignored), lengths [M] = steps taken; returns [M, 4] (pos, vel, att deg, rot deg).  Same rule as
+    monte_carlo.py:159-189: the first index at which all four constraints hold, else the first with three
+    (pos, vel and att or rot), else pos and vel, else pos, else the last sample; then the mean of the tail."""
+    errors = np.asarray(errors, dtype=np.float64)
+    t_max, m = errors.shape[0], errors.shape[1]
+    valid = np.arange(t_max)[:, None] <= np.asarray(lengths)[None, :]                     # [T, M]
+    lim = np.asarray(limits, dtype=np.float64)
+    ok = (errors < lim[None, None, :]) & valid[:, :, None]                                  # NaN rows compare False
+    pm, vm, am, rm = ok[..., 0], ok[..., 1], ok[..., 2], ok[..., 3]
+    levels = (pm & vm & am & rm, (pm & vm & am) | (pm & vm & rm), pm & vm, pm)
+    last = np.asarray(lengths, dtype=np.int64)
+    index = last.copy()                                                                     # the "-1" case: last sample
+    decided = np.zeros(m, dtype=bool)
+    for mask in levels:
+        hit = mask.any(axis=0) & ~decided
+        index = np.where(hit, mask.argmax(axis=0), index)
+        decided |= hit
+    tail = valid & (np.arange(t_max)[:, None] >= index[None, :])                            # [T, M]
+    count = tail.sum(axis=0)
+    mean = np.where(tail[:, :, None], np.nan_to_num(errors), 0.0).sum(axis=0) / count[:, None]
+    mean[:, 2:] = np.degrees(mean[:, 2:])
+    return mean
+
+
 def evaluate(model, env, initial_state):
     """One deterministic episode from ``initial_state`` (dict rc vc qc wc qt wt) -- monte_carlo.py:94-207."""
     num_collisions = num_successes = 0
@@ -126,7 +152,7 @@ def evaluate_batch(policy, initial_states, config=None, reward_kwargs=None, devi
     err_np = err_log.cpu().numpy()
     length_np = length.cpu().numpy()
     limits = (p.max_rd_error, p.max_vd_error, p.max_qd_error, p.max_wd_error)
-    te = np.array([_terminal_errors(err_np[:length_np[i] + 1, i], limits) for i in range(m)])
+    te = _terminal_errors_batch(err_np, length_np, limits)
     n_col_np, n_suc_np = n_col.cpu().numpy(), n_suc.cpu().numpy()
     dt = p.dt
     return dict(

@@ -55,6 +55,25 @@ def test_terminal_error_reduction():
     assert _terminal_errors(e4, lim)[1] == pytest.approx(9.0)
 
 
+def test_terminal_error_reduction_batched_equals_per_episode():
+    """evaluate_batch reduces all episodes at once (_terminal_errors_batch); same rule, episode by episode, on ragged
+    random episodes that exercise every level of the first-index cascade."""
+    from reinforcement_learning_rendezvous_b200.monte_carlo import _terminal_errors, _terminal_errors_batch
+    lim = (0.5, 0.1, np.radians(5), np.radians(1))
+    rng = np.random.default_rng(0)
+    t, m = 62, 600
+    err = np.abs(rng.normal(size=(t, m, 4))) * np.array([1.0, 0.2, 0.15, 0.03]) * np.linspace(2, 0.1, t)[:, None, None]
+    err[:, 100:200, 3] = 1.0                            # rot never met
+    err[:, 200:300, 2:] = 1.0                           # only pos / vel can be met
+    err[:, 300:400, 1:] = 1.0                           # only pos
+    err[:, 400:450] = 9.0                               # nothing met
+    lengths = rng.integers(1, t - 1, m)
+    for i in range(m):
+        err[lengths[i] + 1:, i] = np.nan                # what evaluate_batch leaves after the episode's end
+    one = np.array([_terminal_errors(err[:lengths[i] + 1, i], lim) for i in range(m)])
+    np.testing.assert_allclose(_terminal_errors_batch(err, lengths, lim), one, rtol=1e-12, atol=0)
+
+
 def test_shard_range_partitions():
     from reinforcement_learning_rendezvous_b200.distributed import shard_range
     for total, world in ((1 << 20, 8), (65536, 4), (1000, 3), (7, 8), (5, 1)):
