@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -138,7 +139,7 @@ def run_reference(args):
     from oracle.subproc_vec_env import time_subproc_baseline
     cores = args.ref_procs or os.cpu_count() or 1
     res = time_subproc_baseline(steps=args.steps, warmup=max(args.warmup, 1), n_procs=cores, seed=0,
-                                max_seconds=args.ref_max_seconds)
+                                max_seconds=args.ref_max_seconds, min_seconds=args.ref_min_seconds)
     sample = (f"{res['steps']} VecEnv steps of {cores} envs (one env per process, Pipe protocol, auto-reset in the "
               f"worker), random fp64 actions, default RendezvousEnv parameters; {res['seconds']:.1f} s")
     line = {
@@ -214,40 +215,84 @@ def run_cuda(args):
         return ms
 
     # ---------------- device-resident leg: fused rollouts, KL steps per launch, Philox actions ----------------
+    # One "repeat" = one K-step rollout (launches of at most KL steps) followed by the per-rollout statistics
+    # reduction.  The timed region holds R repeats, R chosen so that it lasts >= ~60 ms whatever --steps is; the
+    # all-reduce of rollout r (NCCL, N > 1) is issued asynchronously on a snapshot of the statistics and waited for
+    # after rollout r + 1 has been enqueued, and one SM is left free for it (RdvRolloutIO.sm_reserve).
     KL = max(1, min(args.steps_per_launch, K))
     launches = [KL] * (K // KL) + ([K % KL] if K % KL else [])
     env = BatchedRendezvousEnv(n, device=dev, seed=args.seed, env_offset=rank * n, auto_reset=True,
                                integrator=args.integrator)
+    env.sm_reserve = 1 if world > 1 else 0
     env.reset()
     done_steps = 0
-    if W:
-        env.rollout(W, action_seed=args.seed + 1, step_base=0)
-        done_steps = W
-    env.stats.zero_()
+    W_eff = max(W, 3)
+    env.rollout(W_eff, action_seed=args.seed + 1, step_base=0)
+    done_steps = W_eff
+    # calibration (untimed, doubles as warm-up of the K-step launch shape): how long is one repeat?
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    c0.record()
+    for kl in launches:
+        env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
+        done_steps += kl
+    c1.record()
+    torch.cuda.synchronize()
+    t_rep = max_over_ranks(c0.elapsed_time(c1))
+    n_l = len(launches)
+    R = max(1, math.ceil(args.min_region_ms / max(t_rep, 1e-3)), math.ceil(25 / n_l))
+    R = min(R, 4000)
+    if world > 1:                                          # every rank must run the same number of repeats
+        rt = torch.tensor([R], dtype=torch.int64, device=dev)
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        R = int(rt[0])
+    stats_bufs = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
+    snaps = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
+    total_stats = torch.zeros(N.NSTATS, dtype=torch.float64, device=dev)
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(launches) + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(R * n_l + 1)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pending = None                                     # (work handle, snapshot) of the previous rollout's reduction
     barrier()
     e0.record()
     ev[0].record()
-    for j, kl in enumerate(launches):
-        env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
-        done_steps += kl
-        ev[j + 1].record()
-    all_reduce_stats(env.stats)                       # the per-rollout statistics reduction (NCCL when N > 1)
+    j = 0
+    for r in range(R):
+        buf = stats_bufs[r & 1]
+        buf.zero_()
+        env.stats = buf
+        for kl in launches:
+            env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
+            done_steps += kl
+            j += 1
+            ev[j].record()
+        # the reduction of the PREVIOUS rollout was issued before this rollout's launches: it ran beside them
+        if pending is not None:
+            work, snap = pending
+            if work is not None:
+                work.wait()
+            total_stats += snap
+        snap = snaps[r & 1]
+        snap.copy_(buf)
+        pending = (all_reduce_stats(snap, async_op=True), snap)    # NCCL when N > 1 (sum over ranks), else a no-op
+    work, snap = pending
+    if work is not None:
+        work.wait()
+    total_stats += snap
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
-    stats = dict(zip(N.STAT_NAMES, env.stats.cpu().tolist()))
+    stats = dict(zip(N.STAT_NAMES, total_stats.cpu().tolist()))
     total_steps = stats["steps"]
-    assert total_steps == world * n * K, (total_steps, world, n, K)
-    value = world * n * K / (ms * 1e-3)
+    assert total_steps == world * n * K * R, (total_steps, world, n, K, R)
+    value = world * n * K * R / (ms * 1e-3)
     rk_mean = stats["rk_accepted"] / (2.0 * max(total_steps, 1.0))
     # dominant kernel: rollout_kernel, per-launch durations of the full-size launches inside the timed region
-    full = [ev[j].elapsed_time(ev[j + 1]) for j, kl in enumerate(launches) if kl == KL]
+    full = [ev[q].elapsed_time(ev[q + 1]) for q in range(R * n_l) if launches[q % n_l] == KL]
     t_launch = sum(full) / len(full)
     t_step = t_launch / KL
+    env.stats = stats_bufs[0]
 
     # fp64 peak: DFMA probe, best of 6
     blocks, threads, iters = 148 * 8, 256, 4096
@@ -266,16 +311,19 @@ def run_cuda(args):
     closed = args.integrator == "closed_form"
     f_step = F_STEP_CLOSED_FORM if closed else F_STEP_BASE + F_STEP_PER_RK * rk_mean
     peaks, peak_src = _peaks()
-    b_step = (386.0 + 68.0) / KL                       # state load + store and the final observation, once per launch
+    # state load + store, the reset-row scratch load + store and the final observation, once per launch
+    b_step = (386.0 + 2 * 8.0 * N.RESET_ROWS + 68.0) / KL
     ach_tf = f_step * n / (t_step * 1e-3) / 1e12
     ach_gbs = b_step * n / (t_step * 1e-3) / 1e9
-    traffic, f_exec = None, None
-    try:                                # dram bytes of one launch from the committed ncu capture (K-independent:
-        with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:      # state in + out, final obs)
+    traffic, f_exec, ncu_pipe, ncu_src = None, None, None, None
+    try:                                # per-launch facts of the committed ncu capture of this kernel
+        with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:
             tr = json.load(f)
         if tr.get("envs") == n:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             f_exec = tr.get("fp64_flop_per_env_step_executed")
+            ncu_pipe = tr.get("fp64_pipe_pct")
+            ncu_src = tr.get("source")
     except Exception:
         pass
     roofline = {
@@ -290,19 +338,20 @@ def run_cuda(args):
         # same step sizes and results) and executes fewer operations; that figure comes from the ncu source page.
         "note": "achieved counts the flops of the reference's formulation (SURVEY.md 8d), as the contract defines "
                 "it; the kernel reaches the same results with fewer executed operations (see `executed`), so frac "
-                "measures delivered reference arithmetic per second against the fp64 peak and can exceed 1",
+                "measures delivered reference arithmetic per second against the fp64 peak and can exceed 1; "
+                "ncu_fp64_pipe_pct is what the profiler reports for the fp64 pipe of this kernel",
         "executed": (None if closed or f_exec is None else
                      {"flop_per_env_step": f_exec, "achieved": f_exec * n / (t_step * 1e-3) / 1e12, "unit": "TFLOP/s",
-                      "frac": f_exec * n / (t_step * 1e-3) / 1e12 / fp64_peak,
-                      "source": "profiles/r01_rollout_kernel.md (ncu source page: DFMA x 2 + DMUL + DADD per thread)"}),
-        "launch_ms": t_launch, "launch_ms_min": min(full), "launches_timed": len(full),
+                      "frac": f_exec * n / (t_step * 1e-3) / 1e12 / fp64_peak, "source": ncu_src}),
+        "ncu_fp64_pipe_pct": ncu_pipe,
+        "launch_ms": t_launch, "launch_ms_min": min(full), "launch_ms_max": max(full), "launches_timed": len(full),
         "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                 "bytes_per_env_step": b_step, "peak_source": peak_src},
     }
 
     # ---------------- the same launches with L2 flushed in between (a 256 MB write before each) ----------------
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    F = min(len(launches), 8)
+    F = 8
     fe = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(F)]
     for j in range(F):
         flush.fill_(j & 0xFF)
@@ -334,7 +383,7 @@ def run_cuda(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(1 + rank)
     ring = torch.rand((RING, n, 6), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
-    KS = min(K, 500)
+    KS = min(max(K, 200), 500)
     for k in range(10):
         env.step(ring[k % RING])
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,25 +400,63 @@ def run_cuda(args):
                 "actions": f"fp64 U(-1,1), pre-generated {RING}-step device ring ({RING * n * 48 / 1e6:.0f} MB > L2)"}
 
     # ---------------- closed-loop rollouts with the shipped policy fused into the launch (tensor-core MLP) --------
-    policy_rollout = None
+    # policy_rollout: this workload's batch (65,536 envs per GPU); policy_rollout_1m: BASELINE.json configs[3],
+    # 131,072 envs per GPU = 1,048,576 envs on 8 GPUs, with the per-rollout statistics all-reduce in the region.
+    policy_rollout = policy_rollout_1m = None
     pol_path = os.path.join(ROOT, "tests", "golden", "policy.npz")
     if os.path.exists(pol_path) and not closed:
         from reinforcement_learning_rendezvous_b200 import MlpPolicy
         pol = MlpPolicy.load(pol_path, device=dev)
-        env.rollout(KL, policy=pol)
-        KP = min(K, 4 * KL)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        p0.record()
-        for j in range(KP // KL):
-            env.rollout(KL, policy=pol)
-        p1.record()
-        barrier()
-        pms = max_over_ranks(p0.elapsed_time(p1))
-        policy_rollout = {"value": world * n * (KP // KL) * KL / (pms * 1e-3), "unit": UNIT,
-                          "ms_per_step": pms / ((KP // KL) * KL), "steps": (KP // KL) * KL,
-                          "policy": "SB3 MlpPolicy actor 17-64-64-6 tanh (models/mlp_model_best weights), deterministic, "
-                                    "3xTF32 tcgen05.mma (TMEM-resident activations) inside rollout_kernel"}
+        what = ("SB3 MlpPolicy actor 17-64-64-6 tanh (models/mlp_model_best weights), deterministic, "
+                "3xTF32 tcgen05.mma (TMEM-resident activations) inside rollout_kernel")
+
+        def policy_leg(penv, kl):
+            penv.sm_reserve = 1 if world > 1 else 0
+            for _ in range(2):
+                penv.rollout(kl, policy=pol)
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            q0.record()
+            penv.rollout(kl, policy=pol)
+            q1.record()
+            torch.cuda.synchronize()
+            reps = max(3, math.ceil(args.min_region_ms / max(max_over_ranks(q0.elapsed_time(q1)), 1e-3)))
+            if world > 1:
+                rt = torch.tensor([reps], dtype=torch.int64, device=dev)
+                dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+                reps = int(rt[0])
+            bufs = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
+            snp = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
+            pend = None
+            barrier()
+            q0.record()
+            for r in range(reps):
+                penv.stats = bufs[r & 1]
+                penv.stats.zero_()
+                penv.rollout(kl, policy=pol)
+                if pend is not None and pend is not False:
+                    pend.wait()
+                snp[r & 1].copy_(penv.stats)
+                pend = all_reduce_stats(snp[r & 1], async_op=True) or False
+            if pend:
+                pend.wait()
+            q1.record()
+            barrier()
+            pms = max_over_ranks(q0.elapsed_time(q1))
+            m = penv.num_envs
+            return {"value": world * m * reps * kl / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms / (reps * kl),
+                    "steps": reps * kl, "steps_per_launch": kl, "repeats": reps, "envs_per_gpu": m,
+                    "total_envs": world * m, "policy": what}
+
+        env.stats = stats_bufs[0]
+        policy_rollout = policy_leg(env, min(KL, max(K, 16)))
+        big = BatchedRendezvousEnv(2 * n, device=dev, seed=args.seed, env_offset=rank * 2 * n, auto_reset=True)
+        big.reset()
+        policy_rollout_1m = policy_leg(big, 64)
+        policy_rollout_1m["config"] = ("BASELINE.json configs[3]: 131,072 envs per GPU (1,048,576 on 8 GPUs), fused "
+                                       "MLP policy inference, 64 steps per launch, one NCCL statistics all-reduce per "
+                                       "launch (overlapped with the next launch)")
+        del big
 
     # ---------------- end-to-end leg: numpy actions in, numpy results out, through the VecEnv ----------------
     del env
@@ -377,8 +464,8 @@ def run_cuda(args):
     venv.reset()
     rng = np.random.default_rng(100 + rank)
     host_ring = rng.uniform(-1, 1, (RING, n, 6)).astype(np.float32)
-    KE = min(K, args.e2e_steps)
-    for k in range(max(3, min(W, 10))):
+    KE = max(args.e2e_steps, 1)              # a floor of its own: ~2 s of steps whatever --steps is
+    for k in range(max(10, min(W, 50))):
         venv.step(host_ring[k % RING])
     checksum = 0.0
     d2h_before = venv.d2h_bytes_total
@@ -396,7 +483,9 @@ def run_cuda(args):
     e2e = {"value": world * n * KE / (e2e_ms * 1e-3), "unit": UNIT, "steps": KE,
            "ms_per_step": e2e_ms / KE, "h2d_bytes_per_step": venv.h2d_bytes_per_step,
            "d2h_bytes_per_step": d2h_e2e,
-           "api": "RendezvousVecEnv.step(np.float32[N,6]) -> (obs, rewards, dones, infos) numpy, pinned staging"}
+           "extra_fetches": venv.extra_fetches,
+           "api": "RendezvousVecEnv.step(np.float32[N,6]) -> (obs, rewards, dones, infos) numpy: one pinned H2D copy, "
+                  "one launch, one D2H copy of [count | rewards | dones | obs | finished rows], one synchronise"}
 
     # the same loop through the array-returning variant (no per-env Python objects)
     barrier()
@@ -416,14 +505,19 @@ def run_cuda(args):
         return 0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / (K * R), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"batched RendezvousEnv, {n:,} envs per GPU, random actions, fp64 step/reset "
                                "(BASELINE.json configs[1])",
                    "envs_per_gpu": n, "total_envs": world * n, "auto_reset": True, "integrator": args.integrator,
                    "actions": "fp64 U(-1,1) drawn on the device every step from the Philox4x32-10 stream "
                               "(action seed; global env id, step index)",
-                   "steps_per_launch": KL,
+                   "steps_per_launch": KL, "repeats": R, "steps_timed": K * R, "timed_region_ms": ms,
+                   "timing": "the timed region is `repeats` x (one `steps`-step rollout + its statistics reduction), "
+                             "sized to last >= %g ms whatever --steps is" % args.min_region_ms,
+                   "stats_all_reduce": ("one 16-double NCCL all-reduce per rollout, issued asynchronously and waited "
+                                        "for after the next rollout is enqueued; the rollout leaves 1 SM free for it"
+                                        if world > 1 else "no-op at N = 1"),
                    "l2": "state lives in registers for the steps of a launch and is re-read from memory once per "
                          "launch; ms_per_step_l2_flushed repeats the launches with a 256 MB L2 flush before each; "
                          "ms_per_step_no_auto_reset = 16-step launches right after a batch reset, auto_reset off "
@@ -432,9 +526,9 @@ def run_cuda(args):
                    "ms_per_step_no_auto_reset": ms_no_reset,
                    "parallelism": f"{world} x independent env shards, no data-path collective; one "
                                   "16-double statistics all-reduce per rollout"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": len(launches),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": R * len(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "step_api": step_api,
-        "policy_rollout": policy_rollout,
+        "policy_rollout": policy_rollout, "policy_rollout_1m": policy_rollout_1m,
         "episode_stats": {"episodes": stats["episodes"], "mean_length": stats["length_sum"] / max(stats["episodes"], 1),
                           "success_rate": stats["succeeded"] / max(stats["episodes"], 1),
                           "rk_rejected": stats["rk_rejected"], "failures": stats["failures"]},
@@ -461,7 +555,9 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--integrator", choices=("rk45", "closed_form"), default="rk45")
-    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-steps", type=int, default=1000)
+    ap.add_argument("--min-region-ms", type=float, default=60.0, help="minimum length of a timed region")
+    ap.add_argument("--ref-min-seconds", type=float, default=8.0, help="time floor of the reference arm")
     ap.add_argument("--steps-per-launch", type=int, default=250, help="env steps fused into one rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

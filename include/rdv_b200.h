@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 13
+#define RDV_ABI_VERSION 14
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -108,6 +108,9 @@ typedef struct RdvParams {
     double obs_inv_r, obs_inv_v, obs_inv_w;           /* 1/(2*max_axial_distance), 1/(2*5), 1/(2*max_wc) */
     double near_sq;                /* max(koz, |rd| + max_rd_error)^2 (+margin): beyond it neither a collision,
                                     * a success nor a reward bonus is possible (:397, :417, :348)        */
+    int32_t box_hi_r, box_hi_v, box_hi_w;   /* high words of max_axial_distance / max_axial_speed / max_wc times  *
+                                             * (1 - 1e-6): the fast path of the observation Box test (:367)       */
+    int32_t reserved1;
 } RdvParams;
 
 /* Environment state: device pointers into caller-owned buffers. */
@@ -129,7 +132,28 @@ typedef struct RdvStepIO {
     int8_t  *end_reason;     /* nullable [n]: -1 running, 0 obs, 1 time, 2 bubble, 3 attitude      */
     double  *episode_record; /* nullable [n][RDV_EP_NCOL]: written for finished episodes only      */
     double  *stats;          /* nullable [RDV_NSTATS] device accumulator                           */
+    /* -- one-copy host path (RendezvousVecEnv): everything a VecEnv step returns, in one caller-owned block -- */
+    float   *reward_f32;     /* nullable [n]: the reward rounded to float32 (what SB3's VecEnv returns)        */
+    int32_t *fin_count;      /* nullable [1]: number of rows appended to fin_rows by this call; the library     *
+                              * zeroes it on the stream before the launch                                       */
+    void    *fin_rows;       /* nullable [fin_capacity] RdvFinishedRow: one row per env whose episode ended in  *
+                              * this call, in no particular order (sort by .env on the host if needed)          */
+    int32_t  fin_capacity;   /* rows fin_rows can hold (n is always enough)                                     */
+    int32_t  fin_append;     /* 1: keep fin_count and append (a further launch of the same step, other env range) */
+    int32_t  fin_env_base;   /* added to the env index stored in the rows (index of env 0 of this launch)       */
+    int32_t  reserved;
 } RdvStepIO;
+
+/* What a VecEnv's info dict of a finished env carries (DummyVecEnv.step_wait + Monitor.step, main.py:33-34):
+ * the env index, the end reason of get_done_condition (rendezvous_env.py:377), the terminal observation and the
+ * episode record.  128 bytes, 16-byte aligned. */
+typedef struct RdvFinishedRow {
+    int32_t env;                         /* local env index                                   */
+    int32_t end_reason;                  /* 0 obs, 1 time, 2 bubble, 3 attitude               */
+    float   terminal_obs[RDV_OBS_DIM];   /* last observation of the episode (pre-reset)       */
+    float   pad;
+    double  record[RDV_EP_NCOL];         /* RDV_EP_* columns                                  */
+} RdvFinishedRow;
 
 /* -- constants ------------------------------------------------------------------------------ */
 int  rdv_abi_version(void);
@@ -150,10 +174,6 @@ int  rdv_params_derive(RdvParams *p);
 int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t n,
              uint64_t seed, int64_t env_offset, void *cuda_stream);
 
-/* K consecutive steps of every env in one launch (state stays in registers; finished envs are reset in
- * place).  This is the rollout-collection loop of SB3's collect_rollouts around env.step
- * (main.py:114 -> OnPolicyAlgorithm.collect_rollouts) with the action taken from `actions` or drawn on the
- * device.  The per-step results a rollout buffer needs are optional outputs. */
 /* fp32 tanh MLP obs[17] -> hidden -> hidden -> action[6] of an SB3 MlpPolicy (main.py:39-48), deterministic mean
  * clipped to [-1,1] (model.predict, monte_carlo.py:128-133).  Weights are row-major [out][in] as in torch.nn.Linear. */
 typedef struct RdvPolicy {
@@ -164,6 +184,10 @@ typedef struct RdvPolicy {
     int32_t reserved;
     const float *log_std;    /* nullable [6]: state-independent log std of the Gaussian head (sampling mode) */
 } RdvPolicy;
+/* K consecutive steps of every env in one launch (state stays in registers; finished envs are reset in
+ * place).  This is the rollout-collection loop of SB3's collect_rollouts around env.step
+ * (main.py:114 -> OnPolicyAlgorithm.collect_rollouts) with the action taken from `actions` or drawn on the
+ * device.  The per-step results a rollout buffer needs are optional outputs. */
 enum { RDV_ACTIONS_F32 = 0, RDV_ACTIONS_F64 = 1, RDV_ACTIONS_PHILOX = 2,
        RDV_ACTIONS_POLICY = 3,          /* a = clip(actor(obs)): model.predict(deterministic=True)                 */
        RDV_ACTIONS_POLICY_SAMPLE = 4 }; /* a ~ N(actor(obs), exp(log_std)^2), the env gets clip(a) and actions_out  *
@@ -176,7 +200,7 @@ typedef struct RdvRolloutIO {
     int32_t  reserved;       /* set to 0 (the library passes its reset-prefetch period to the kernel here)   */
     const void *actions;     /* [K][n][6] float32 / float64 for the tensor sources                         */
     uint64_t action_seed;    /* RDV_ACTIONS_PHILOX: U(-1,1) fp64 actions from Philox(action_seed; global   */
-    int64_t  step_base;      /*   env id, step_base + k): 6 draws per env-step                             */
+    int64_t  step_base;      /*   env id, step_base + k): six 32-bit draws per env-step, a = (w + 0.5) 2^-31 - 1 */
     double  *actions_out;    /* nullable [K][n][6]: the applied Philox (float64) or policy (float32!) actions */
     float   *obs;            /* [n][17] observation after the last step (post-reset for finished envs)     */
     double  *rewards;        /* nullable [K][n]                                                            */
@@ -184,7 +208,30 @@ typedef struct RdvRolloutIO {
     float   *obs_steps;      /* nullable [K][n][17] observation returned by every step                     */
     double  *stats;          /* nullable [RDV_NSTATS] device accumulator                                   */
     RdvPolicy policy;        /* RDV_ACTIONS_POLICY: a = clip(actor(obs)), evaluated in the launch (tensor cores) */
+    /* Caller-owned scratch that carries every env's prefetched NEXT reset state (rendezvous_env.py:223-270 for
+     * (env, episode + 1): it depends on the seed and the counters only, not on the trajectory) from one launch to
+     * the next, so that short launches run at the rate of long ones.  [RDV_RESET_ROWS][ld] like RdvState.f64, offset
+     * to the same env; rows 0..19 state, 20 / 21 the collided / success flags, row 22 the episode index the row was
+     * computed for (0 = none; a row is used only if it equals the env's episode + 1).  Zero row 22 whenever the
+     * seed or the parameters change.  NULL: the rows live and die with the launch. */
+    double  *reset_rows;
+    int32_t  sm_reserve;     /* SMs left without a CTA of this launch, e.g. 1 so that the statistics all-reduce of the *
+                              * previous rollout (another stream) runs beside it instead of behind it                  */
+    int32_t  reserved2;
+    /* Monte-Carlo evaluator mode (monte_carlo.py:94-207), needs auto_reset = 0: [n][RDV_MC_NCOL] per-episode
+     * results accumulated in registers from the state at launch (sample 0) to the env's first done; finished envs
+     * stop stepping.  NULL: off. */
+    double  *mc_out;
 } RdvRolloutIO;
+#define RDV_RESET_ROWS 23
+/* Columns of RdvRolloutIO.mc_out: the workbook columns of monte_carlo.py:190-203 (errors in rad / rad/s, the host
+ * converts to degrees; ep_len in steps), then what else an evaluator wants. */
+enum { RDV_MC_EP_LEN = 0, RDV_MC_NUM_COLLISIONS, RDV_MC_COLLIDED, RDV_MC_TOTAL_REWARD, RDV_MC_TOTAL_DELTA_V,
+       RDV_MC_NUM_SUCCESSES, RDV_MC_SUCCEEDED, RDV_MC_MIN_KOZ, RDV_MC_POS_ERR, RDV_MC_VEL_ERR, RDV_MC_ATT_ERR,
+       RDV_MC_ROT_ERR, RDV_MC_LEVEL,      /* constraints met at the averaging start: 0 all four .. 3 position only, 4 none */
+       RDV_MC_TAIL_COUNT,                 /* samples averaged                                                   */
+       RDV_MC_END_REASON,                 /* -1: still running when the launch ended                             */
+       RDV_MC_TOTAL_DELTA_W, RDV_MC_NCOL };
 int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, int64_t n, uint64_t seed,
                 int64_t env_offset, void *cuda_stream);
 
@@ -222,6 +269,13 @@ int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n
  * rdv_policy_forward_ffma: the same op as plain fp32 FMAs, one thread per env (numerics reference). */
 int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
 int rdv_policy_forward_ffma(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
+
+/* Development / test knobs that used to be environment variables (read once at load as defaults):
+ * RDV_TUNE_ROLLOUT_TPB forces the rollout CTA size (256 | 384 | 448 | 512, 0 = automatic), RDV_TUNE_RESET_REFILL sets
+ * the reset prefetch period in steps (0 = reset on demand only; default 8).  Returns the previous value, or
+ * RDV_ERR_SIZE for an unknown key. */
+enum { RDV_TUNE_ROLLOUT_TPB = 0, RDV_TUNE_RESET_REFILL = 1 };
+int rdv_tune(int key, int value);
 
 /* Test hook: y[i] = f(x[i]) for the device math helpers the step is built from.  op 0: 1/sqrt(x), 1: 1/x,
  * 2: sqrt(x), 3: x^-0.1 (fp64 controller), 4: x^-0.1 (float32 controller), 5: acos(round(x, 5))

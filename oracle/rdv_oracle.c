@@ -576,20 +576,19 @@ void orc_philox_uniforms(uint64_t seed, int64_t env_id, int32_t episode_idx, dou
  * step index lo, 0x40000000 | block | step index hi << 4), blocks 0..2, key = action seed; a = 2u - 1. */
 void orc_philox_actions(uint64_t seed, int64_t n, const int64_t *env_ids, int64_t step_index, double *actions)
 {
+    /* two blocks per env-step; six of the eight 32-bit words become a = (w + 0.5) 2^-31 - 1 (exact in double) */
     for (int64_t e = 0; e < n; ++e) {
-        for (uint32_t blk = 0; blk < 3; ++blk) {
+        uint32_t w[8];
+        for (uint32_t blk = 0; blk < 2; ++blk) {
             uint32_t c[4] = {(uint32_t)env_ids[e], (uint32_t)((uint64_t)env_ids[e] >> 32), (uint32_t)step_index,
                              0x40000000u | blk | (((uint32_t)((uint64_t)step_index >> 32) & 0x00FFFFFFu) << 4)};
             philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-            double u0 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6)) / 9007199254740992.0;
-            double u1 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) / 9007199254740992.0;
-            actions[6 * e + 2 * blk] = 2.0 * u0 - 1.0;
-            actions[6 * e + 2 * blk + 1] = 2.0 * u1 - 1.0;
+            for (int j = 0; j < 4; ++j) w[4 * blk + j] = c[j];
         }
+        for (int j = 0; j < 6; ++j) actions[6 * e + j] = (double)w[j] * 4.656612873077392578125e-10 + (-1.0 + 2.3283064365386962890625e-10);
     }
 }
 
-/* all 24 reset draws of many envs at once */
 void orc_philox_uniforms_batch(uint64_t seed, int64_t n, const int64_t *env_ids, const int32_t *episode_idx, double *u)
 {
     for (int64_t e = 0; e < n; ++e) orc_philox_uniforms(seed, env_ids[e], episode_idx[e], u + 24 * e);

@@ -90,9 +90,10 @@ class OracleSubprocVecEnv:
             p.join(timeout=10)
 
 
-def time_subproc_baseline(steps, warmup=1, n_procs=None, seed=0, max_seconds=None, **env_kwargs):
+def time_subproc_baseline(steps, warmup=1, n_procs=None, seed=0, max_seconds=None, min_seconds=None, **env_kwargs):
     """Random fp64 actions through the SubprocVecEnv protocol.  Returns dict(value=env-steps/s, cores, steps,
-    seconds).  ``max_seconds`` bounds the timed part (the loop stops early and reports the steps it did)."""
+    seconds).  ``max_seconds`` bounds the timed part (the loop stops early and reports the steps it did);
+    ``min_seconds`` is a floor: the loop keeps stepping past ``steps`` until that much time has been sampled."""
     venv = OracleSubprocVecEnv(n_procs=n_procs, seed=seed, **env_kwargs)
     try:
         rng = np.random.default_rng(seed)
@@ -101,10 +102,13 @@ def time_subproc_baseline(steps, warmup=1, n_procs=None, seed=0, max_seconds=Non
             venv.step(rng.uniform(-1, 1, (venv.num_envs, 6)))
         done_steps = 0
         t0 = time.perf_counter()
-        for _ in range(steps):
+        while True:
             venv.step(rng.uniform(-1, 1, (venv.num_envs, 6)))
             done_steps += 1
-            if max_seconds is not None and time.perf_counter() - t0 > max_seconds:
+            el = time.perf_counter() - t0
+            if max_seconds is not None and el > max_seconds:
+                break
+            if done_steps >= steps and (min_seconds is None or el >= min_seconds):
                 break
         dt = time.perf_counter() - t0
     finally:

@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200
 SOURCES = ("rdv_b200.cu",)
 HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh", "rdv_policy.cuh", "rdv_policy_tc.cuh")
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -69,6 +69,7 @@ class RdvParams(C.Structure):
         ("att_scale", C.c_double), ("bonus_scale", C.c_double), ("collision_scale", C.c_double),
         ("obs_inv_r", C.c_double), ("obs_inv_v", C.c_double), ("obs_inv_w", C.c_double),
         ("near_sq", C.c_double),
+        ("box_hi_r", C.c_int32), ("box_hi_v", C.c_int32), ("box_hi_w", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -82,7 +83,14 @@ class RdvStepIO(C.Structure):
         ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
         ("terminal_obs", C.c_void_p), ("end_reason", C.c_void_p), ("episode_record", C.c_void_p),
         ("stats", C.c_void_p),
+        ("reward_f32", C.c_void_p), ("fin_count", C.c_void_p), ("fin_rows", C.c_void_p),
+        ("fin_capacity", C.c_int32), ("fin_append", C.c_int32), ("fin_env_base", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class RdvFinishedRow(C.Structure):
+    _fields_ = [("env", C.c_int32), ("end_reason", C.c_int32), ("terminal_obs", C.c_float * 17), ("pad", C.c_float),
+                ("record", C.c_double * 6)]
 
 
 class RdvPolicy(C.Structure):
@@ -99,7 +107,15 @@ class RdvRolloutIO(C.Structure):
         ("actions", C.c_void_p), ("action_seed", C.c_uint64), ("step_base", C.c_int64),
         ("actions_out", C.c_void_p), ("obs", C.c_void_p), ("rewards", C.c_void_p), ("dones", C.c_void_p),
         ("obs_steps", C.c_void_p), ("stats", C.c_void_p), ("policy", RdvPolicy),
+        ("reset_rows", C.c_void_p), ("sm_reserve", C.c_int32), ("reserved2", C.c_int32), ("mc_out", C.c_void_p),
     ]
+
+
+RESET_ROWS = 23
+(MC_EP_LEN, MC_NUM_COLLISIONS, MC_COLLIDED, MC_TOTAL_REWARD, MC_TOTAL_DELTA_V, MC_NUM_SUCCESSES, MC_SUCCEEDED,
+ MC_MIN_KOZ, MC_POS_ERR, MC_VEL_ERR, MC_ATT_ERR, MC_ROT_ERR, MC_LEVEL, MC_TAIL_COUNT, MC_END_REASON,
+ MC_TOTAL_DELTA_W, MC_NCOL) = range(17)
+TUNE_ROLLOUT_TPB, TUNE_RESET_REFILL = 0, 1
 
 
 ACTIONS_F32, ACTIONS_F64, ACTIONS_PHILOX, ACTIONS_POLICY, ACTIONS_POLICY_SAMPLE = 0, 1, 2, 3, 4
@@ -110,6 +126,7 @@ PROTOTYPES = {
     "rdv_abi_version": (C.c_int, []),
     "rdv_sizeof_params": (C.c_int, []),
     "rdv_strerror": (C.c_char_p, [C.c_int]),
+    "rdv_tune": (C.c_int, [C.c_int, C.c_int]),
     "rdv_params_default": (None, [C.POINTER(RdvParams)]),
     "rdv_params_derive": (C.c_int, [C.POINTER(RdvParams)]),
     "rdv_step": (C.c_int, [C.POINTER(RdvParams), C.POINTER(RdvState), C.POINTER(RdvStepIO), C.c_int64,

@@ -70,8 +70,10 @@ class BatchedRendezvousEnv:
         self.num_envs = n = int(num_envs)
         if n <= 0:
             raise ValueError("num_envs must be positive")
-        self.seed, self.env_offset, self.auto_reset = int(seed), int(env_offset), bool(auto_reset)
+        self._seed, self.env_offset, self.auto_reset = int(seed), int(env_offset), bool(auto_reset)
         self.ctor_kwargs = dict(ctor_kwargs)
+        self.reset_rows = None          # prefetched reset rows carried from rollout to rollout (allocated on first use)
+        self.sm_reserve = 0             # SMs a rollout launch leaves free (distributed.py: overlapped stats all-reduce)
 
         if param_batches:
             groups, lo = [], 0
@@ -104,12 +106,66 @@ class BatchedRendezvousEnv:
         self.end_reason = torch.full((n,), -1, dtype=torch.int8, device=dev)
         self.episode_record = torch.zeros((n, N.EP_NCOL), dtype=torch.float64, device=dev)
         self.stats = torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) if track_stats else None
-        self._io_cache = {}
+        self.host_block = None          # see enable_host_block()
+        self.reward_f32 = self.fin_count = self.fin_rows = None
         self._keepalive = None
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def seed(self) -> int:
+        return self._seed
+
+    @seed.setter
+    def seed(self, value: int):
+        self._seed = int(value)
+        self.invalidate_reset_rows()
+
+    def invalidate_reset_rows(self):
+        """The prefetched reset rows are a function of (seed, parameters, env id, episode): forget them when the
+        first two change (the episode tag row covers the rest)."""
+        if self.reset_rows is not None:
+            self.reset_rows[N.RESET_ROWS - 1].zero_()
+
+    def _reset_rows_ptr(self, g: "ParamGroup"):
+        if not self.auto_reset:
+            return None
+        if self.reset_rows is None:
+            self.reset_rows = torch.zeros((N.RESET_ROWS, self.ld), dtype=torch.float64, device=self.device)
+        return self.reset_rows.data_ptr() + 8 * g.lo
+
     def _state_of(self, g: ParamGroup) -> N.RdvState:
         return N.RdvState(self.f64.data_ptr() + 8 * g.lo, self.i32.data_ptr() + 4 * g.lo, self.ld)
+
+    def enable_host_block(self):
+        """Re-home everything one ``step`` returns to a host-side VecEnv into ONE contiguous device block, so that a
+        single device-to-host copy fetches it: ``[count | reward f32[N] | done u8[N] | obs f32[N,17] | finished rows]``
+        (every section 256-byte aligned).  ``obs`` / ``done`` become views of the block; ``step`` then also writes
+        float32 rewards and appends one 128-byte :class:`RdvFinishedRow` per finished env (index, end reason, terminal
+        observation, episode record) through one atomic counter.  Returns the section offsets in bytes."""
+        if self.host_block is not None:
+            return self.block_layout
+        n = self.num_envs
+
+        def up(x):
+            return (x + 255) // 256 * 256
+        off_rew = 256
+        off_done = up(off_rew + 4 * n)
+        off_obs = up(off_done + n)
+        off_rows = up(off_obs + 4 * N.OBS_DIM * n)
+        total = off_rows + C.sizeof(N.RdvFinishedRow) * n
+        blk = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        self.host_block = blk
+        self.block_layout = dict(count=0, reward=off_rew, done=off_done, obs=off_obs, rows=off_rows, total=total,
+                                 row_bytes=C.sizeof(N.RdvFinishedRow))
+        self.fin_count = blk[0:4].view(torch.int32)
+        self.reward_f32 = blk[off_rew:off_rew + 4 * n].view(torch.float32)
+        new_done = blk[off_done:off_done + n]
+        new_obs = blk[off_obs:off_obs + 4 * N.OBS_DIM * n].view(torch.float32).view(n, N.OBS_DIM)
+        new_done.copy_(self.done)
+        new_obs.copy_(self.obs)
+        self.done, self.obs = new_done, new_obs
+        self.fin_rows = blk[off_rows:]
+        return self.block_layout
 
     def _check_actions(self, actions: torch.Tensor) -> torch.Tensor:
         if not isinstance(actions, torch.Tensor):
@@ -131,6 +187,7 @@ class BatchedRendezvousEnv:
         act_f64 = 1 if actions.dtype == torch.float64 else 0
         esz = 8 if act_f64 else 4
         stream = _stream_ptr(self.device)
+        blk = self.host_block is not None
         with torch.cuda.device(self.device):
             for gi, g in enumerate(self.groups):
                 io = N.RdvStepIO(
@@ -139,7 +196,10 @@ class BatchedRendezvousEnv:
                     self.done.data_ptr() + g.lo,
                     self.terminal_obs.data_ptr() + g.lo * N.OBS_DIM * 4, self.end_reason.data_ptr() + g.lo,
                     self.episode_record.data_ptr() + g.lo * N.EP_NCOL * 8,
-                    self.stats.data_ptr() if self.stats is not None else None)
+                    self.stats.data_ptr() if self.stats is not None else None,
+                    self.reward_f32.data_ptr() + g.lo * 4 if blk else None,
+                    self.fin_count.data_ptr() if blk else None, self.fin_rows.data_ptr() if blk else None,
+                    self.num_envs if blk else 0, 1 if gi else 0, g.lo, 0)
                 st = self._state_of(g)
                 N.check(self.lib.rdv_step(C.byref(g.params), C.byref(st), C.byref(io), g.n, self.seed,
                                           self.env_offset + g.lo, stream), "rdv_step")
@@ -149,7 +209,7 @@ class BatchedRendezvousEnv:
     def rollout(self, steps: int, actions: Optional[torch.Tensor] = None, action_seed: Optional[int] = None,
                 step_base: int = 0, record_rewards: bool = False, record_dones: bool = False,
                 record_obs: bool = False, record_actions: bool = False, policy=None,
-                stochastic: bool = False) -> dict:
+                stochastic: bool = False, carry_reset_rows: bool = True, monte_carlo: bool = False) -> dict:
         """``steps`` consecutive env steps in ONE kernel launch (state stays in registers, finished envs restart
         in place when ``auto_reset``).  Actions come from ``actions`` ([steps, N, 6] float32/float64 on the device) or,
         when it is None, from the device Philox stream ``(action_seed; global env id, step_base + k)`` as U(-1,1) fp64
@@ -159,7 +219,11 @@ class BatchedRendezvousEnv:
         policy's Gaussian head N(pi(obs), exp(log_std)^2) with Philox noise keyed by ``action_seed`` (SB3's
         collect_rollouts: the env gets the clipped draw, ``actions`` records the unclipped one).  Returns a dict with ``obs`` (final observation, f32 [N,17]) and the
         requested per-step records (``rewards`` f64 [steps,N], ``dones`` u8 [steps,N], ``obs_steps`` f32 [steps,N,17],
-        ``actions`` f64 [steps,N,6] for Philox actions).  Asynchronous on the current stream."""
+        ``actions`` f64 [steps,N,6] for Philox actions).  ``carry_reset_rows``: keep every env's prefetched next reset
+        state in a device scratch between launches (short launches then run at the rate of long ones).
+        ``monte_carlo`` (needs ``auto_reset=False``): evaluator mode -- an env stops at its first done and the launch
+        returns ``mc`` f64 [N, MC_NCOL], the per-episode columns of monte_carlo.py:190-203 accumulated on the device.
+        Asynchronous on the current stream."""
         steps = int(steps)
         n, dev = self.num_envs, self.device
         if steps < 0:
@@ -188,6 +252,11 @@ class BatchedRendezvousEnv:
         obs_steps = torch.empty((steps, n, N.OBS_DIM), dtype=torch.float32, device=dev) if record_obs else None
         act_out = torch.empty((steps, n, N.ACT_DIM), dtype=torch.float32 if policy is not None else torch.float64,
                               device=dev) if (record_actions and actions is None) else None
+        mc_out = None
+        if monte_carlo:
+            if self.auto_reset:
+                raise ValueError("monte_carlo mode needs an env with auto_reset=False")
+            mc_out = torch.empty((n, N.MC_NCOL), dtype=torch.float64, device=dev)
         if len(self.groups) > 1 and (rew is not None or don is not None or obs_steps is not None or act_out is not None
                                      or actions is not None):
             raise NotImplementedError("per-step records / tensor actions with param_batches: use step()")
@@ -203,7 +272,9 @@ class BatchedRendezvousEnv:
                     rew.data_ptr() if rew is not None else None, don.data_ptr() if don is not None else None,
                     obs_steps.data_ptr() if obs_steps is not None else None,
                     self.stats.data_ptr() if self.stats is not None else None,
-                    policy._c if policy is not None else N.RdvPolicy())
+                    policy._c if policy is not None else N.RdvPolicy(),
+                    self._reset_rows_ptr(g) if carry_reset_rows else None, int(self.sm_reserve), 0,
+                    mc_out.data_ptr() + g.lo * N.MC_NCOL * 8 if mc_out is not None else None)
                 st = self._state_of(g)
                 N.check(self.lib.rdv_rollout(C.byref(g.params), C.byref(st), C.byref(io), g.n, self.seed,
                                              self.env_offset + g.lo, stream), "rdv_rollout")
@@ -216,6 +287,8 @@ class BatchedRendezvousEnv:
             out["obs_steps"] = obs_steps
         if act_out is not None:
             out["actions"] = act_out
+        if mc_out is not None:
+            out["mc"] = mc_out
         return out
 
     def reset(self, mask: Optional[torch.Tensor] = None, uniforms: Optional[torch.Tensor] = None,
@@ -351,7 +424,7 @@ class BatchedRendezvousEnv:
         self.f64.copy_(sd["f64"])
         self.i32.copy_(sd["i32"])
         self.obs.copy_(sd["obs"])
-        self.seed, self.env_offset = int(sd["seed"]), int(sd["env_offset"])
+        self.seed, self.env_offset = int(sd["seed"]), int(sd["env_offset"])      # the setter forgets the reset rows
         if self.stats is not None and sd.get("stats") is not None:
             self.stats.copy_(sd["stats"])
 
@@ -362,6 +435,10 @@ class BatchedRendezvousEnv:
         other.params = other.groups[0].params
         for name in ("f64", "i32", "obs", "reward", "done", "terminal_obs", "end_reason", "episode_record"):
             setattr(other, name, getattr(self, name).clone())
+        if self.host_block is not None:
+            other.host_block = None
+            other.enable_host_block()
         other.stats = None if self.stats is None else self.stats.clone()
+        other.reset_rows = None if self.reset_rows is None else self.reset_rows.clone()
         other._keepalive = None
         return other

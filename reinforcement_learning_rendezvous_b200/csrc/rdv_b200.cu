@@ -15,6 +15,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <atomic>
 #include "rdv_step.cuh"
 #include "rdv_policy.cuh"
 #include "rdv_policy_tc.cuh"
@@ -114,7 +115,9 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
     __shared__ double s_stats[TPB / 32][RDV_NSTATS];
     __shared__ double s_team[TPB / RDV_TEAM][RDV_TEAM_ROW];   // scratch rows of the reset teams
     __shared__ int s_reset_idx[EPB];                          // envs of this CTA whose episode just ended
-    __shared__ int s_reset_n;
+    __shared__ int s_reset_n, s_fin_base;
+    __shared__ double s_fin_rec[EPB][RDV_EP_NCOL];            // episode records of the finished envs (compacted rows)
+    __shared__ int s_fin_reason[EPB];
     if (threadIdx.x == 0) s_reset_n = 0;
     __syncthreads();
 
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
     st.rk_acc = active ? rk_acc : 0; st.rk_rej = active ? rk_rej : 0; st.fail = active ? fail : 0;
 
     // ---- chaser lane: latch, time, bubble, done, reward, outputs ----
-    int done = 0;
+    int done = 0, fin_pos = 0;
     if (!body) {
         int step = S.i32[RDV_I_STEP * ld + i], success = S.i32[RDV_I_SUCCESS * ld + i];
         int collided = S.i32[RDV_I_COLLIDED * ld + i];
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
         ep_ret += rew;
         if (active) {
             io.reward[i] = rew;
+            if (io.reward_f32) io.reward_f32[i] = (float)rew;
             io.done[i] = (uint8_t)done;
             if (io.end_reason) io.end_reason[i] = (int8_t)reason;
             st.steps = 1; st.reward = rew;
@@ -346,18 +350,45 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
                     rec[RDV_EP_SUCCESS] = (double)success; rec[RDV_EP_COLLIDED] = (double)collided;
                     rec[RDV_EP_DELTA_V] = total_t; rec[RDV_EP_DELTA_W] = total;
                 }
-                if (io.auto_reset) s_reset_idx[atomicAdd(&s_reset_n, 1)] = threadIdx.x >> 1;
+                if (io.auto_reset || io.fin_rows) {
+                    fin_pos = atomicAdd(&s_reset_n, 1);
+                    s_reset_idx[fin_pos] = threadIdx.x >> 1;
+                }
+                if (io.fin_rows) {
+                    double *fr = s_fin_rec[threadIdx.x >> 1];
+                    fr[RDV_EP_RETURN] = ep_ret; fr[RDV_EP_LENGTH] = (double)step;
+                    fr[RDV_EP_SUCCESS] = (double)success; fr[RDV_EP_COLLIDED] = (double)collided;
+                    fr[RDV_EP_DELTA_V] = total_t; fr[RDV_EP_DELTA_W] = total;
+                    s_fin_reason[threadIdx.x >> 1] = reason;
+                }
             }
         }
     }
 
     // ---- terminal observation of finished episodes: the pair copies its staged row ----
     __syncwarp();
+    const int done_pair = __shfl_sync(0xffffffffu, done, (threadIdx.x & 31) & ~1);
     if (io.terminal_obs) {
-        const int done_pair = __shfl_sync(0xffffffffu, done, (threadIdx.x & 31) & ~1);
         if (done_pair && active) {
             float *to = io.terminal_obs + RDV_OBS_DIM * i;
             for (int k = body; k < RDV_OBS_DIM; k += 2) to[k] = o[k];
+        }
+    }
+    // ---- compacted rows of the finished envs (what a VecEnv's infos carry), one global atomic per CTA ----
+    if (io.fin_rows) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_fin_base = s_reset_n ? atomicAdd(io.fin_count, s_reset_n) : 0;
+        __syncthreads();
+        const int pos_pair = __shfl_sync(0xffffffffu, fin_pos, (threadIdx.x & 31) & ~1);
+        const int slot = s_fin_base + pos_pair;
+        if (done_pair && active && slot < io.fin_capacity) {
+            RdvFinishedRow *fr = static_cast<RdvFinishedRow *>(io.fin_rows) + slot;
+            if (!body) {
+                fr->env = io.fin_env_base + (int32_t)i; fr->end_reason = s_fin_reason[threadIdx.x >> 1]; fr->pad = 0.0f;
+#pragma unroll
+                for (int k = 0; k < RDV_EP_NCOL; ++k) fr->record[k] = s_fin_rec[threadIdx.x >> 1][k];
+            }
+            for (int k = body; k < RDV_OBS_DIM; k += 2) fr->terminal_obs[k] = o[k];
         }
     }
 
@@ -419,7 +450,22 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 #define RDV_LOCKSTEP_MAX_TPB 256      /* CTAs up to this size interleave the two attitude solves (rk45_iso_plane_pair) */
 #endif
 constexpr int RDV_NEXT_ROW = 22;          // doubles per prefetched reset row: state[20], collided, success
-template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false>
+constexpr int RDV_ROW_TAG = 22;           // row of RdvRolloutIO.reset_rows holding the episode index a row belongs to
+
+// state of `e` / counters of `c` from a reset row (stride 1 in shared memory, stride ld in the global scratch)
+RDV_DEV void take_reset_row(const double *rw, const int64_t rs, EnvRegs &e, EnvCounters &c)
+{
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { e.rc[j] = rw[(RDV_RCX + j) * rs]; e.vc[j] = rw[(RDV_VCX + j) * rs]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { e.qc[j] = rw[(RDV_QCW + j) * rs]; e.qt[j] = rw[(RDV_QTW + j) * rs]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { e.wc[j] = rw[(RDV_WCX + j) * rs]; e.wt[j] = rw[(RDV_WTX + j) * rs]; }
+    c.collided = (int)rw[20 * rs]; c.success = (int)rw[21 * rs];
+    c.step = 0; c.episode += 1; c.tdv = c.tdw = c.ep_ret = 0.0;
+}
+
+template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false, bool MC = false>
 __global__ void __launch_bounds__(TPB_, 1)
 rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __grid_constant__ RdvRolloutIO io,
                const int64_t n, const uint64_t seed, const int64_t env_offset)
@@ -435,16 +481,24 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int src = io.action_source;
-    // Reset prefetch (variants without the actor, launches of >= 2 refill periods): the reset state of
-    // (env, episode + 1) does not depend on the trajectory, so every lane keeps its NEXT reset row ready in shared
-    // memory.  A finished lane just reads its row; the rows are recomputed for all lanes that used theirs every
-    // `refill` steps, four per pass of the warp's 8-lane teams with every team busy, instead of one pass with
-    // 1.6 of 4 teams busy on 80 % of the steps.  A lane that finishes twice between refills gets its row at once.
-    const int refill = (!POLICY && io.auto_reset && io.reserved > 0 && io.steps >= 2 * io.reserved) ? io.reserved : 0;
+    const int64_t ld = S.ld;
+    // Reset prefetch: the reset state of (env, episode + 1) does not depend on the trajectory, so every lane keeps its
+    // NEXT reset row ready.  A finished lane just reads its row; the rows are recomputed for all lanes that used
+    // theirs every `refill` steps, four per pass of the warp's 8-lane teams with every team busy, instead of one pass
+    // with 1.6 of 4 teams busy on 80 % of the steps.  A lane that finishes twice between refills gets its row at once.
+    // The rows live in shared memory (in the caller's global scratch when the fused actor owns the shared memory);
+    // with io.reset_rows they are loaded at entry and stored at exit, so they survive from launch to launch and a
+    // 16-step launch runs at the rate of a 250-step one.  Without the scratch, launches of < 2 refill periods and the
+    // fused actor reset on demand.
+    const bool persist = io.reset_rows != nullptr && io.auto_reset && !MC;
+    const int refill = (!MC && io.auto_reset && io.reserved > 0 && (persist || (!POLICY && io.steps >= 2 * io.reserved)))
+                           ? io.reserved : 0;
     double *next_rows = reinterpret_cast<double *>(dyn_smem) + (size_t)warp * 32 * RDV_NEXT_ROW;
     // the warp's observation staging row; with the fused actor it borrows the group's activation tile, which is
     // only live between the step barrier and the end of the actor's third layer
     float *obs_stage = POLICY ? ts->al[warp >> 2] + (warp & 3) * (32 * RDV_OBS_DIM) : s_obs[POLICY ? 0 : warp];
+    // the float32 observation is formed every step only when something consumes it
+    const bool want_obs = POLICY || io.obs_steps != nullptr;
     // this CTA's slice [lo, hi) and its passes
     const int64_t lo = n * (int64_t)blockIdx.x / gridDim.x, hi = n * ((int64_t)blockIdx.x + 1) / gridDim.x;
     const int64_t span = hi - lo;
@@ -466,9 +520,58 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
         load_env(S, i, e);
         load_counters(S, i, c);
         float ov[RDV_OBS_DIM];
-        make_obs(e, obs_scale(P), ov);
+        if (want_obs) make_obs(e, obs_scale(P), ov);
         unsigned fresh = 0;                                    // lanes whose next reset row is ready
         int countdown = refill;                                // steps until the next refill of the rows
+        // where this lane's row lives
+        double *my_row = POLICY ? io.reset_rows + i : next_rows + lane * RDV_NEXT_ROW;
+        const int64_t row_stride = POLICY ? ld : 1;
+        if (persist) {
+            const bool ok = active && io.reset_rows[RDV_ROW_TAG * ld + i] == (double)(c.episode + 1);
+            fresh = __ballot_sync(full, ok);
+            if (!POLICY && ok) {
+#pragma unroll
+                for (int j = 0; j < RDV_NEXT_ROW; ++j) my_row[j] = io.reset_rows[j * ld + i];
+            }
+            __syncwarp();
+        }
+        // rows for the lanes of `todo`, four per pass of the warp's teams
+        auto fill_rows = [&](unsigned todo) {
+            while (todo) {
+                const int team = lane >> 3;
+                const unsigned src_bit = __fns(todo, 0, team + 1);            // team-th lane of the set, or ~0u
+                const int src_lane = src_bit < 32 ? (int)src_bit : lane;
+                const int64_t r_env = __shfl_sync(full, env_id, src_lane);
+                const int r_episode = __shfl_sync(full, c.episode, src_lane) + 1;
+                if (POLICY) {
+                    // computed in the team's scratch row, then copied to the env's column of the global scratch
+                    double *tr = s_team[warp][team];
+                    team_reset_core(P, seed, r_env, r_episode, nullptr, tr);
+                    if (src_bit < 32) {
+                        double *dst = io.reset_rows + (r_env - env_offset);
+                        for (int j = lane & 7; j < RDV_NEXT_ROW; j += 8) dst[j * ld] = tr[j];
+                        if ((lane & 7) == 0) dst[RDV_ROW_TAG * ld] = (double)r_episode;
+                    }
+                    __syncwarp();
+                } else {
+                    team_reset_core(P, seed, r_env, r_episode, nullptr,
+                                    src_bit < 32 ? next_rows + src_lane * RDV_NEXT_ROW : s_team[warp][team]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) todo &= todo - 1;                  // drop the four handled lanes
+            }
+        };
+
+        // Monte-Carlo evaluator mode: sample 0 is the state at launch (monte_carlo.py:117-124)
+        McAcc mc;
+        bool alive = true;
+        int mc_reason = -1;
+        if constexpr (MC) {
+            mc_init(mc);
+            EvalDetail d;
+            eval_detail_of_state(P, e, d);
+            mc_sample(P, d, c.collided, mc);
+        }
 
         for (int k = 0; k < io.steps; ++k) {
             // Keep the CTA's warps in the same code region (instruction-cache locality).  With the first, ~60 KB
@@ -513,12 +616,12 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
                 }
 #pragma unroll
                 for (int j = 0; j < RDV_ACT_DIM; ++j) a[j] = ac[j];
-                ingest_action_f32(P, a, c, t);
+                if (!MC || alive) ingest_action_f32(P, a, c, t);
             } else if (src == RDV_ACTIONS_F32) {
                 const float2 *ap = reinterpret_cast<const float2 *>(static_cast<const float *>(io.actions) + 6 * row);
                 const float2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
                 const float a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
-                ingest_action_f32(P, a, c, t);
+                if (!MC || alive) ingest_action_f32(P, a, c, t);
             } else {
                 double a[6];
                 if (src == RDV_ACTIONS_F64) {
@@ -533,17 +636,35 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
                         op[2] = make_double2(a[4], a[5]);
                     }
                 }
-                ingest_action_f64(P, a, c, t);
+                if (!MC || alive) ingest_action_f64(P, a, c, t);
             }
             // ---- step ----
             int rk_acc = 0, rk_rej = 0, fail = 0;
-            env_advance<ISO, CLOSED, (TPB_ <= RDV_LOCKSTEP_MAX_TPB)>(P, e, t, rk_acc, rk_rej, fail);
-            const StepResult r = env_evaluate(P, e, t.fuel, c, ov);
+            StepResult r;
+            if constexpr (MC) {
+                // evaluator mode: an env stops at its first done (its lanes idle from then on)
+                r.rew = 0.0; r.done = 0; r.reason = -1;
+                if (alive) {
+                    env_advance<ISO, CLOSED, (TPB_ <= RDV_LOCKSTEP_MAX_TPB)>(P, e, t, rk_acc, rk_rej, fail);
+                    EvalDetail d;
+                    r = env_evaluate<true, true>(P, e, t.fuel, c, ov, &d);
+                    mc_sample(P, d, c.collided, mc);                          // monte_carlo.py:140-149
+                    mc.total_reward += r.rew;
+                    mc.len += 1;
+                    if (r.done) { alive = false; mc_reason = r.reason; }
+                }
+            } else {
+                env_advance<ISO, CLOSED, (TPB_ <= RDV_LOCKSTEP_MAX_TPB)>(P, e, t, rk_acc, rk_rej, fail);
+                if (want_obs) r = env_evaluate<true>(P, e, t.fuel, c, ov);
+                else r = env_evaluate<false>(P, e, t.fuel, c, ov);
+            }
             const bool done = r.done && active;
             if (active) {
                 if (io.rewards) io.rewards[row] = r.rew;
                 if (io.dones) io.dones[row] = (uint8_t)r.done;
-                st.steps += 1; st.reward += r.rew; st.rk_acc += rk_acc; st.rk_rej += rk_rej; st.fail += fail;
+                if (!MC || r.reason != -1 || alive) {
+                    st.steps += 1; st.reward += r.rew; st.rk_acc += rk_acc; st.rk_rej += rk_rej; st.fail += fail;
+                }
                 if (r.done) {
                     st.episodes += 1; st.succeeded += c.success > 0; st.collided += c.collided;
                     st.end0 += r.reason == 0; st.end1 += r.reason == 1; st.end2 += r.reason == 2;
@@ -552,36 +673,14 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
                 }
             }
             // ---- auto-reset inside the warp ----
-            if (!POLICY && io.auto_reset && refill) {
+            if (!MC && io.auto_reset && refill) {
                 // prefetched rows: compute what is missing right now (rare), consume, refill periodically
                 const unsigned m = __ballot_sync(full, done);
-                // rows for the lanes of `todo`, four per pass
-                auto fill_rows = [&](unsigned todo) {
-                    while (todo) {
-                        const int team = lane >> 3;
-                        const unsigned src_bit = __fns(todo, 0, team + 1);        // team-th lane of the set, or ~0u
-                        const int src_lane = src_bit < 32 ? (int)src_bit : lane;
-                        const int64_t r_env = __shfl_sync(full, env_id, src_lane);
-                        const int r_episode = __shfl_sync(full, c.episode, src_lane) + 1;
-                        team_reset_core(P, seed, r_env, r_episode, nullptr,
-                                        src_bit < 32 ? next_rows + src_lane * RDV_NEXT_ROW : s_team[warp][team]);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) todo &= todo - 1;              // drop the four handled lanes
-                    }
-                };
                 const unsigned need = m & ~fresh;
                 if (need) fill_rows(need);
                 if (done) {
-                    const double *rw = next_rows + lane * RDV_NEXT_ROW;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) { e.rc[j] = rw[RDV_RCX + j]; e.vc[j] = rw[RDV_VCX + j]; }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { e.qc[j] = rw[RDV_QCW + j]; e.qt[j] = rw[RDV_QTW + j]; }
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) { e.wc[j] = rw[RDV_WCX + j]; e.wt[j] = rw[RDV_WTX + j]; }
-                    c.collided = (int)rw[20]; c.success = (int)rw[21];
-                    c.step = 0; c.episode += 1; c.tdv = c.tdw = c.ep_ret = 0.0;
-                    make_obs(e, obs_scale(P), ov);                             // post-reset observation
+                    take_reset_row(my_row, row_stride, e, c);
+                    if (want_obs) make_obs(e, obs_scale(P), ov);               // post-reset observation
                 }
                 fresh = (fresh | need) & ~m;
                 __syncwarp();
@@ -591,7 +690,7 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
                     fill_rows(todo);                  // (serving only full passes of four measured no faster)
                     fresh |= todo;
                 }
-            } else if (io.auto_reset) {
+            } else if (!MC && io.auto_reset) {
                 // four finished lanes per pass, one 8-lane team each
                 unsigned m = __ballot_sync(full, done);
                 while (m) {
@@ -603,16 +702,8 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
                     team_reset_core(P, seed, r_env, r_episode, nullptr, s_team[warp][team]);
                     const int rank = __popc(m & ((1u << lane) - 1));
                     if (((m >> lane) & 1u) && rank < 4) {
-                        const double *rw = s_team[warp][rank];
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) { e.rc[j] = rw[RDV_RCX + j]; e.vc[j] = rw[RDV_VCX + j]; }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { e.qc[j] = rw[RDV_QCW + j]; e.qt[j] = rw[RDV_QTW + j]; }
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) { e.wc[j] = rw[RDV_WCX + j]; e.wt[j] = rw[RDV_WTX + j]; }
-                        c.collided = (int)rw[20]; c.success = (int)rw[21];
-                        c.step = 0; c.episode += 1; c.tdv = c.tdw = c.ep_ret = 0.0;
-                        make_obs(e, obs_scale(P), ov);                         // post-reset observation
+                        take_reset_row(s_team[warp][rank], 1, e, c);
+                        if (want_obs) make_obs(e, obs_scale(P), ov);           // post-reset observation
                     }
                     __syncwarp();
 #pragma unroll
@@ -631,11 +722,36 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
             }
         }
 
+        // ---- the rows that were used since the last refill are recomputed before they go back to the scratch,
+        //      so the next launch starts with every row ready ----
+        if (persist) {
+            const unsigned todo = __ballot_sync(full, active) & ~fresh;
+            fill_rows(todo);
+            if (!POLICY && active) {
+#pragma unroll
+                for (int j = 0; j < RDV_NEXT_ROW; ++j) io.reset_rows[j * ld + i] = my_row[j];
+                io.reset_rows[RDV_ROW_TAG * ld + i] = (double)(c.episode + 1);
+            }
+            __syncwarp();
+        }
         // ---- write the state back once per pass, and the final observation ----
         if (active) {
             store_env(S, i, e);
             store_counters(S, i, c);
+            if constexpr (MC) {
+                double *mo = io.mc_out + (size_t)RDV_MC_NCOL * i;
+                const double inv = 1.0 / (double)(mc.count > 0 ? mc.count : 1);
+                mo[RDV_MC_EP_LEN] = (double)mc.len; mo[RDV_MC_NUM_COLLISIONS] = (double)mc.n_col;
+                mo[RDV_MC_COLLIDED] = mc.n_col > 0 ? 1.0 : 0.0; mo[RDV_MC_TOTAL_REWARD] = mc.total_reward;
+                mo[RDV_MC_TOTAL_DELTA_V] = c.tdv; mo[RDV_MC_NUM_SUCCESSES] = (double)mc.n_suc;
+                mo[RDV_MC_SUCCEEDED] = mc.n_suc > 0 ? 1.0 : 0.0; mo[RDV_MC_MIN_KOZ] = mc.min_koz;
+                mo[RDV_MC_POS_ERR] = mc.sum[0] * inv; mo[RDV_MC_VEL_ERR] = mc.sum[1] * inv;
+                mo[RDV_MC_ATT_ERR] = mc.sum[2] * inv; mo[RDV_MC_ROT_ERR] = mc.sum[3] * inv;
+                mo[RDV_MC_LEVEL] = (double)mc.level; mo[RDV_MC_TAIL_COUNT] = (double)mc.count;
+                mo[RDV_MC_END_REASON] = (double)mc_reason; mo[RDV_MC_TOTAL_DELTA_W] = c.tdw;
+            }
         }
+        if (!want_obs || MC) make_obs(e, obs_scale(P), ov);
         float *o = obs_stage + lane * RDV_OBS_DIM;
 #pragma unroll
         for (int j = 0; j < RDV_OBS_DIM; ++j) o[j] = ov[j];
@@ -831,9 +947,52 @@ static int launch_status()
     return e == cudaSuccess ? RDV_OK : RDV_ERR_CUDA;
 }
 
+// Per-device facts, keyed by the CUDA device ordinal: one process may drive several GPUs, and both the SM count
+// and cudaFuncSetAttribute(MaxDynamicSharedMemorySize) are per device.
+constexpr int RDV_MAX_DEVICES = 64;
+static std::atomic<int> g_sm_count[RDV_MAX_DEVICES];
+static int current_device(int *sm_count)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= RDV_MAX_DEVICES) return -1;
+    int sms = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (sms == 0) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return -1;
+        g_sm_count[dev].store(sms, std::memory_order_relaxed);
+    }
+    *sm_count = sms;
+    return dev;
+}
+// opt a kernel into `bytes` of dynamic shared memory once per device (mask: one bit per device, per kernel)
+template <class K>
+static bool ensure_smem(K kernel, std::atomic<uint64_t> &mask, int dev, size_t bytes)
+{
+    const uint64_t bit = 1ull << dev;
+    if (mask.load(std::memory_order_acquire) & bit) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+    mask.fetch_or(bit, std::memory_order_release);
+    return true;
+}
+
+// development / test knobs: the environment variables are read once, rdv_tune changes them at run time
+static int env_int(const char *name, int fallback)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : fallback;
+}
+static std::atomic<int> g_tune_tpb{env_int("RDV_ROLLOUT_TPB", 0)};
+static std::atomic<int> g_tune_refill{env_int("RDV_RESET_REFILL", 8)};
+
 extern "C" {
 
 int rdv_abi_version(void) { return RDV_ABI_VERSION; }
+
+int rdv_tune(int key, int value)
+{
+    if (key == RDV_TUNE_ROLLOUT_TPB) return g_tune_tpb.exchange(value);
+    if (key == RDV_TUNE_RESET_REFILL) return g_tune_refill.exchange(value);
+    return RDV_ERR_SIZE;
+}
 int rdv_sizeof_params(void) { return (int)sizeof(RdvParams); }
 
 const char *rdv_strerror(int status)
@@ -939,6 +1098,13 @@ int rdv_params_derive(RdvParams *p)
     p->obs_inv_r = 1.0 / (2.0 * p->max_axial_distance);
     p->obs_inv_v = 1.0 / (2.0 * p->max_axial_speed);
     p->obs_inv_w = 1.0 / (2.0 * p->max_wc);
+    {   // high words of hi * (1 - 1e-6): a state entry whose |x| has a smaller high word maps into the Box for sure
+        auto hiword = [](double x) { uint64_t b; memcpy(&b, &x, 8); return (int32_t)((b >> 32) & 0x7fffffffu); };
+        p->box_hi_r = hiword(p->max_axial_distance * (1.0 - 1e-6));
+        p->box_hi_v = hiword(p->max_axial_speed * (1.0 - 1e-6));
+        p->box_hi_w = hiword(p->max_wc * (1.0 - 1e-6));
+        p->reserved1 = 0;
+    }
     {
         const double reach = rd_n + p->max_rd_error, lim = reach > p->koz_radius ? reach : p->koz_radius;
         p->near_sq = lim * lim * (1.0 + 1e-9);
@@ -971,6 +1137,13 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
     const bool iso = p->iso_c && p->iso_t;
     const bool closed = p->integrator == RDV_INTEGRATOR_CLOSED_FORM;
     if (io->auto_reset != 0 && io->auto_reset != 1) return RDV_ERR_SIZE;
+    if (io->fin_rows) {
+        if (!io->fin_count) return RDV_ERR_NULL;
+        if (io->fin_capacity < 0) return RDV_ERR_SIZE;
+        if (((uintptr_t)io->fin_rows & 15) || ((uintptr_t)io->fin_count & 3)) return RDV_ERR_ALIGN;
+        if (!io->fin_append && cudaMemsetAsync(io->fin_count, 0, sizeof(int32_t), st) != cudaSuccess) return RDV_ERR_CUDA;
+    }
+    if ((uintptr_t)io->reward_f32 & 3) return RDV_ERR_ALIGN;
 #define RDV_LAUNCH(ISO_, F64_, CL_) \
     step_kernel<ISO_, F64_, CL_><<<grid, TPB, 0, st>>>(*p, *s, *io, n, seed, env_offset)
     if (closed) { if (io->act_f64) RDV_LAUNCH(true, true, true); else RDV_LAUNCH(true, false, true); }
@@ -1003,59 +1176,45 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     const bool iso = p->iso_c && p->iso_t;
     const bool closed = p->integrator == RDV_INTEGRATOR_CLOSED_FORM;
     // one CTA per SM; the CTA size is the smallest instantiated one that covers a slice in the fewest passes
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) {
-            sm_count = 0;
-            return RDV_ERR_CUDA;
-        }
-    }
-    const int64_t grid = n < sm_count ? n : sm_count;
+    int sm_count = 0;
+    const int dev = current_device(&sm_count);
+    if (dev < 0) return RDV_ERR_CUDA;
+    if (io->sm_reserve < 0 || io->sm_reserve >= sm_count) return RDV_ERR_SIZE;
+    const int64_t sms = sm_count - io->sm_reserve;
+    const int64_t grid = n < sms ? n : sms;
     const int64_t per_cta = (n + grid - 1) / grid;
-    // development / test override of the CTA size: RDV_ROLLOUT_TPB = 256 | 384 | 448 | 512
-    const char *tpb_env = getenv("RDV_ROLLOUT_TPB");
-    const int force_tpb = tpb_env ? atoi(tpb_env) : 0;
+    const bool mc = io->mc_out != nullptr;
+    if (mc && (io->auto_reset || ((uintptr_t)io->mc_out & 7))) return io->auto_reset ? RDV_ERR_UNSUPPORTED : RDV_ERR_ALIGN;
+    if ((uintptr_t)io->reset_rows & 7) return RDV_ERR_ALIGN;
+    // development / test override of the CTA size (rdv_tune): 256 | 384 | 448 | 512; the evaluator mode has one size
+    const int force_tpb = mc ? 256 : g_tune_tpb.load(std::memory_order_relaxed);
     const int64_t max_tpb = force_tpb > 0 ? force_tpb : 512;
     const int64_t passes = (per_cta + max_tpb - 1) / max_tpb;
     const int64_t chunk = force_tpb > 0 ? force_tpb : (per_cta + passes - 1) / passes;
-    // reset prefetch period (steps between refills of the per-lane reset rows; 0 = reset on demand only).
-    // RDV_RESET_REFILL overrides it (development / tests).
+    // reset prefetch period (steps between refills of the per-lane reset rows; 0 = reset on demand only)
     RdvRolloutIO io_k = *io;
-    {
-        const char *rf = getenv("RDV_RESET_REFILL");
-        io_k.reserved = rf ? atoi(rf) : 8;
-        if (io_k.reserved < 0 || io_k.reserved > 64) io_k.reserved = 0;
-    }
-#define RDV_LAUNCH_R(ISO_, CL_, T_)                                                                               \
+    io_k.reserved = g_tune_refill.load(std::memory_order_relaxed);
+    if (io_k.reserved < 0 || io_k.reserved > 64) io_k.reserved = 0;
+#define RDV_LAUNCH_K(KERNEL, T_, SMEM)                                                                            \
     {                                                                                                             \
-        constexpr size_t smem_ = (size_t)(T_ / 32) * 32 * RDV_NEXT_ROW * sizeof(double);                          \
-        static bool attr_done = false;                                                                            \
-        if (!attr_done) {                                                                                         \
-            if (cudaFuncSetAttribute(rollout_kernel<ISO_, CL_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                     (int)smem_) != cudaSuccess) return RDV_ERR_CUDA;                             \
-            attr_done = true;                                                                                     \
-        }                                                                                                         \
-        rollout_kernel<ISO_, CL_, T_><<<(unsigned)grid, T_, smem_, st>>>(*p, *s, io_k, n, seed, env_offset);      \
+        static std::atomic<uint64_t> attr_mask{0};                                                                \
+        if (!ensure_smem(KERNEL, attr_mask, dev, SMEM)) return RDV_ERR_CUDA;                                      \
+        KERNEL<<<(unsigned)grid, T_, SMEM, st>>>(*p, *s, io_k, n, seed, env_offset);                              \
     }
+#define RDV_ROWS_SMEM(T_) ((size_t)(T_ / 32) * 32 * RDV_NEXT_ROW * sizeof(double))
+#define RDV_LAUNCH_R(ISO_, CL_, T_) RDV_LAUNCH_K((rollout_kernel<ISO_, CL_, T_, false, false>), T_, RDV_ROWS_SMEM(T_))
 #define RDV_PICK_R(ISO_, CL_)                                 \
     if (chunk <= 256) RDV_LAUNCH_R(ISO_, CL_, 256)            \
     else if (chunk <= 384) RDV_LAUNCH_R(ISO_, CL_, 384)       \
     else if (chunk <= 448) RDV_LAUNCH_R(ISO_, CL_, 448)       \
     else RDV_LAUNCH_R(ISO_, CL_, 512)
-#define RDV_LAUNCH_P(T_)                                                                                          \
-    {                                                                                                             \
-        static bool attr_done = false;                                                                            \
-        if (!attr_done) {                                                                                         \
-            if (cudaFuncSetAttribute(rollout_kernel<true, false, T_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)sizeof(tc::TileSmem)) != cudaSuccess) return RDV_ERR_CUDA;              \
-            attr_done = true;                                                                                     \
-        }                                                                                                         \
-        rollout_kernel<true, false, T_, true><<<(unsigned)grid, T_, sizeof(tc::TileSmem), st>>>(*p, *s, io_k, n, seed, \
-                                                                                                env_offset);      \
+#define RDV_LAUNCH_P(T_) RDV_LAUNCH_K((rollout_kernel<true, false, T_, true, false>), T_, sizeof(tc::TileSmem))
+    if (mc) {
+        if (!iso || closed) return RDV_ERR_UNSUPPORTED;      // the evaluator mode is built for the reference's env
+        if (policy) RDV_LAUNCH_K((rollout_kernel<true, false, 256, true, true>), 256, sizeof(tc::TileSmem))
+        else RDV_LAUNCH_K((rollout_kernel<true, false, 256, false, true>), 256, RDV_ROWS_SMEM(256))
     }
-    if (policy) {
+    else if (policy) {
         if (!iso || closed) return RDV_ERR_UNSUPPORTED;      // the fused policy is built for the reference's env
         if (chunk <= 256) RDV_LAUNCH_P(256)
         else if (chunk <= 384) RDV_LAUNCH_P(384)
@@ -1068,6 +1227,8 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
 #undef RDV_LAUNCH_P
 #undef RDV_PICK_R
 #undef RDV_LAUNCH_R
+#undef RDV_ROWS_SMEM
+#undef RDV_LAUNCH_K
     return launch_status();
 }
 
@@ -1132,20 +1293,11 @@ int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, in
     if (pi->hidden != tc::H) return RDV_ERR_UNSUPPORTED;
     if (n < 0) return RDV_ERR_SIZE;
     if (n == 0) return RDV_OK;
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) {
-            sm_count = 0;
-            return RDV_ERR_CUDA;
-        }
-        if (cudaFuncSetAttribute(tc::policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(tc::Smem)) != cudaSuccess) {
-            sm_count = 0;
-            return RDV_ERR_CUDA;
-        }
-    }
+    int sm_count = 0;
+    const int dev = current_device(&sm_count);
+    if (dev < 0) return RDV_ERR_CUDA;
+    static std::atomic<uint64_t> attr_mask{0};
+    if (!ensure_smem(tc::policy_tc_kernel, attr_mask, dev, sizeof(tc::Smem))) return RDV_ERR_CUDA;
     const int64_t pairs = ((n + tc::TM - 1) / tc::TM + tc::GROUPS - 1) / tc::GROUPS;
     const unsigned grid = (unsigned)(pairs < sm_count ? pairs : sm_count);
     tc::policy_tc_kernel<<<grid, tc::GROUPS * tc::TM, sizeof(tc::Smem), (cudaStream_t)cuda_stream>>>(*pi, obs, actions, n);
@@ -1159,11 +1311,11 @@ int rdv_policy_forward_ffma(const RdvPolicy *pi, const float *obs, float *action
     if (n < 0) return RDV_ERR_SIZE;
     if (n == 0) return RDV_OK;
     const size_t smem = sizeof(float) * (PH * 17 + PH * PH + 6 * PH + PH + PH + 8 + PH * PTPB);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    int sm_count = 0;
+    const int dev = current_device(&sm_count);
+    if (dev < 0) return RDV_ERR_CUDA;
+    static std::atomic<uint64_t> attr_mask{0};
+    if (!ensure_smem(policy_kernel, attr_mask, dev, smem)) return RDV_ERR_CUDA;
     policy_kernel<<<(unsigned)((n + PTPB - 1) / PTPB), PTPB, smem, (cudaStream_t)cuda_stream>>>(*pi, obs, actions, n);
     return launch_status();
 }

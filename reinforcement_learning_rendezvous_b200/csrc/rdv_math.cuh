@@ -501,10 +501,12 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 // exact arithmetic) at 159 instead of 307 fp64 operations per attempted step.  No division by omega occurs:
 // w = 0 gives p = 0 and a constant quaternion.
 // ---------------------------------------------------------------------------------
-RDV_DEV void rhs_plane(const double a, const double b, const double om2, const double inv_n0, double &ka, double &kb)
+// Slope of y = a q0 + b p in plane coordinates.  The basis is scaled so that |q0| drops out: p = (M / |q0|) q0 and
+// om2 = omega^2 / |q0|^2, hence y' = M y / |y| = (M / |q0|) y / sqrt(a^2 + om2 b^2).
+RDV_DEV void rhs_plane(const double a, const double b, const double om2, double &ka, double &kb)
 {
     const double t = om2 * b;
-    const double g = fast_rsqrt(fma(t, b, a * a)) * inv_n0;       // 1 / |y|
+    const double g = fast_rsqrt(fma(t, b, a * a));                // |q0| / |y|
     ka = -(t * g);
     kb = a * g;
 }
@@ -542,16 +544,16 @@ RDV_DEV double plane_err2_f64(const double ea, const double eb, const double a, 
     }
     return es * (1.0 / 7.0);
 }
-// select_initial_step (scipy common.py:68-134, order 4) from the first slope (0, kb0) at (a, b) = (1, 0)
-RDV_DEV double plane_initial_step(const double (&y)[7], const float (&q0f)[4], const float (&pf)[4], const double kb0,
-                                  const double om2, const double inv_n0, const double dt)
+// select_initial_step (scipy common.py:68-134, order 4).  The first slope at (a, b) = (1, 0) is (0, 1) exactly:
+// f0 = M q0 / |q0| = p.
+RDV_DEV double plane_initial_step(const double (&y)[7], const float (&q0f)[4], const float (&pf)[4], const double om2,
+                                  const double dt)
 {
     float inv_sc[4], d0s = 0.0f, d1s = 0.0f;
-    const float kb0f = (float)kb0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         inv_sc[i] = rcp_f32(fmaf(fabsf(q0f[i]), (float)RK_RTOL, (float)RK_ATOL));
-        const float v = q0f[i] * inv_sc[i], f = kb0f * pf[i] * inv_sc[i];       // y0 / scale, f0 / scale
+        const float v = q0f[i] * inv_sc[i], f = pf[i] * inv_sc[i];               // y0 / scale, f0 / scale
         d0s = fmaf(v, v, d0s);
         d1s = fmaf(f, f, d1s);
     }
@@ -569,17 +571,17 @@ RDV_DEV double plane_initial_step(const double (&y)[7], const float (&q0f)[4], c
     else h0f = 0.01f * sqrtf(d0s * rcp_f32(d1s));
     const double h0 = fmin((double)h0f, dt);
     // d2 = rms((f(y0 + h0 f0) - f0) / scale) / h0 only enters through max(d1, d2).  In plane coordinates
-    // f1 - f0 = da q0 + db p with |da| <= omega^2 h0 kb0^2 and |db| <= omega^2 h0^2 kb0^3 / 2, hence
-    // d2 <= omega^2 kb0^2 (rms(q0 / scale) + h0 d1 / 2): of the order omega d1, i.e. below d1 unless the body
+    // f1 - f0 = da q0 + db p with |da| <= om2 h0 and |db| <= om2 h0^2 / 2, hence
+    // d2 <= om2 (rms(q0 / scale) + h0 d1 / 2): of the order omega d1, i.e. below d1 unless the body
     // spins at ~1 rad/s.  When this bound (with 5 % slack for the float32 arithmetic) is below d1 the second slope
     // is not evaluated at all; otherwise d2 is formed exactly as scipy does.
     const float h0c = (float)h0;
-    const float ub = (float)om2 * kb0f * kb0f * fmaf(0.5f * h0c, sqrtf(d1s), sqrtf(d0q));
+    const float ub = (float)om2 * fmaf(0.5f * h0c, sqrtf(d1s), sqrtf(d0q));
     float dmax = d1s;
     if (!(ub * ub * 1.05f <= d1s)) {
         double ka1, kb1;
-        rhs_plane(1.0, h0 * kb0, om2, inv_n0, ka1, kb1);         // y1 = y0 + h0 f0
-        const float daf = (float)ka1, dbf = (float)(kb1 - kb0);  // f1 - f0 in plane coordinates (ka0 = 0)
+        rhs_plane(1.0, h0, om2, ka1, kb1);                       // y1 = y0 + h0 f0
+        const float daf = (float)ka1, dbf = (float)(kb1 - 1.0);  // f1 - f0 in plane coordinates
         float d2s = 0.0f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -596,94 +598,121 @@ RDV_DEV double plane_initial_step(const double (&y)[7], const float (&q0f)[4], c
     return fmin(fmin(100.0 * h0, (double)h1), dt);
 }
 
+// basis of the invariant plane of one body: q0, p = (0.5 Omega(w) / |q0|) q0 (dynamics.py:137-150), om2 = |0.5 w|^2 / |q0|^2
+RDV_DEV void plane_basis(const double (&y)[7], double (&q0)[4], double (&p)[4], double &om2)
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q0[i] = y[i];
+    const double hs = 0.5 * fast_rsqrt(dot4(q0, q0));
+    const double hw[3] = {hs * y[4], hs * y[5], hs * y[6]};
+    p[0] = -fma(hw[2], q0[3], fma(hw[1], q0[2], hw[0] * q0[1]));
+    p[1] = fma(-hw[1], q0[3], fma(hw[2], q0[2], hw[0] * q0[0]));
+    p[2] = fma(hw[0], q0[3], fma(-hw[2], q0[1], hw[1] * q0[0]));
+    p[3] = fma(-hw[0], q0[2], fma(hw[1], q0[1], hw[2] * q0[0]));
+    om2 = fma(hw[2], hw[2], fma(hw[1], hw[1], hw[0] * hw[0]));
+}
+
+// One point of the solution in plane coordinates, with what the next step needs from it: the slope (FSAL) and the
+// float32 quaternion components the controller's scale vector uses.
+struct PlanePoint { double a, b, ka, kb, t; float yf[4]; };
+
+// One solver.step() of scipy's RungeKutta._step_impl (rk.py:111-179): attempts from `s` until one is accepted; the
+// accepted point goes to `n` (`s` is left untouched, so the caller alternates two points and no copy is made).
+// Returns false on TOO_SMALL_STEP / a non-finite error norm.
+#ifndef RDV_RK_PINGPONG
+#define RDV_RK_PINGPONG 1
+#endif
+RDV_DEV bool plane_step(const PlanePoint &s, PlanePoint &n, double &h_abs, int &n_rejected, const double om2, const double dt,
+                        const double (&q0)[4], const double (&p)[4], const float (&q0f)[4], const float (&pf)[4])
+{
+    const double a = s.a, b = s.b, t = s.t;
+    const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+    if (h_abs < min_step) h_abs = min_step;
+    bool rejected = false;
+    for (;;) {
+        if (h_abs < min_step) return false;
+        double t_new = t + h_abs;
+        if (t_new - dt > 0.0) t_new = dt;
+        const double h = t_new - t;
+        h_abs = fabs(h);
+        // ---- rk_step: six stages, FSAL row ----
+        double ka[7], kb[7], as, bs;
+        ka[0] = s.ka; kb[0] = s.kb;
+        as = fma(ka[0] * RK_A21, h, a);
+        bs = fma(kb[0] * RK_A21, h, b);
+        rhs_plane(as, bs, om2, ka[1], kb[1]);
+        as = fma(fma(ka[1], RK_A32, ka[0] * RK_A31), h, a);
+        bs = fma(fma(kb[1], RK_A32, kb[0] * RK_A31), h, b);
+        rhs_plane(as, bs, om2, ka[2], kb[2]);
+        as = fma(fma(ka[2], RK_A43, fma(ka[1], RK_A42, ka[0] * RK_A41)), h, a);
+        bs = fma(fma(kb[2], RK_A43, fma(kb[1], RK_A42, kb[0] * RK_A41)), h, b);
+        rhs_plane(as, bs, om2, ka[3], kb[3]);
+        as = fma(fma(ka[3], RK_A54, fma(ka[2], RK_A53, fma(ka[1], RK_A52, ka[0] * RK_A51))), h, a);
+        bs = fma(fma(kb[3], RK_A54, fma(kb[2], RK_A53, fma(kb[1], RK_A52, kb[0] * RK_A51))), h, b);
+        rhs_plane(as, bs, om2, ka[4], kb[4]);
+        as = fma(fma(ka[4], RK_A65, fma(ka[3], RK_A64, fma(ka[2], RK_A63, fma(ka[1], RK_A62, ka[0] * RK_A61)))), h, a);
+        bs = fma(fma(kb[4], RK_A65, fma(kb[3], RK_A64, fma(kb[2], RK_A63, fma(kb[1], RK_A62, kb[0] * RK_A61)))), h, b);
+        rhs_plane(as, bs, om2, ka[5], kb[5]);
+        const double a_new = fma(h, fma(ka[5], RK_B6, fma(ka[4], RK_B5, fma(ka[3], RK_B4, fma(ka[2], RK_B3, ka[0] * RK_B1)))), a);
+        const double b_new = fma(h, fma(kb[5], RK_B6, fma(kb[4], RK_B5, fma(kb[3], RK_B4, fma(kb[2], RK_B3, kb[0] * RK_B1)))), b);
+        rhs_plane(a_new, b_new, om2, ka[6], kb[6]);
+        // ---- error estimate (K^T E) h in the plane; the controller's norm in quaternion components ----
+        const double ea = h * fma(ka[6], RK_E7, fma(ka[5], RK_E6, fma(ka[4], RK_E5, fma(ka[3], RK_E4,
+                              fma(ka[2], RK_E3, ka[0] * RK_E1)))));
+        const double eb = h * fma(kb[6], RK_E7, fma(kb[5], RK_E6, fma(kb[4], RK_E5, fma(kb[3], RK_E4,
+                              fma(kb[2], RK_E3, kb[0] * RK_E1)))));
+        const float esf = plane_err2_f32(ea, eb, a_new, b_new, q0f, pf, s.yf, n.yf);
+        if (!(esf < 1.0e30f)) return false;        // NaN / inf: the reference shrinks h to failure
+        bool accept = esf < 1.0f;
+        if (fabsf(esf - 1.0f) < 1.0e-3f)           // threshold region: decide with the fp64 norm
+            accept = plane_err2_f64(ea, eb, a, b, a_new, b_new, q0, p) < 1.0;
+        // 0.9 err^-0.2, clamped where the controller's min / max saturate anyway
+        const float pw = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
+        if (accept) {
+            float factor = fminf(10.0f, pw);
+            if (rejected) factor = fminf(1.0f, factor);
+            h_abs *= (double)factor;
+            n.a = a_new; n.b = b_new; n.ka = ka[6]; n.kb = kb[6]; n.t = t_new;
+            return true;
+        }
+        h_abs *= (double)fmaxf(0.2f, pw);
+        rejected = true;
+        ++n_rejected;
+    }
+}
+
 RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
 {
-    const double hw[3] = {0.5 * y[4], 0.5 * y[5], 0.5 * y[6]};
-    const double q0[4] = {y[0], y[1], y[2], y[3]};
-    // p = M q0 = 0.5 Omega(w) q0 (dynamics.py:137-150)
-    const double p[4] = {-fma(hw[2], q0[3], fma(hw[1], q0[2], hw[0] * q0[1])),
-                         fma(-hw[1], q0[3], fma(hw[2], q0[2], hw[0] * q0[0])),
-                         fma(hw[0], q0[3], fma(-hw[2], q0[1], hw[1] * q0[0])),
-                         fma(-hw[0], q0[2], fma(hw[1], q0[1], hw[2] * q0[0]))};
-    const double om2 = fma(hw[2], hw[2], fma(hw[1], hw[1], hw[0] * hw[0]));
-    const double inv_n0 = fast_rsqrt(dot4(q0, q0));
-    float q0f[4], pf[4], ycf[4];
+    double q0[4], p[4], om2;
+    plane_basis(y, q0, p, om2);
+    float q0f[4], pf[4];
+    PlanePoint X, Y;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { q0f[i] = (float)q0[i]; pf[i] = (float)p[i]; ycf[i] = q0f[i]; }
-    double a = 1.0, b = 0.0;                    // y = a q0 + b p
-    double ka[7], kb[7];                        // slopes in plane coordinates
-    rhs_plane(a, b, om2, inv_n0, ka[0], kb[0]);
-    double h_abs = plane_initial_step(y, q0f, pf, kb[0], om2, inv_n0, dt);
-
-    double t = 0.0;
+    for (int i = 0; i < 4; ++i) { q0f[i] = (float)q0[i]; pf[i] = (float)p[i]; X.yf[i] = q0f[i]; }
+    X.a = 1.0; X.b = 0.0; X.ka = 0.0; X.kb = 1.0; X.t = 0.0;     // y = a q0 + b p; slope there = p
+    double h_abs = plane_initial_step(y, q0f, pf, om2, dt);
     int accepted = 0;
+#if RDV_RK_PINGPONG
+    // two copies of the step that read one point and write the other: the accepted candidate is never copied
     for (;;) {
-        // ---- one solver.step(): _step_impl ----
-        const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
-        if (h_abs < min_step) h_abs = min_step;
-        bool rejected = false;
-        double t_new, h, a_new, b_new;
-        float ynf[4];
-        for (;;) {
-            if (h_abs < min_step) return -1;
-            t_new = t + h_abs;
-            if (t_new - dt > 0.0) t_new = dt;
-            h = t_new - t;
-            h_abs = fabs(h);
-            // ---- rk_step: six stages, FSAL row ----
-            double as, bs;
-            as = fma(ka[0] * RK_A21, h, a);
-            bs = fma(kb[0] * RK_A21, h, b);
-            rhs_plane(as, bs, om2, inv_n0, ka[1], kb[1]);
-            as = fma(fma(ka[1], RK_A32, ka[0] * RK_A31), h, a);
-            bs = fma(fma(kb[1], RK_A32, kb[0] * RK_A31), h, b);
-            rhs_plane(as, bs, om2, inv_n0, ka[2], kb[2]);
-            as = fma(fma(ka[2], RK_A43, fma(ka[1], RK_A42, ka[0] * RK_A41)), h, a);
-            bs = fma(fma(kb[2], RK_A43, fma(kb[1], RK_A42, kb[0] * RK_A41)), h, b);
-            rhs_plane(as, bs, om2, inv_n0, ka[3], kb[3]);
-            as = fma(fma(ka[3], RK_A54, fma(ka[2], RK_A53, fma(ka[1], RK_A52, ka[0] * RK_A51))), h, a);
-            bs = fma(fma(kb[3], RK_A54, fma(kb[2], RK_A53, fma(kb[1], RK_A52, kb[0] * RK_A51))), h, b);
-            rhs_plane(as, bs, om2, inv_n0, ka[4], kb[4]);
-            as = fma(fma(ka[4], RK_A65, fma(ka[3], RK_A64, fma(ka[2], RK_A63, fma(ka[1], RK_A62, ka[0] * RK_A61)))), h, a);
-            bs = fma(fma(kb[4], RK_A65, fma(kb[3], RK_A64, fma(kb[2], RK_A63, fma(kb[1], RK_A62, kb[0] * RK_A61)))), h, b);
-            rhs_plane(as, bs, om2, inv_n0, ka[5], kb[5]);
-            a_new = fma(h, fma(ka[5], RK_B6, fma(ka[4], RK_B5, fma(ka[3], RK_B4, fma(ka[2], RK_B3, ka[0] * RK_B1)))), a);
-            b_new = fma(h, fma(kb[5], RK_B6, fma(kb[4], RK_B5, fma(kb[3], RK_B4, fma(kb[2], RK_B3, kb[0] * RK_B1)))), b);
-            rhs_plane(a_new, b_new, om2, inv_n0, ka[6], kb[6]);
-            // ---- error estimate (K^T E) h in the plane; the controller's norm in quaternion components ----
-            const double ea = h * fma(ka[6], RK_E7, fma(ka[5], RK_E6, fma(ka[4], RK_E5, fma(ka[3], RK_E4,
-                                  fma(ka[2], RK_E3, ka[0] * RK_E1)))));
-            const double eb = h * fma(kb[6], RK_E7, fma(kb[5], RK_E6, fma(kb[4], RK_E5, fma(kb[3], RK_E4,
-                                  fma(kb[2], RK_E3, kb[0] * RK_E1)))));
-            const float esf = plane_err2_f32(ea, eb, a_new, b_new, q0f, pf, ycf, ynf);
-            if (!(esf < 1.0e30f)) return -1;           // NaN / inf: the reference shrinks h to failure
-            bool accept = esf < 1.0f;
-            if (fabsf(esf - 1.0f) < 1.0e-3f)           // threshold region: decide with the fp64 norm
-                accept = plane_err2_f64(ea, eb, a, b, a_new, b_new, q0, p) < 1.0;
-            // 0.9 err^-0.2, clamped where the controller's min / max saturate anyway
-            const float pw = 0.9f * pow_neg_tenth_f32(fminf(fmaxf(esf, 1e-12f), 1e8f));
-            if (accept) {
-                float factor = fminf(10.0f, pw);
-                if (rejected) factor = fminf(1.0f, factor);
-                h_abs *= (double)factor;
-                break;
-            }
-            h_abs *= (double)fmaxf(0.2f, pw);
-            rejected = true;
-            ++n_rejected;
-        }
+        if (!plane_step(X, Y, h_abs, n_rejected, om2, dt, q0, p, q0f, pf)) return -1;
         ++accepted;
-        t = t_new;
-        a = a_new; b = b_new;
-        ka[0] = ka[6]; kb[0] = kb[6];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ycf[i] = ynf[i];
-        if (t - dt >= 0.0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) y[i] = fma(b, p[i], a * q0[i]);
-            return accepted;
-        }
+        if (Y.t - dt >= 0.0) { X.a = Y.a; X.b = Y.b; break; }
+        if (!plane_step(Y, X, h_abs, n_rejected, om2, dt, q0, p, q0f, pf)) return -1;
+        ++accepted;
+        if (X.t - dt >= 0.0) break;
     }
+#else
+    for (;;) {
+        if (!plane_step(X, Y, h_abs, n_rejected, om2, dt, q0, p, q0f, pf)) return -1;
+        ++accepted;
+        X = Y;
+        if (X.t - dt >= 0.0) break;
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fma(X.b, p[i], X.a * q0[i]);
+    return accepted;
 }
 
 // Lock-step form of rk45_iso_plane for TWO bodies in one thread (chaser and target of one env): the control flow of
@@ -694,30 +723,20 @@ RDV_RK_FN int rk45_iso_plane(double (&y)[7], const double dt, int &n_rejected)
 // operation for operation (tests/test_gpu_rollout.py compares the bits).
 RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double dt, int &n_rejected)
 {
-    double q0[2][4], p[2][4], om2[2], inv_n0[2], a[2], b[2], ka0[2], kb0[2], h_abs[2], t[2];
+    double q0[2][4], p[2][4], om2[2], a[2], b[2], ka0[2], kb0[2], h_abs[2], t[2];
     float q0f[2][4], pf[2][4], ycf[2][4];
     int accepted[2] = {0, 0};
     bool done[2] = {false, false}, rejected[2] = {false, false}, failed[2] = {false, false};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { q0[0][i] = ya[i]; q0[1][i] = yb[i]; }
+    plane_basis(ya, q0[0], p[0], om2[0]);
+    plane_basis(yb, q0[1], p[1], om2[1]);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        const double *w = c ? yb + 4 : ya + 4;
-        const double hw[3] = {0.5 * w[0], 0.5 * w[1], 0.5 * w[2]};
-        p[c][0] = -fma(hw[2], q0[c][3], fma(hw[1], q0[c][2], hw[0] * q0[c][1]));
-        p[c][1] = fma(-hw[1], q0[c][3], fma(hw[2], q0[c][2], hw[0] * q0[c][0]));
-        p[c][2] = fma(hw[0], q0[c][3], fma(-hw[2], q0[c][1], hw[1] * q0[c][0]));
-        p[c][3] = fma(-hw[0], q0[c][2], fma(hw[1], q0[c][1], hw[2] * q0[c][0]));
-        om2[c] = fma(hw[2], hw[2], fma(hw[1], hw[1], hw[0] * hw[0]));
-        inv_n0[c] = fast_rsqrt(dot4(q0[c], q0[c]));
-        a[c] = 1.0; b[c] = 0.0;
+        a[c] = 1.0; b[c] = 0.0; ka0[c] = 0.0; kb0[c] = 1.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { q0f[c][i] = (float)q0[c][i]; pf[c][i] = (float)p[c][i]; ycf[c][i] = q0f[c][i]; }
     }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) rhs_plane(a[c], b[c], om2[c], inv_n0[c], ka0[c], kb0[c]);
-    h_abs[0] = plane_initial_step(ya, q0f[0], pf[0], kb0[0], om2[0], inv_n0[0], dt);
-    h_abs[1] = plane_initial_step(yb, q0f[1], pf[1], kb0[1], om2[1], inv_n0[1], dt);
+    h_abs[0] = plane_initial_step(ya, q0f[0], pf[0], om2[0], dt);
+    h_abs[1] = plane_initial_step(yb, q0f[1], pf[1], om2[1], dt);
     t[0] = t[1] = 0.0;
     // ---- attempted steps, both bodies per pass, predicated commit ----
     while (!((done[0] || failed[0]) && (done[1] || failed[1]))) {
@@ -736,7 +755,7 @@ RDV_DEV int rk45_iso_plane_pair(double (&ya)[7], double (&yb)[7], const double d
         }
 #define RDV_PSTAGE(KA, KB, EA, EB)                                                       \
         _Pragma("unroll") for (int c = 0; c < 2; ++c) { as[c] = (EA); bs[c] = (EB); }    \
-        _Pragma("unroll") for (int c = 0; c < 2; ++c) rhs_plane(as[c], bs[c], om2[c], inv_n0[c], KA[c], KB[c]);
+        _Pragma("unroll") for (int c = 0; c < 2; ++c) rhs_plane(as[c], bs[c], om2[c], KA[c], KB[c]);
         RDV_PSTAGE(ka1, kb1, fma(ka0[c] * RK_A21, h[c], a[c]), fma(kb0[c] * RK_A21, h[c], b[c]))
         RDV_PSTAGE(ka2, kb2, fma(fma(ka1[c], RK_A32, ka0[c] * RK_A31), h[c], a[c]),
                    fma(fma(kb1[c], RK_A32, kb0[c] * RK_A31), h[c], b[c]))

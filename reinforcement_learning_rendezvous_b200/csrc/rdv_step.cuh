@@ -102,10 +102,35 @@ RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, i
 
 struct StepResult { double rew; int done, reason; };
 
+// gym 0.21 Box.contains on the float32 observation (rendezvous_env.py:367) WITHOUT forming the observation: a double
+// x rounds to a float in [-1, 1] iff |x| <= 1 + 2^-24.  Fast path on the high words of the raw state: a scaled entry
+// with |x| < hi (1 - 1e-6) maps to |o| < 1 whatever the rounding of normalize_value, and a quaternion component with
+// |q| < 1 is in the box; P.box_hi_* are the high words of those thresholds (rdv_params_derive).  Everything else --
+// a component at exactly +-1, a state near the edge of the box, NaN -- takes the exact path through make_obs.
+RDV_DEV bool obs_in_box_state(const RdvParams &P, const EnvRegs &e)
+{
+    auto hi = [](double x) { return __double2hiint(x) & 0x7fffffff; };
+    const int mr = max(max(hi(e.rc[0]), hi(e.rc[1])), hi(e.rc[2]));
+    const int mv = max(max(hi(e.vc[0]), hi(e.vc[1])), hi(e.vc[2]));
+    const int mw = max(max(hi(e.wc[0]), hi(e.wc[1])), hi(e.wc[2]));
+    const int mq = max(max(max(hi(e.qc[0]), hi(e.qc[1])), max(hi(e.qc[2]), hi(e.qc[3]))),
+                       max(max(hi(e.qt[0]), hi(e.qt[1])), max(hi(e.qt[2]), hi(e.qt[3]))));
+    if (mr < P.box_hi_r && mv < P.box_hi_v && mw < P.box_hi_w && mq < 0x3FF00000) return true;
+    float ov[RDV_OBS_DIM];
+    make_obs(e, obs_scale(P), ov);
+    return obs_in_box(ov);
+}
+
+// What an evaluator reads after a step (monte_carlo.py:140-152): get_errors, check_collision, dist_from_koz.
+struct EvalDetail { double err[4]; double koz; bool col_now, within; };
+
 // Everything after the propagation: collision / success latch (:186-190), time and bubble (:193-198),
 // observation (:205), done + end reason (:355-386), reward (:313-353).  Updates the counters.
+// WANT_OBS: form the float32 observation (the policy's input, a per-step record); otherwise only its Box test.
+// DETAIL: also return the evaluator quantities -- this disables the far-from-the-target shortcut below.
+template <bool WANT_OBS = true, bool DETAIL = false>
 RDV_DEV StepResult env_evaluate(const RdvParams &P, const EnvRegs &e, const double fuel, EnvCounters &c,
-                                float (&ov)[RDV_OBS_DIM])
+                                float (&ov)[RDV_OBS_DIM], EvalDetail *detail = nullptr)
 {
     const Rot Rc = rot_from_quat(e.qc);
     const double rc_sq = dot3(e.rc, e.rc);
@@ -117,10 +142,22 @@ RDV_DEV StepResult env_evaluate(const RdvParams &P, const EnvRegs &e, const doub
     bool col_now = false;
     ErrSq es;
     es.pos = es.vel = es.rot = 1.0e300;
-    if (rc_sq < P.near_sq) {
+    if (DETAIL || rc_sq < P.near_sq) {
         const Rot Rt = rot_from_quat(e.qt);
-        col_now = rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle;
-        es = errors_sq(P, e, Rc, Rt);
+        if (DETAIL) {
+            // the evaluator's own forms (errors_kernel): IEEE square roots, the corridor angle at any distance
+            const double rc_n = sqrt(rc_sq), th = corridor_angle(P, e, Rt, rc_sq);
+            col_now = rc_n < P.koz_radius && th > P.corridor_half_angle;
+            es = errors_sq(P, e, Rc, Rt);
+            detail->err[0] = sqrt(es.pos); detail->err[1] = sqrt(es.vel); detail->err[2] = att; detail->err[3] = sqrt(es.rot);
+            detail->koz = koz_distance(P, rc_n, th);
+            detail->col_now = col_now;
+            detail->within = detail->err[0] <= P.max_rd_error && detail->err[1] <= P.max_vd_error &&
+                             att <= P.max_qd_error && detail->err[3] <= P.max_wd_error;
+        } else {
+            col_now = rc_sq < P.koz_radius_sq && corridor_angle(P, e, Rt, rc_sq) > P.corridor_half_angle;
+            es = errors_sq(P, e, Rc, Rt);
+        }
     }
     if (!c.collided) {
         c.collided = col_now ? 1 : 0;
@@ -130,8 +167,14 @@ RDV_DEV StepResult env_evaluate(const RdvParams &P, const EnvRegs &e, const doub
     }
     c.step += 1;
     const double bubble = fmax(fma(-(double)c.step, P.bubble_rate, P.bubble0), P.bubble_min);
-    make_obs(e, obs_scale(P), ov);
-    const bool c0 = !obs_in_box(ov), c1 = c.step >= P.done_steps, c2 = rc_sq > bubble * bubble,
+    bool in_box;
+    if (WANT_OBS) {
+        make_obs(e, obs_scale(P), ov);
+        in_box = obs_in_box(ov);
+    } else {
+        in_box = obs_in_box_state(P, e);
+    }
+    const bool c0 = !in_box, c1 = c.step >= P.done_steps, c2 = rc_sq > bubble * bubble,
                c3 = att > P.max_attitude_error;
     StepResult r;
     r.done = (c0 || c1 || c2 || c3) ? 1 : 0;
@@ -146,6 +189,54 @@ RDV_DEV StepResult env_evaluate(const RdvParams &P, const EnvRegs &e, const doub
     r.rew = rew;
     c.ep_ret += rew;
     return r;
+}
+
+// Per-episode accumulators of monte_carlo.evaluate (monte_carlo.py:94-207), one sample per visited state.
+// Terminal errors (:159-189): the constraint sets are nested (all four < limits  =>  pos, vel and att-or-rot  =>
+// pos and vel  =>  pos), so "mean of the errors from the first index at which the most constraints are met" needs
+// ONE running sum: restart it whenever a sample reaches a better level than any before, keep adding otherwise;
+// with no level reached at all it holds the last sample only (index = -1).
+struct McAcc {
+    double sum[4], min_koz, total_reward;
+    int count, level, n_col, n_suc, len;
+};
+RDV_DEV void mc_init(McAcc &m)
+{
+    m.sum[0] = m.sum[1] = m.sum[2] = m.sum[3] = 0.0;
+    m.min_koz = 1.0e300; m.total_reward = 0.0;
+    m.count = 0; m.level = 4; m.n_col = m.n_suc = m.len = 0;
+}
+RDV_DEV void mc_sample(const RdvParams &P, const EvalDetail &d, const int sticky_collided, McAcc &m)
+{
+    m.n_col += d.col_now ? 1 : 0;                                         // :121, :143
+    if (!sticky_collided) m.n_suc += d.within ? 1 : 0;                    // :122-123, :144-145
+    if (d.koz < m.min_koz) m.min_koz = d.koz;                             // :124, :146-148
+    const bool pm = d.err[0] < P.max_rd_error, vm = d.err[1] < P.max_vd_error, am = d.err[2] < P.max_qd_error,
+               rm = d.err[3] < P.max_wd_error;                            // strict, :166-169
+    const int level = !pm ? 4 : !vm ? 3 : !(am || rm) ? 2 : !(am && rm) ? 1 : 0;
+    if (level < m.level || m.level == 4) {
+        m.level = level;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m.sum[j] = d.err[j];
+        m.count = 1;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m.sum[j] += d.err[j];
+        m.count += 1;
+    }
+}
+// the evaluator quantities of the CURRENT state without a step (sample 0, monte_carlo.py:117-124)
+RDV_DEV void eval_detail_of_state(const RdvParams &P, const EnvRegs &e, EvalDetail &d)
+{
+    const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
+    const double rc_sq = dot3(e.rc, e.rc), rc_n = sqrt(rc_sq);
+    const double att = attitude_error(P, e, Rc, rc_sq), th = corridor_angle(P, e, Rt, rc_sq);
+    const ErrSq es = errors_sq(P, e, Rc, Rt);
+    d.err[0] = sqrt(es.pos); d.err[1] = sqrt(es.vel); d.err[2] = att; d.err[3] = sqrt(es.rot);
+    d.koz = koz_distance(P, rc_n, th);
+    d.col_now = rc_n < P.koz_radius && th > P.corridor_half_angle;
+    d.within = d.err[0] <= P.max_rd_error && d.err[1] <= P.max_vd_error && att <= P.max_qd_error &&
+               d.err[3] <= P.max_wd_error;
 }
 
 RDV_DEV void load_counters(const RdvState &S, int64_t i, EnvCounters &c)
@@ -163,20 +254,24 @@ RDV_DEV void store_counters(const RdvState &S, int64_t i, const EnvCounters &c)
     S.i32[RDV_I_COLLIDED * ld + i] = c.collided; S.i32[RDV_I_EPISODE * ld + i] = c.episode;
 }
 
-// U(-1,1) actions from the Philox stream (action_seed; env id, step index): blocks 0x40000000 | {0,1,2} of the
-// counter space, disjoint from the reset() draws (blocks 0..11 keyed by the episode index).
+// U(-1,1) fp64 actions from the Philox stream (action_seed; env id, step index): blocks 0x40000000 | {0,1} of the
+// counter space, disjoint from the reset() draws (blocks 0..11 keyed by the episode index).  Six of the eight 32-bit
+// words of the two blocks become a_j = (w_j + 0.5) 2^-31 - 1: uniform on a symmetric 2^-31 grid inside (-1, 1) --
+// finer than the float32 actions gym's Box.sample() or an SB3 policy produce -- at two Philox blocks, six
+// conversions and six DFMA per env-step (the 53-bit form took three blocks and 42 instructions for the conversions).
 RDV_DEV void philox_actions(uint64_t action_seed, int64_t env_id, int64_t step_index, double (&a)[6])
 {
+    uint32_t w[8];
 #pragma unroll
-    for (uint32_t blk = 0; blk < 3; ++blk) {
+    for (uint32_t blk = 0; blk < 2; ++blk) {
         uint32_t c[4] = {(uint32_t)env_id, (uint32_t)((uint64_t)env_id >> 32), (uint32_t)step_index,
                          0x40000000u | blk | (((uint32_t)((uint64_t)step_index >> 32) & 0x00FFFFFFu) << 4)};
         philox4x32_10(c, (uint32_t)action_seed, (uint32_t)(action_seed >> 32));
-        const double u0 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6)) * (1.0 / 9007199254740992.0);
-        const double u1 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) * (1.0 / 9007199254740992.0);
-        a[2 * blk] = fma(2.0, u0, -1.0);
-        a[2 * blk + 1] = fma(2.0, u1, -1.0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[4 * blk + j] = c[j];
     }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a[j] = fma((double)w[j], 4.656612873077392578125e-10, -1.0 + 2.3283064365386962890625e-10);
 }
 
 }  // namespace rdv

@@ -9,15 +9,24 @@ utils/general.py:55-56) with N environments stepped by one kernel launch.  Contr
   ``infos[i]["terminal_observation"]`` holds the episode's last observation
 * ``infos[i]["episode"] = {"r": return, "l": length, "t": wall seconds}`` for finished envs (Monitor)
 * no ``TimeLimit.truncated`` key is ever set (the reference treats time-outs as terminations)
+* the returned arrays are never overwritten by a later step (``DummyVecEnv`` hands out copies; SB3's
+  ``collect_rollouts`` keeps ``_last_obs`` / ``_last_episode_starts`` across the next ``env.step``)
 
-Host side per step: one H2D copy of the actions from pinned memory, one kernel launch (step + fused
-auto-reset), D2H copies of obs/reward/done/terminal_obs/episode_record into pinned buffers, one stream
-synchronise, then one small dict per FINISHED env (all other entries share one empty dict).  The returned arrays are views of those pinned buffers and are
-overwritten by the next ``step_wait``; SB3 copies them into its rollout buffer immediately.
+Host side per step: ONE host-to-device copy of the actions from pinned memory, ONE kernel launch (step +
+fused auto-reset; it writes float32 rewards and appends the finished envs' rows -- index, end reason, terminal
+observation, episode record -- through one atomic counter), ONE device-to-host copy of a contiguous block
+``[count | rewards | dones | obs | finished rows]`` into a pinned host block, ONE stream synchronise, then one
+small dict per FINISHED env.  No torch kernel runs on the step path.
+
+Zero-copy without aliasing: the pinned host blocks come from a small pool, and a block is reused only when
+no numpy view of it is alive any more (``sys.getrefcount`` of the block's base array), so the arrays a step
+returns stay valid for as long as the caller keeps them -- exactly like copies -- at the cost of none.  A
+caller that hoards arrays beyond the pool's capacity gets real copies from then on.
 """
 from __future__ import annotations
 
 import gc
+import sys
 import time
 from typing import Any, List, Optional, Sequence
 
@@ -32,6 +41,11 @@ try:                                                   # pragma: no cover - SB3 
     from stable_baselines3.common.vec_env import VecEnv as _SB3VecEnv
 except Exception:                                      # noqa: BLE001
     _SB3VecEnv = None
+
+# numpy mirror of RdvFinishedRow (include/rdv_b200.h), 128 bytes
+FINISHED_ROW = np.dtype([("env", "<i4"), ("end_reason", "<i4"), ("terminal_obs", "<f4", (N.OBS_DIM,)), ("pad", "<f4"),
+                         ("record", "<f8", (N.EP_NCOL,))])
+assert FINISHED_ROW.itemsize == 128
 
 
 class _VecEnvBase:
@@ -60,7 +74,40 @@ class _VecEnvBase:
 
 
 _Base = _SB3VecEnv if _SB3VecEnv is not None else _VecEnvBase
-_EMPTY_INFO: dict = {}
+
+
+class _PinnedBlockPool:
+    """Pinned host blocks of ``nbytes``; ``acquire`` returns one no live numpy view refers to."""
+
+    def __init__(self, nbytes: int, initial: int = 3, capacity: int = 8):
+        self.nbytes, self.capacity = int(nbytes), int(capacity)
+        self._tensors: List[torch.Tensor] = []
+        self._arrays: List[np.ndarray] = []
+        for _ in range(initial):
+            self._grow()
+        self._next = 0
+
+    def _grow(self):
+        t = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()     # zeros: every page is touched here
+        self._tensors.append(t)
+        self._arrays.append(t.numpy())
+
+    def acquire(self):
+        """(tensor, base array, shared) -- ``shared`` is True when every block is still referenced by the caller
+        and the pool is at capacity: the block returned then is a scratch whose views must be copied."""
+        k = len(self._arrays)
+        for j in range(k):
+            i = (self._next + j) % k
+            if sys.getrefcount(self._arrays[i]) == 2:          # the list's reference + getrefcount's argument
+                self._next = (i + 1) % k
+                return self._tensors[i], self._arrays[i], False
+        if k < self.capacity:
+            self._grow()
+            self._next = 0
+            return self._tensors[k], self._arrays[k], False
+        if not hasattr(self, "_scratch"):
+            self._scratch = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
+        return self._scratch, self._scratch.numpy(), True
 
 
 class RendezvousVecEnv(_Base):
@@ -70,77 +117,97 @@ class RendezvousVecEnv(_Base):
                                         **ctor_kwargs)
         _Base.__init__(self, num_envs, observation_space(), action_space())
         n = num_envs
+        # True: obs / rewards / dones are np.copy'd out of the pinned block (plain pageable arrays).  False
+        # (default): views of a pinned block that is not reused while any view of it is alive -- equally safe.
         self.copy_outputs = copy_outputs
         # False: infos carry only the keys SB3 reads (terminal_observation, episode); True adds is_success,
         # collided, total_delta_v, total_delta_w, end_reason (about 1 us of host time more per finished env)
         self.rich_infos = rich_infos
+        self.layout = self.env.enable_host_block()
+        self._pool = _PinnedBlockPool(self.layout["total"])
         self._h_act32 = torch.zeros((n, N.ACT_DIM), dtype=torch.float32).pin_memory()
         self._h_act64 = torch.zeros((n, N.ACT_DIM), dtype=torch.float64).pin_memory()
+        self._a_act32, self._a_act64 = self._h_act32.numpy(), self._h_act64.numpy()
         self._d_act32 = torch.zeros((n, N.ACT_DIM), dtype=torch.float32, device=self.env.device)
         self._d_act64 = torch.zeros((n, N.ACT_DIM), dtype=torch.float64, device=self.env.device)
-        self._d_rew32 = torch.zeros(n, dtype=torch.float32, device=self.env.device)
-        self._h_obs = torch.zeros((n, N.OBS_DIM), dtype=torch.float32).pin_memory()
-        self._h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
-        self._h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
-        self._h_term = torch.zeros((n, N.OBS_DIM), dtype=torch.float32).pin_memory()
-        self._h_rec = torch.zeros((n, N.EP_NCOL), dtype=torch.float64).pin_memory()
-        self._h_reason = torch.zeros(n, dtype=torch.int8).pin_memory()
-        self._h_idx = torch.zeros(n, dtype=torch.int64).pin_memory()
         self._pending = None
         self._t_start = time.time()
+        # one independent dict per env (DummyVecEnv semantics); finished envs get a fresh one per episode end
+        self._infos: List[dict] = [{} for _ in range(n)]
+        self._dirty: List[int] = []                     # envs whose slot holds last step's episode-end dict
+        self._rows_guess = max(64, n // 8)              # finished rows fetched with the fixed part of the block
         self.h2d_bytes_per_step = n * N.ACT_DIM * 4
-        # device -> host per step: obs, reward, done for every env, plus the compacted rows of the finished ones
-        self._d2h_fixed = n * (N.OBS_DIM * 4 + 4 + 1)
-        self._d2h_row = N.OBS_DIM * 4 + N.EP_NCOL * 8 + 1 + 8
-        self.d2h_bytes_per_step = self._d2h_fixed          # + _d2h_row per finished env; see d2h_bytes_last_step
+        # device -> host per step: count, obs, reward, done of every env, plus the rows of the finished ones
+        self._d2h_fixed = self.layout["rows"]
+        self._d2h_row = self.layout["row_bytes"]
+        self.d2h_bytes_per_step = self._d2h_fixed          # + _d2h_row per fetched row; see d2h_bytes_last_step
         self.d2h_bytes_last_step = self._d2h_fixed
         self.d2h_bytes_total = 0
+        self.extra_fetches = 0                             # steps that needed a second copy for their finished rows
+        gc.freeze()                                        # the long-lived objects above never need another GC walk
 
     # ------------------------------------------------------------------ VecEnv API
+    def _views(self, base: np.ndarray, shared: bool):
+        n, L = self.num_envs, self.layout
+        obs = base[L["obs"]:L["obs"] + 4 * N.OBS_DIM * n].view(np.float32).reshape(n, N.OBS_DIM)
+        rew = base[L["reward"]:L["reward"] + 4 * n].view(np.float32)
+        done = base[L["done"]:L["done"] + n].view(np.bool_)
+        if shared or self.copy_outputs:
+            return obs.copy(), rew.copy(), done.copy()
+        return obs, rew, done
+
     def reset(self):
-        self.env.reset()
-        self._h_obs.copy_(self.env.obs, non_blocking=True)
-        torch.cuda.current_stream(self.env.device).synchronize()
-        obs = self._h_obs.numpy()
-        return obs.copy() if self.copy_outputs else obs
+        env = self.env
+        env.reset()
+        t, base, shared = self._pool.acquire()
+        lo, hi = self.layout["obs"], self.layout["rows"]
+        t[lo:hi].copy_(env.host_block[lo:hi], non_blocking=True)
+        torch.cuda.current_stream(env.device).synchronize()
+        return self._views(base, shared)[0]
 
     def step_async(self, actions):
         a = np.asarray(actions)
         if a.shape != (self.num_envs, N.ACT_DIM):
             raise ValueError(f"actions must have shape ({self.num_envs}, {N.ACT_DIM})")
         if a.dtype == np.float64:
-            self._h_act64.numpy()[...] = a
+            self._a_act64[...] = a
             self._d_act64.copy_(self._h_act64, non_blocking=True)
             self._pending = self._d_act64
         else:
-            self._h_act32.numpy()[...] = a          # float32 (what SB3 policies emit); other dtypes are cast
+            self._a_act32[...] = a                  # float32 (what SB3 policies emit); other dtypes are cast
             self._d_act32.copy_(self._h_act32, non_blocking=True)
             self._pending = self._d_act32
 
     def _launch_and_fetch(self):
+        """One launch, one device-to-host copy, one synchronise.  Returns (obs, rew, done, rows) with ``rows`` the
+        finished envs' records (structured array, ascending env index, own memory)."""
         if self._pending is None:
             raise RuntimeError("step_wait() called without step_async()")
-        env = self.env
+        env, L = self.env, self.layout
         env.step(self._pending)
         self._pending = None
-        self._d_rew32.copy_(env.reward)
-        self._h_obs.copy_(env.obs, non_blocking=True)
-        self._h_rew.copy_(self._d_rew32, non_blocking=True)
-        self._h_done.copy_(env.done, non_blocking=True)
-        # finished envs: compact their rows on the device (ascending env index) and copy only those
-        idx_d = torch.nonzero(env.done).squeeze(1)
-        m = int(idx_d.numel())
-        if m:
-            self._h_idx[:m].copy_(idx_d, non_blocking=True)
-            self._h_term[:m].copy_(env.terminal_obs.index_select(0, idx_d), non_blocking=True)
-            self._h_rec[:m].copy_(env.episode_record.index_select(0, idx_d), non_blocking=True)
-            self._h_reason[:m].copy_(env.end_reason.index_select(0, idx_d), non_blocking=True)
-        torch.cuda.current_stream(env.device).synchronize()
-        self.d2h_bytes_last_step = self._d2h_fixed + m * self._d2h_row
+        t, base, shared = self._pool.acquire()
+        guess = self._rows_guess
+        nbytes = L["rows"] + self._d2h_row * guess
+        stream = torch.cuda.current_stream(env.device)
+        t[:nbytes].copy_(env.host_block[:nbytes], non_blocking=True)
+        stream.synchronize()
+        m = int(base[0:4].view(np.int32)[0])
+        fetched = guess
+        if m > guess:                                   # rare: more episodes ended than the running bound allowed for
+            lo, hi = nbytes, L["rows"] + self._d2h_row * m
+            t[lo:hi].copy_(env.host_block[lo:hi], non_blocking=True)
+            stream.synchronize()
+            fetched = m
+            self.extra_fetches += 1
+        # running bound for the next step: 25 % + 4 sigma (binomial) above what this step saw
+        self._rows_guess = min(self.num_envs, int(1.25 * m + 4.0 * (m ** 0.5)) + 32)
+        self.d2h_bytes_last_step = self._d2h_fixed + fetched * self._d2h_row
         self.d2h_bytes_total += self.d2h_bytes_last_step
-        obs, rew = self._h_obs.numpy(), self._h_rew.numpy()
-        done = self._h_done.numpy().view(np.bool_)
-        return obs, rew, done, self._h_idx.numpy()[:m].copy()
+        obs, rew, done = self._views(base, shared)
+        rows = base[L["rows"]:L["rows"] + self._d2h_row * m].view(FINISHED_ROW)
+        rows = rows[np.argsort(rows["env"], kind="stable")] if m else rows.copy()    # sorted gather = own memory
+        return obs, rew, done, rows
 
     def step_arrays(self, actions):
         """``step`` without per-env Python objects: returns ``(obs, rewards, dones, finished)`` where ``finished`` is
@@ -148,62 +215,64 @@ class RendezvousVecEnv(_Base):
         ``episode_return``, ``episode_length``, ``is_success``, ``collided``, ``total_delta_v``, ``total_delta_w``,
         ``end_reason`` (0 obs, 1 time, 2 bubble, 3 attitude).  Same data as the ``infos`` of ``step``."""
         self.step_async(actions)
-        obs, rew, done, idx = self._launch_and_fetch()
-        m = idx.size
-        rec = self._h_rec.numpy()[:m].copy()
+        obs, rew, done, rows = self._launch_and_fetch()
+        rec = rows["record"]
         finished = {
-            "index": idx, "terminal_observation": self._h_term.numpy()[:m].copy(),
+            "index": rows["env"].astype(np.int64), "terminal_observation": rows["terminal_obs"],
             "episode_return": rec[:, N.EP_RETURN], "episode_length": rec[:, N.EP_LENGTH].astype(np.int64),
             "is_success": rec[:, N.EP_SUCCESS] > 0, "collided": rec[:, N.EP_COLLIDED] > 0,
             "total_delta_v": rec[:, N.EP_DELTA_V], "total_delta_w": rec[:, N.EP_DELTA_W],
-            "end_reason": self._h_reason.numpy()[:m].copy(),
+            "end_reason": rows["end_reason"].astype(np.int8),
         }
-        if self.copy_outputs:
-            return obs.copy(), rew.copy(), done.copy(), finished
         return obs, rew, done, finished
 
     def step_wait(self):
-        obs, rew, done, idx = self._launch_and_fetch()
+        obs, rew, done, rows = self._launch_and_fetch()
         # The cyclic garbage collector is paused while the per-env objects are created: a step at 65,536 envs
-        # allocates a 65,536-slot list and ~6,500 small dicts, none of them cyclic, and the generation-0 passes
-        # they trigger (each one walking the new list) cost more than building them (3.9 -> 1.6 ms per step).
+        # allocates ~6,500 small dicts, none of them cyclic, and the generation-0 passes they trigger cost more
+        # than building them.
         paused = gc.isenabled()
         if paused:
             gc.disable()
         try:
-            infos = self._build_infos(idx)
+            infos = self._build_infos(rows)
         finally:
             if paused:
                 gc.enable()
-        if self.copy_outputs:
-            return obs.copy(), rew.copy(), done.copy(), infos
         return obs, rew, done, infos
 
-    def _build_infos(self, idx) -> List[dict]:
-        infos: List[dict] = [_EMPTY_INFO] * self.num_envs
-        if idx.size:
-            # bulk numpy work first, then one small dict per finished env, built by comprehensions over zipped
-            # columns (row views of ONE gathered array) -- about half the cost of an indexed Python loop
-            m = idx.size
-            rec = self._h_rec.numpy()[:m]                          # rows of the finished envs, compacted on the device
-            term = list(self._h_term.numpy()[:m].copy())           # one copy; a list of row views of it
+    def _build_infos(self, rows) -> List[dict]:
+        infos = self._infos
+        for i in self._dirty:                              # last step's episode-end dicts make way for fresh ones
+            infos[i] = {}
+        m = rows.shape[0]
+        if m:
+            # bulk numpy work first, then one small dict per finished env, built by ONE comprehension over zipped
+            # columns (row views of the gathered array)
+            rec = rows["record"]
+            term = list(rows["terminal_obs"])
             elapsed = round(time.time() - self._t_start, 6)
             rets = np.round(rec[:, N.EP_RETURN], 6).tolist()
             lens = rec[:, N.EP_LENGTH].astype(np.int64).tolist()
-            episodes = [{"r": r, "l": l, "t": elapsed} for r, l in zip(rets, lens)]
             if self.rich_infos:
-                reason = [N.END_REASONS[j] for j in self._h_reason.numpy()[:m].tolist()]
+                reason = [N.END_REASONS[j] for j in rows["end_reason"].tolist()]
                 succ = (rec[:, N.EP_SUCCESS] > 0).tolist()
                 coll = (rec[:, N.EP_COLLIDED] > 0).tolist()
                 dv, dw = rec[:, N.EP_DELTA_V].tolist(), rec[:, N.EP_DELTA_W].tolist()
-                new = [{"terminal_observation": t, "episode": e, "is_success": s, "collided": c, "total_delta_v": v,
-                        "total_delta_w": w, "end_reason": r}
-                       for t, e, s, c, v, w, r in zip(term, episodes, succ, coll, dv, dw, reason)]
+                new = [{"terminal_observation": t, "episode": {"r": r, "l": l, "t": elapsed}, "is_success": s,
+                        "collided": c, "total_delta_v": v, "total_delta_w": w, "end_reason": q}
+                       for t, r, l, s, c, v, w, q in zip(term, rets, lens, succ, coll, dv, dw, reason)]
             else:
-                new = [{"terminal_observation": t, "episode": e} for t, e in zip(term, episodes)]
-            for i, d in zip(idx.tolist(), new):
+                new = [{"terminal_observation": t, "episode": {"r": r, "l": l, "t": elapsed}}
+                       for t, r, l in zip(term, rets, lens)]
+            idx = rows["env"].tolist()
+            for i, d in zip(idx, new):
                 infos[i] = d
-        return infos
+            self._dirty = idx
+        else:
+            self._dirty = []
+        # a new list object per step (DummyVecEnv returns a fresh list); the dicts of running envs are each env's own
+        return list(infos)
 
     def close(self):
         return None

@@ -152,50 +152,108 @@ def test_rollout_shard_invariance_and_edges():
     assert (a.episode_index == 1).all()
 
 
-def test_rollout_launch_shapes_are_bit_identical(monkeypatch):
+def _tune(key, value):
+    from reinforcement_learning_rendezvous_b200 import _native as N
+    return N.lib().rdv_tune(key, int(value))
+
+
+def test_rollout_launch_shapes_are_bit_identical():
     """The lock-step (<= 256 envs per CTA) and the sequential (larger CTAs) solvers, and every CTA size, give the
     same bits: results cannot depend on the batch size or on how a batch is sharded over GPUs."""
     import torch
     from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
     n, K = 3000, 40
     states, obs, stats = [], [], []
-    for tpb in ("256", "384", "448", "512"):
-        monkeypatch.setenv("RDV_ROLLOUT_TPB", tpb)
-        env = BatchedRendezvousEnv(n, seed=2, t_max=25)
-        env.reset()
-        out = env.rollout(K, action_seed=7, record_rewards=True)
-        states.append(env.get_state().clone()); obs.append(out["rewards"].clone()); stats.append(env.read_stats())
-    monkeypatch.delenv("RDV_ROLLOUT_TPB")
+    from reinforcement_learning_rendezvous_b200 import _native as N
+    try:
+        for tpb in (256, 384, 448, 512):
+            _tune(N.TUNE_ROLLOUT_TPB, tpb)
+            env = BatchedRendezvousEnv(n, seed=2, t_max=25)
+            env.reset()
+            out = env.rollout(K, action_seed=7, record_rewards=True)
+            states.append(env.get_state().clone()); obs.append(out["rewards"].clone()); stats.append(env.read_stats())
+    finally:
+        _tune(N.TUNE_ROLLOUT_TPB, 0)
     for k in range(1, 4):
         assert torch.equal(states[0], states[k]) and torch.equal(obs[0], obs[k])
         assert stats[0]["rk_accepted"] == stats[k]["rk_accepted"] and stats[0]["episodes"] == stats[k]["episodes"]
 
 
-def test_reset_prefetch_is_bit_identical(monkeypatch):
-    """The rollout keeps every env's NEXT reset state ready in shared memory and refills the used rows every few
-    steps (the reset of (env, episode) does not depend on the trajectory).  On-demand resets (period 0), short and
-    long refill periods and short episodes (t_max = 3: envs finish again before the next refill) give the same bits."""
+def test_reset_prefetch_is_bit_identical():
+    """The rollout keeps every env's NEXT reset state ready (shared memory inside a launch, a device scratch between
+    launches) and refills the used rows every few steps (the reset of (env, episode) does not depend on the
+    trajectory).  On-demand resets (period 0), short and long refill periods, rows carried or not carried from
+    launch to launch, and short episodes (t_max = 3: envs finish again before the next refill) give the same bits."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, _native as N
+    try:
+        for kw in (dict(t_max=25), dict(t_max=3)):
+            ref = None
+            for period, carry in ((0, False), (2, True), (3, False), (8, True), (8, False), (16, True)):
+                _tune(N.TUNE_RESET_REFILL, period)
+                env = BatchedRendezvousEnv(2500, seed=5, **kw)
+                env.reset()
+                out = env.rollout(70, action_seed=3, record_rewards=True, record_dones=True, carry_reset_rows=carry)
+                env.rollout(33, action_seed=3, step_base=70, carry_reset_rows=carry)   # a second launch
+                got = (env.get_state().clone(), out["rewards"].clone(), out["dones"].clone(), env.episode_index.clone(),
+                       env.read_stats())
+                if ref is None:
+                    ref = got
+                    assert int(out["dones"].sum()) > 2500                  # resets really happened
+                    continue
+                for a, b in zip(ref[:4], got[:4]):
+                    assert torch.equal(a, b), (kw, period, carry)
+                for key, v in ref[4].items():  # counters exact; the fp64 sums are atomically reduced over CTAs in any order
+                    assert got[4][key] == v if float(v).is_integer() else abs(got[4][key] - v) <= 1e-12 * abs(v), key
+    finally:
+        _tune(N.TUNE_RESET_REFILL, 8)
+
+
+def test_reset_rows_carried_over_many_short_launches():
+    """Rows carried over N short launches == one long launch (bit for bit), also when the caller resets envs, changes
+    the seed or overwrites the state between launches, and for the policy-fused variant (rows in the global scratch)."""
     import torch
     from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
-    for kw in (dict(t_max=25), dict(t_max=3)):
-        ref = None
-        for period in ("0", "2", "3", "8", "16"):
-            monkeypatch.setenv("RDV_RESET_REFILL", period)
-            env = BatchedRendezvousEnv(2500, seed=5, **kw)
-            env.reset()
-            out = env.rollout(70, action_seed=3, record_rewards=True, record_dones=True)
-            env.rollout(33, action_seed=3, step_base=70)               # a second launch starts without rows
-            got = (env.get_state().clone(), out["rewards"].clone(), out["dones"].clone(), env.episode_index.clone(),
-                   env.read_stats())
-            if ref is None:
-                ref = got
-                assert int(out["dones"].sum()) > 2500                  # resets really happened
-                continue
-            for a, b in zip(ref[:4], got[:4]):
-                assert torch.equal(a, b), (kw, period)
-            for key, v in ref[4].items():      # counters exact; the fp64 sums are atomically reduced over CTAs in any order
-                assert got[4][key] == v if float(v).is_integer() else abs(got[4][key] - v) <= 1e-12 * abs(v), key
-    monkeypatch.delenv("RDV_RESET_REFILL")
+    n = 3000
+    one = BatchedRendezvousEnv(n, seed=8, t_max=12)
+    one.reset()
+    one.rollout(96, action_seed=2, carry_reset_rows=False)
+    for chunk in (1, 5, 16):
+        many = BatchedRendezvousEnv(n, seed=8, t_max=12)
+        many.reset()
+        for k in range(0, 96, chunk):
+            many.rollout(min(chunk, 96 - k), action_seed=2, step_base=k)
+        assert many.reset_rows is not None and float(many.reset_rows[-1].max()) > 1      # rows are in use
+        assert torch.equal(one.get_state(), many.get_state()) and torch.equal(one.i32, many.i32), chunk
+        assert torch.equal(one.obs, many.obs)
+        sa, sb = one.read_stats(), many.read_stats()
+        assert sa["episodes"] == sb["episodes"] and sa["rk_accepted"] == sb["rk_accepted"]
+    # interventions between launches: the carried rows must never leak a stale state
+    a = BatchedRendezvousEnv(n, seed=8, t_max=12)
+    b = BatchedRendezvousEnv(n, seed=8, t_max=12)
+    for e, carry in ((a, True), (b, False)):
+        e.reset()
+        e.rollout(20, action_seed=2, carry_reset_rows=carry)
+        mask = torch.zeros(n, dtype=torch.uint8, device=e.device)
+        mask[::3] = 1
+        e.reset(mask=mask)                                  # bumps the episode index of a third of the envs
+        e.rollout(20, action_seed=2, step_base=20, carry_reset_rows=carry)
+        e.seed = 99                                         # another reset stream from here on
+        e.rollout(20, action_seed=2, step_base=40, carry_reset_rows=carry)
+        e.load_state_dict(e.state_dict())
+        e.rollout(7, action_seed=2, step_base=60, carry_reset_rows=carry)
+    assert torch.equal(a.get_state(), b.get_state()) and torch.equal(a.i32, b.i32)
+    # policy-fused variant: rows live in the global scratch
+    pol = _policy()
+    p1 = BatchedRendezvousEnv(n, seed=4, t_max=10)
+    p2 = BatchedRendezvousEnv(n, seed=4, t_max=10)
+    p1.reset(); p2.reset()
+    p1.rollout(48, policy=pol, carry_reset_rows=False)
+    for k in range(0, 48, 12):
+        p2.rollout(12, policy=pol)
+    assert float(p2.reset_rows[-1].max()) > 1
+    assert torch.equal(p1.get_state(), p2.get_state()) and torch.equal(p1.i32, p2.i32)
+    assert p1.read_stats()["episodes"] == p2.read_stats()["episodes"] > n
 
 
 def _policy():

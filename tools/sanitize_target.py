@@ -10,11 +10,12 @@ for n in (1, 33, 1000):
         env.step(torch.rand((n, 6), dtype=torch.float32, device='cuda') * 2 - 1)
     env.errors(); env.observe(); env.refresh_flags()
     env.reset(mask=torch.ones(n, dtype=torch.uint8))
-    for tpb in ("256", "448"):
-        os.environ["RDV_ROLLOUT_TPB"] = tpb
+    from reinforcement_learning_rendezvous_b200 import _native as N
+    for tpb in (256, 448):
+        N.lib().rdv_tune(N.TUNE_ROLLOUT_TPB, tpb)
         env.rollout(10, action_seed=3, record_rewards=True, record_dones=True, record_obs=True, record_actions=True)
         env.rollout(5, actions=torch.rand((5, n, 6), dtype=torch.float32, device='cuda'))
-    del os.environ["RDV_ROLLOUT_TPB"]
+    N.lib().rdv_tune(N.TUNE_ROLLOUT_TPB, 0)
     aniso = BatchedRendezvousEnv(n, seed=1, inertia=np.diag([10.0, 16.0, 22.0]), chaser_torque=[1e-3, 0, 0])
     aniso.reset(); aniso.step(torch.zeros((n, 6), dtype=torch.float64, device='cuda')); aniso.rollout(3, action_seed=1)
     cf = BatchedRendezvousEnv(n, seed=1, integrator="closed_form")
