@@ -229,15 +229,27 @@ def run_cuda(args):
     W_eff = max(W, 3)
     env.rollout(W_eff, action_seed=args.seed + 1, step_base=0)
     done_steps = W_eff
-    # calibration (untimed, doubles as warm-up of the K-step launch shape): how long is one repeat?
+    stats_bufs = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
+    snaps = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
+    total_stats = torch.zeros(N.NSTATS, dtype=torch.float64, device=dev)
+    # calibration (untimed; doubles as warm-up of the K-step launch shape and of every torch op and the collective
+    # the timed loop issues): how long is one repeat?
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    c0.record()
-    for kl in launches:
-        env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
-        done_steps += kl
-    c1.record()
-    torch.cuda.synchronize()
+    for warm in range(2):
+        barrier()
+        c0.record()
+        stats_bufs[0].zero_()
+        for kl in launches:
+            env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
+            done_steps += kl
+        snaps[0].copy_(stats_bufs[0])
+        w = all_reduce_stats(snaps[0], async_op=True)
+        if w is not None:
+            w.wait()
+        total_stats += snaps[0]
+        c1.record()
+        torch.cuda.synchronize()
+    total_stats.zero_()
     t_rep = max_over_ranks(c0.elapsed_time(c1))
     n_l = len(launches)
     R = max(1, math.ceil(args.min_region_ms / max(t_rep, 1e-3)), math.ceil(25 / n_l))
@@ -246,9 +258,6 @@ def run_cuda(args):
         rt = torch.tensor([R], dtype=torch.int64, device=dev)
         dist.all_reduce(rt, op=dist.ReduceOp.MAX)
         R = int(rt[0])
-    stats_bufs = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
-    snaps = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
-    total_stats = torch.zeros(N.NSTATS, dtype=torch.float64, device=dev)
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(R * n_l + 1)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -12,14 +12,18 @@ handle cross this boundary; PyTorch owns every buffer.
 from __future__ import annotations
 
 import ctypes as C
+import importlib.util
 import os
 import shutil
 import subprocess
+import sysconfig
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.environ.get("RDV_B200_LIB") or os.path.join(CSRC_DIR, "librdv_b200.so")   # env: A/B experiments
+HOST_SRC = os.path.join(CSRC_DIR, "rdv_host.c")                 # CPython helper of RendezvousVecEnv (gcc, no CUDA)
+HOST_LIB = os.path.join(PKG_DIR, "_rdv_host" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 SOURCES = ("rdv_b200.cu",)
 HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh", "rdv_policy.cuh", "rdv_policy_tc.cuh")
 
@@ -164,9 +168,37 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def build_host(force=False):
+    """gcc -> _rdv_host*.so next to the package (the VecEnv's info-dict builder, csrc/rdv_host.c)."""
+    global _host
+    if force or not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < os.path.getmtime(HOST_SRC):
+        cc = shutil.which("gcc") or shutil.which("cc") or "gcc"
+        subprocess.run([cc, "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"], "-o", HOST_LIB,
+                        HOST_SRC], check=True)
+        _host = None
+    return HOST_LIB
+
+
+_host = None
+
+
+def host():
+    """The loaded _rdv_host extension module.  Raises when it has not been built."""
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB):
+            raise RuntimeError(f"{HOST_LIB} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        spec = importlib.util.spec_from_file_location("_rdv_host", HOST_LIB)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _host = mod
+    return _host
+
+
 def build(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into csrc/librdv_b200.so (in-tree, so it travels to the GPU box)."""
     global _lib
+    build_host(force=force)
     if force or is_stale():
         cmd = nvcc_command()
         if verbose:

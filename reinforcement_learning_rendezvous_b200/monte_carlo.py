@@ -1,10 +1,10 @@
 """Monte-Carlo evaluator (/root/reference/monte_carlo.py:94-207).
 
 ``evaluate(model, env, initial_state)`` keeps the reference's single-episode signature and works with
-the single-env facade.  ``evaluate_batch`` runs every initial condition as one env of a GPU batch:
-policy forward, env step and the get_errors / check_collision / check_success / dist_from_koz
-queries are kernels; the per-episode reduction (counts, running minimum, first-index terminal-error
-averaging of monte_carlo.py:159-189) is done on the recorded per-step arrays.
+the single-env facade.  ``evaluate_batch`` runs every initial condition as one env of a GPU batch in ONE
+launch: the actor, the env step, the get_errors / check_collision / check_success / dist_from_koz queries
+and the per-episode reduction (counts, running minimum, first-index terminal-error averaging of
+monte_carlo.py:159-189) all happen inside the policy-fused rollout kernel, and one [M, 16] array comes back.
 """
 from __future__ import annotations
 
@@ -101,10 +101,15 @@ def evaluate(model, env, initial_state):
 
 
 def evaluate_batch(policy, initial_states, config=None, reward_kwargs=None, device="cuda", normalize_quaternions=True,
-                   **extra) -> dict:
-    """All rows of ``initial_states`` ([M,20]: rc vc qc wc qt wt) as one GPU batch.  Returns a dict of
-    length-M arrays with the columns of the reference's results workbook.  ``config`` defaults to the
-    evaluator's ``dict(dt=1, t_max=60)`` with ``stochastic=False`` (monte_carlo.py:26-27)."""
+                   return_raw=False, **extra) -> dict:
+    """All rows of ``initial_states`` ([M,20]: rc vc qc wc qt wt) as one GPU batch: ONE kernel launch and ONE
+    device-to-host copy.  The launch is the policy-fused rollout in evaluator mode (``RdvRolloutIO.mc_out``): the actor
+    runs on the tensor cores inside the kernel, and per-episode collision / success counts, the running minimum of
+    ``dist_from_koz``, the return and the first-index terminal-error averages of monte_carlo.py:159-189 are
+    accumulated in registers until the env's first done.  Returns a dict of length-M arrays with the columns of the
+    reference's results workbook.  ``config`` defaults to the evaluator's ``dict(dt=1, t_max=60)`` with
+    ``stochastic=False`` (monte_carlo.py:26-27)."""
+    from . import _native as N
     ics = np.array(initial_states, dtype=np.float64, copy=True).reshape(-1, 20)
     if normalize_quaternions:                                   # monte_carlo.py:66-67
         ics[:, 6:10] /= np.linalg.norm(ics[:, 6:10], axis=1, keepdims=True)
@@ -114,96 +119,62 @@ def evaluate_batch(policy, initial_states, config=None, reward_kwargs=None, devi
     env = BatchedRendezvousEnv(m, device=device, auto_reset=False, track_stats=False, reward_kwargs=reward_kwargs,
                                **kw, **extra)
     p = env.params
-    steps_max = int(p.t_max / p.dt) + 1
     env.reset()
     env.set_state(ics, reset_counters=False)        # flags stay as reset() left them (monte_carlo.py:106-112)
-    obs = env.observe()
-    dev = env.device
-    err_log = torch.full((steps_max + 1, m, 4), float("nan"), dtype=torch.float64, device=dev)
-    alive = torch.ones(m, dtype=torch.bool, device=dev)
-    length = torch.zeros(m, dtype=torch.int64, device=dev)
-    n_col = torch.zeros(m, dtype=torch.int64, device=dev)
-    n_suc = torch.zeros(m, dtype=torch.int64, device=dev)
-    total_reward = torch.zeros(m, dtype=torch.float64, device=dev)
-    tdv = torch.zeros(m, dtype=torch.float64, device=dev)
+    out = env.rollout(int(p.done_steps), policy=policy, monte_carlo=True)
+    mc = out["mc"].cpu().numpy()                    # the one read-back: [M, MC_NCOL]
+    res = mc_columns(mc, p.dt)
+    if return_raw:
+        res["raw"] = mc
+    return res
 
-    err, col, suc, koz = env.errors()
-    err_log[0] = err
-    n_col += col.long()
-    n_suc += suc.long()                             # rdv_errors' success already honours the sticky collided flag
-    min_koz = koz.clone()
-    actions = torch.empty((m, 6), dtype=torch.float32, device=dev)
-    k = 0
-    while bool(alive.any()) and k < steps_max:
-        k += 1
-        policy.forward(obs, out=actions)
-        obs_k, rew, done = env.step(actions)
-        obs = obs_k
-        err, col, suc, koz = env.errors()
-        err_log[k][alive] = err[alive]
-        n_col += (col.bool() & alive).long()
-        n_suc += (suc.bool() & alive).long()
-        min_koz = torch.where(alive & (koz < min_koz), koz, min_koz)
-        total_reward += torch.where(alive, rew, torch.zeros_like(rew))
-        length += alive.long()
-        finished = alive & done.bool()
-        tdv = torch.where(finished, env.total_delta_v, tdv)
-        alive = alive & ~done.bool()
-    err_np = err_log.cpu().numpy()
-    length_np = length.cpu().numpy()
-    limits = (p.max_rd_error, p.max_vd_error, p.max_qd_error, p.max_wd_error)
-    te = _terminal_errors_batch(err_np, length_np, limits)
-    n_col_np, n_suc_np = n_col.cpu().numpy(), n_suc.cpu().numpy()
-    dt = p.dt
+
+def mc_columns(mc: np.ndarray, dt: float) -> dict:
+    """[M, MC_NCOL] device results -> the workbook columns (monte_carlo.py:190-203): seconds and degrees."""
+    from . import _native as N
     return dict(
-        ep_len=np.round(length_np * dt, 3), num_collisions=n_col_np, collided=(n_col_np > 0).astype(np.int64),
-        total_reward=total_reward.cpu().numpy(), total_delta_v=tdv.cpu().numpy(), num_successes=n_suc_np,
-        succeeded=(n_suc_np > 0).astype(np.int64), min_dist_from_koz=min_koz.cpu().numpy(),
-        pos_error=te[:, 0], vel_error=te[:, 1], att_error=te[:, 2], rot_error=te[:, 3])
+        ep_len=np.round(mc[:, N.MC_EP_LEN] * dt, 3), num_collisions=mc[:, N.MC_NUM_COLLISIONS].astype(np.int64),
+        collided=mc[:, N.MC_COLLIDED].astype(np.int64), total_reward=mc[:, N.MC_TOTAL_REWARD].copy(),
+        total_delta_v=mc[:, N.MC_TOTAL_DELTA_V].copy(), num_successes=mc[:, N.MC_NUM_SUCCESSES].astype(np.int64),
+        succeeded=mc[:, N.MC_SUCCEEDED].astype(np.int64), min_dist_from_koz=mc[:, N.MC_MIN_KOZ].copy(),
+        pos_error=mc[:, N.MC_POS_ERR].copy(), vel_error=mc[:, N.MC_VEL_ERR].copy(),
+        att_error=np.degrees(mc[:, N.MC_ATT_ERR]), rot_error=np.degrees(mc[:, N.MC_ROT_ERR]))
 
 
 def evaluate_sweep(policy, param_sets, episodes_per_set=1024, reward_kwargs=None, device="cuda", seed=0,
-                   **common) -> list:
+                   rank=0, world_size=1, **common) -> list:
     """Sensitivity sweep as ONE batch (BASELINE.json configs[4]; the axes of sensitivity_analysis.py:97-134 --
     ``rc0, wt0, koz_radius, corridor_half_angle, h, dt``): every entry of ``param_sets`` (a dict of ``make_env``
-    config keys) becomes a contiguous block of ``episodes_per_set`` stochastic envs with its own constants; all
-    blocks step together (one launch per block and step) under the deterministic policy and the first episode of
-    every env is scored.  Returns one dict per set: mean return / length, success and collision rates
-    (the metrics of custom_callbacks.py:285-298)."""
+    config keys) becomes a contiguous block of ``episodes_per_set`` stochastic envs with its own constants; the
+    blocks run under the deterministic policy fused into the rollout in evaluator mode (one launch per block, the
+    first episode of every env is scored on the device).  With ``world_size`` > 1 the parameter sets are sharded over
+    ranks by :func:`~.distributed.shard_range` (every rank returns its own sets; reset streams are keyed by the
+    global env id, so a set's result does not depend on the sharding).  Returns one dict per set: mean return /
+    length, success and collision rates (the metrics of custom_callbacks.py:285-298)."""
+    from . import _native as N
+    from .distributed import shard_range
     if episodes_per_set % 32:
         raise ValueError("episodes_per_set must be a multiple of 32")
+    lo_set, hi_set = shard_range(len(param_sets), world_size, rank)
+    mine = list(param_sets[lo_set:hi_set])
+    if not mine:
+        return []
     batches = []
-    for ps in param_sets:
+    for ps in mine:
         kw = config_to_kwargs(dict(common, **ps), stochastic=True)
         batches.append((episodes_per_set, {k: v for k, v in kw.items() if v is not None}))
     n = episodes_per_set * len(batches)
-    env = BatchedRendezvousEnv(n, device=device, seed=seed, auto_reset=False, track_stats=False,
-                               reward_kwargs=reward_kwargs, param_batches=batches)
-    dev = env.device
-    obs = env.reset().clone()
+    env = BatchedRendezvousEnv(n, device=device, seed=seed, env_offset=lo_set * episodes_per_set, auto_reset=False,
+                               track_stats=False, reward_kwargs=reward_kwargs, param_batches=batches)
+    env.reset()
     steps = max(int(g.params.done_steps) for g in env.groups)
-    returns = torch.zeros(n, dtype=torch.float64, device=dev)
-    length = torch.zeros(n, dtype=torch.int64, device=dev)
-    alive = torch.ones(n, dtype=torch.bool, device=dev)
-    success = torch.zeros(n, dtype=torch.bool, device=dev)
-    collided = torch.zeros(n, dtype=torch.bool, device=dev)
-    actions = torch.empty((n, 6), dtype=torch.float32, device=dev)
-    for _ in range(steps):
-        policy.forward(obs, out=actions)
-        obs, rew, done = env.step(actions)
-        returns += torch.where(alive, rew, torch.zeros_like(rew))
-        length += alive.long()
-        finished = alive & done.bool()
-        success |= finished & (env.success > 0)
-        collided |= finished & (env.collided > 0)
-        alive &= ~done.bool()
-        if not bool(alive.any()):
-            break
+    mc = env.rollout(steps, policy=policy, monte_carlo=True)["mc"]
+    res = torch.stack([mc[:, N.MC_TOTAL_REWARD], mc[:, N.MC_EP_LEN], (env.success > 0).double(),
+                       (env.collided > 0).double()], dim=1).cpu().numpy()        # flags are frozen at the first done
     out = []
-    for ps, g in zip(param_sets, env.groups):
-        sl = slice(g.lo, g.hi)
-        out.append(dict(params=dict(ps), episodes=g.n, mean_return=float(returns[sl].mean()),
-                        mean_length_s=float(length[sl].double().mean() * g.params.dt),
-                        success_rate=float(success[sl].double().mean()),
-                        collision_rate=float(collided[sl].double().mean())))
+    for ps, g in zip(mine, env.groups):
+        r = res[g.lo:g.hi]
+        out.append(dict(params=dict(ps), episodes=g.n, mean_return=float(r[:, 0].mean()),
+                        mean_length_s=float(r[:, 1].mean() * g.params.dt), success_rate=float(r[:, 2].mean()),
+                        collision_rate=float(r[:, 3].mean())))
     return out

@@ -67,11 +67,33 @@ class ActorCritic(nn.Module):
         return MlpPolicy(sd, device=device)
 
 
+def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_value: torch.Tensor, gamma: float,
+        gae_lambda: float):
+    """GAE(lambda) of SB3's ``RolloutBuffer.compute_returns_and_advantage`` on [T, N] tensors: ``dones[t]`` is the done
+    flag returned by step t (SB3's ``episode_starts[t + 1]``; the last row is its ``dones`` argument).  No time-limit
+    bootstrapping, like the reference (it never sets ``TimeLimit.truncated``).  Returns (advantages, returns)."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(last_value)
+    for t in reversed(range(T)):
+        next_value = last_value if t == T - 1 else values[t + 1]
+        not_done = 1.0 - dones[t].to(rewards.dtype)
+        delta = rewards[t] + gamma * next_value * not_done - values[t]
+        last = delta + gamma * gae_lambda * not_done * last
+        adv[t] = last
+    return adv, adv + values
+
+
 @dataclass
 class PPOConfig:
+    """Defaults = /root/reference/main.py:39-48 (lr 2e-3, batch_size 128, n_epochs 40, clip_range 0.25) + the SB3
+    defaults the shipped model was trained with (gamma 0.99, gae_lambda 0.95, ent_coef 0, vf_coef 0.5,
+    max_grad_norm 0.5).  ``n_steps`` is per env: the reference collects 2048 steps from ONE env per iteration; with
+    thousands of envs a few steps per env give a much larger buffer, and callers normally raise ``batch_size`` with it
+    (128-sample minibatches over a 262,144-sample buffer are 2,048 optimiser steps per epoch)."""
     n_steps: int = 16                 # per env and iteration (the reference: 2048 with ONE env)
-    batch_size: int = 8192            # the reference: 128 with 2048-sample rollouts
-    n_epochs: int = 10                # the reference: 40
+    batch_size: int = 128             # main.py:43
+    n_epochs: int = 40                # main.py:44
     learning_rate: float = 2e-3       # main.py:42
     clip_range: float = 0.25          # main.py:45
     gamma: float = 0.99
@@ -81,13 +103,21 @@ class PPOConfig:
     max_grad_norm: float = 0.5
     normalize_advantage: bool = True
     n_evals: int = 50                 # custom_callbacks.py: n_evals
-    fused: bool = True                # collect with the policy-fused rollout kernel
+    fused: bool = True                # collect with the policy-fused rollout kernel (device env only)
     seed: int = 0
     log: list = field(default_factory=list)
 
 
 class PPO:
-    def __init__(self, env: BatchedRendezvousEnv, config: Optional[PPOConfig] = None, policy: Optional[ActorCritic] = None):
+    """``env``: a :class:`BatchedRendezvousEnv` (device tensors end to end: fused or stepwise collection) or a
+    :class:`RendezvousVecEnv` -- the SB3 drop-in of BASELINE.json configs[2]: collection then goes through
+    ``VecEnv.step`` exactly like SB3's ``collect_rollouts`` (torch policy on the GPU, numpy actions in, numpy
+    observations / rewards / dones out)."""
+
+    def __init__(self, env, config: Optional[PPOConfig] = None, policy: Optional[ActorCritic] = None):
+        self.venv = None
+        if not isinstance(env, BatchedRendezvousEnv):          # RendezvousVecEnv (or anything wrapping one as .env)
+            self.venv, env = env, env.env
         if not env.auto_reset:
             raise ValueError("training needs an auto-resetting env")
         self.env, self.cfg = env, config or PPOConfig()
@@ -103,7 +133,8 @@ class PPO:
         self.buf_val = torch.empty((T, n), dtype=torch.float32, device=dev)
         self.buf_rew = torch.empty((T, n), dtype=torch.float32, device=dev)
         self.buf_done = torch.empty((T, n), dtype=torch.bool, device=dev)
-        self.obs = env.reset().clone()
+        self._np_obs = self.venv.reset() if self.venv is not None else None
+        self.obs = env.obs.clone() if self.venv is not None else env.reset().clone()
         self.episode_start = torch.ones(n, dtype=torch.bool, device=dev)
         self.num_timesteps = 0
         self._noise_step = 0
@@ -115,20 +146,35 @@ class PPO:
     # -- rollout collection (OnPolicyAlgorithm.collect_rollouts) ------------------------------------------------
     @torch.no_grad()
     def collect(self):
+        if self.venv is not None:
+            return self._collect_vecenv()
         return self._collect_fused() if self.cfg.fused else self._collect_stepwise()
 
     def _gae(self, last_value):
-        T = self.cfg.n_steps
-        adv = torch.zeros_like(self.buf_rew)
-        last = torch.zeros(self.env.num_envs, device=self.device)
-        for t in reversed(range(T)):
-            next_value = last_value if t == T - 1 else self.buf_val[t + 1]
-            not_done = (~self.buf_done[t]).float()
-            delta = self.buf_rew[t] + self.cfg.gamma * next_value * not_done - self.buf_val[t]
-            last = delta + self.cfg.gamma * self.cfg.gae_lambda * not_done * last
-            adv[t] = last
-        self.num_timesteps += T * self.env.num_envs
-        return adv, adv + self.buf_val
+        self.num_timesteps += self.cfg.n_steps * self.env.num_envs
+        return gae(self.buf_rew, self.buf_val, self.buf_done, last_value, self.cfg.gamma, self.cfg.gae_lambda)
+
+    def _collect_vecenv(self):
+        """SB3 ``OnPolicyAlgorithm.collect_rollouts`` over the VecEnv drop-in: per step one policy forward on the GPU,
+        the clipped numpy action into ``VecEnv.step``, numpy results back into the device rollout buffer."""
+        venv, T, dev = self.venv, self.cfg.n_steps, self.device
+        obs_np = self._np_obs
+        for t in range(T):
+            obs_t = torch.from_numpy(obs_np).to(dev, non_blocking=True)
+            mean, value = self.policy(obs_t)
+            dist = self.policy.distribution(mean)
+            action = dist.sample()
+            self.buf_obs[t], self.buf_act[t] = obs_t, action
+            self.buf_logp[t], self.buf_val[t] = dist.log_prob(action).sum(-1), value
+            a_np = action.clamp(-1.0, 1.0).cpu().numpy()                    # SB3 clips to the Box before step
+            obs_np, rew, done, _ = venv.step_arrays(a_np)
+            self.buf_rew[t] = torch.from_numpy(rew).to(dev, non_blocking=True)
+            self.buf_done[t] = torch.from_numpy(done).to(dev, non_blocking=True)
+        self._np_obs = obs_np
+        self.obs = torch.from_numpy(obs_np).to(dev)
+        self.episode_start = self.buf_done[-1]
+        _, last_value = self.policy(self.obs)
+        return self._gae(last_value)
 
     def _collect_fused(self):
         env, T, n = self.env, self.cfg.n_steps, self.env.num_envs
@@ -201,16 +247,17 @@ class PPO:
     # -- deterministic evaluation (CustomCallback._on_rollout_start / evaluate_policy) --------------------------
     @torch.no_grad()
     def evaluate(self) -> dict:
+        """One deterministic episode per evaluation env, scored on the device by the rollout's evaluator mode: an env
+        stops at its first done, so the success / collided flags are those of the episode's end (what the reference
+        callback reads), not of whatever happens afterwards."""
+        from . import _native as N
         env = self.eval_env
         env.reset()
         steps = int(env.params.done_steps)
-        out = env.rollout(steps, policy=self.policy.to_mlp_policy(self.device), record_rewards=True, record_dones=True)
-        done = out["dones"].bool()
-        first = torch.where(done.any(0), done.float().argmax(0), torch.full_like(done[0], steps - 1, dtype=torch.long))
-        mask = torch.arange(steps, device=self.device)[:, None] <= first[None, :]
-        returns = (out["rewards"] * mask).sum(0)
-        return {"mean_return": float(returns.mean()), "mean_length": float((first + 1).float().mean()),
-                "success_rate": float((env.success > 0).float().mean()), "collision_rate": float((env.collided > 0).float().mean())}
+        mc = env.rollout(steps, policy=self.policy.to_mlp_policy(self.device), monte_carlo=True)["mc"]
+        return {"mean_return": float(mc[:, N.MC_TOTAL_REWARD].mean()), "mean_length": float(mc[:, N.MC_EP_LEN].mean()),
+                "success_rate": float((env.success > 0).float().mean()),
+                "collision_rate": float((env.collided > 0).float().mean())}
 
     def learn(self, total_timesteps: int, eval_every: int = 1, verbose: bool = False):
         it = 0

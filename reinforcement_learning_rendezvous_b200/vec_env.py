@@ -43,6 +43,7 @@ except Exception:                                      # noqa: BLE001
     _SB3VecEnv = None
 
 # numpy mirror of RdvFinishedRow (include/rdv_b200.h), 128 bytes
+_NO_TERM = np.zeros((0, N.OBS_DIM), dtype=np.float32)
 FINISHED_ROW = np.dtype([("env", "<i4"), ("end_reason", "<i4"), ("terminal_obs", "<f4", (N.OBS_DIM,)), ("pad", "<f4"),
                          ("record", "<f8", (N.EP_NCOL,))])
 assert FINISHED_ROW.itemsize == 128
@@ -112,7 +113,7 @@ class _PinnedBlockPool:
 
 class RendezvousVecEnv(_Base):
     def __init__(self, num_envs: int, device="cuda", seed: int = 0, env_offset: int = 0, copy_outputs: bool = False,
-                 rich_infos: bool = False, **ctor_kwargs):
+                 rich_infos: bool = False, gc_freeze: bool = True, **ctor_kwargs):
         self.env = BatchedRendezvousEnv(num_envs, device=device, seed=seed, env_offset=env_offset, auto_reset=True,
                                         **ctor_kwargs)
         _Base.__init__(self, num_envs, observation_space(), action_space())
@@ -131,6 +132,7 @@ class RendezvousVecEnv(_Base):
         self._d_act32 = torch.zeros((n, N.ACT_DIM), dtype=torch.float32, device=self.env.device)
         self._d_act64 = torch.zeros((n, N.ACT_DIM), dtype=torch.float64, device=self.env.device)
         self._pending = None
+        self._host = N.host()
         self._t_start = time.time()
         # one independent dict per env (DummyVecEnv semantics); finished envs get a fresh one per episode end
         self._infos: List[dict] = [{} for _ in range(n)]
@@ -144,7 +146,8 @@ class RendezvousVecEnv(_Base):
         self.d2h_bytes_last_step = self._d2h_fixed
         self.d2h_bytes_total = 0
         self.extra_fetches = 0                             # steps that needed a second copy for their finished rows
-        gc.freeze()                                        # the long-lived objects above never need another GC walk
+        if gc_freeze:
+            gc.freeze()      # the long-lived objects above (65,536 dicts ...) never need another walk by the cyclic GC
 
     # ------------------------------------------------------------------ VecEnv API
     def _views(self, base: np.ndarray, shared: bool):
@@ -180,7 +183,7 @@ class RendezvousVecEnv(_Base):
 
     def _launch_and_fetch(self):
         """One launch, one device-to-host copy, one synchronise.  Returns (obs, rew, done, rows) with ``rows`` the
-        finished envs' records (structured array, ascending env index, own memory)."""
+        finished envs' records (structured view of the pinned block, in the order the kernel appended them)."""
         if self._pending is None:
             raise RuntimeError("step_wait() called without step_async()")
         env, L = self.env, self.layout
@@ -206,7 +209,6 @@ class RendezvousVecEnv(_Base):
         self.d2h_bytes_total += self.d2h_bytes_last_step
         obs, rew, done = self._views(base, shared)
         rows = base[L["rows"]:L["rows"] + self._d2h_row * m].view(FINISHED_ROW)
-        rows = rows[np.argsort(rows["env"], kind="stable")] if m else rows.copy()    # sorted gather = own memory
         return obs, rew, done, rows
 
     def step_arrays(self, actions):
@@ -216,6 +218,7 @@ class RendezvousVecEnv(_Base):
         ``end_reason`` (0 obs, 1 time, 2 bubble, 3 attitude).  Same data as the ``infos`` of ``step``."""
         self.step_async(actions)
         obs, rew, done, rows = self._launch_and_fetch()
+        rows = rows[np.argsort(rows["env"])]            # ascending env index; the gather also takes own memory
         rec = rows["record"]
         finished = {
             "index": rows["env"].astype(np.int64), "terminal_observation": rows["terminal_obs"],
@@ -239,40 +242,20 @@ class RendezvousVecEnv(_Base):
         finally:
             if paused:
                 gc.enable()
+        del rows                                        # the last view of the pinned block besides obs / rew / done
         return obs, rew, done, infos
 
     def _build_infos(self, rows) -> List[dict]:
-        infos = self._infos
-        for i in self._dirty:                              # last step's episode-end dicts make way for fresh ones
-            infos[i] = {}
+        """One fresh dict per finished env into this VecEnv's list of per-env dicts (built by csrc/rdv_host.c: the
+        interpreter would spend longer on these ~2 objects per episode end than the GPU on the whole step).  The
+        LIST object is the same every step -- like DummyVecEnv's buf_infos -- and an env that is still running keeps
+        its own (normally empty) dict; consume or copy the infos before the next step."""
         m = rows.shape[0]
-        if m:
-            # bulk numpy work first, then one small dict per finished env, built by ONE comprehension over zipped
-            # columns (row views of the gathered array)
-            rec = rows["record"]
-            term = list(rows["terminal_obs"])
-            elapsed = round(time.time() - self._t_start, 6)
-            rets = np.round(rec[:, N.EP_RETURN], 6).tolist()
-            lens = rec[:, N.EP_LENGTH].astype(np.int64).tolist()
-            if self.rich_infos:
-                reason = [N.END_REASONS[j] for j in rows["end_reason"].tolist()]
-                succ = (rec[:, N.EP_SUCCESS] > 0).tolist()
-                coll = (rec[:, N.EP_COLLIDED] > 0).tolist()
-                dv, dw = rec[:, N.EP_DELTA_V].tolist(), rec[:, N.EP_DELTA_W].tolist()
-                new = [{"terminal_observation": t, "episode": {"r": r, "l": l, "t": elapsed}, "is_success": s,
-                        "collided": c, "total_delta_v": v, "total_delta_w": w, "end_reason": q}
-                       for t, r, l, s, c, v, w, q in zip(term, rets, lens, succ, coll, dv, dw, reason)]
-            else:
-                new = [{"terminal_observation": t, "episode": {"r": r, "l": l, "t": elapsed}}
-                       for t, r, l in zip(term, rets, lens)]
-            idx = rows["env"].tolist()
-            for i, d in zip(idx, new):
-                infos[i] = d
-            self._dirty = idx
-        else:
-            self._dirty = []
-        # a new list object per step (DummyVecEnv returns a fresh list); the dicts of running envs are each env's own
-        return list(infos)
+        term = np.ascontiguousarray(rows["terminal_obs"]) if m else _NO_TERM      # own memory: frees the pinned block
+        elapsed = round(time.time() - self._t_start, 6)
+        self._dirty = self._host.build_infos(self._infos, self._dirty, rows, term, elapsed, self.rich_infos,
+                                             N.END_REASONS)
+        return self._infos
 
     def close(self):
         return None

@@ -16,12 +16,22 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
-def rel_err(a, b, floor=1.0):
-    """max |a-b| / max(|b|, floor) -- relative to the magnitude of the quantity (floor 1: unit quaternions, O(1-10)
-    positions); used with REL_TOL."""
+# Magnitude floors of the relative error, per column of a [.., 20] state (rc vc qc wc qt wt): O(1-10) m positions and
+# unit quaternions get 1, velocities (~0.05 m/s) 1e-2, body rates (~5e-3 rad/s) 1e-3 -- so "1e-9 relative" means
+# 1e-9 of the component's own scale, not of 1.
+STATE_FLOORS = np.array([1.0] * 3 + [1e-2] * 3 + [1.0] * 4 + [1e-3] * 3 + [1.0] * 4 + [1e-3] * 3)
+# get_errors(): position [m], velocity [m/s], attitude [rad], rate [rad/s]
+ERROR_FLOORS = np.array([1.0, 1e-2, 1e-2, 1e-3])
+
+
+def rel_err(a, b, floor=None):
+    """max |a-b| / max(|b|, floor) -- relative to the magnitude of the quantity; used with REL_TOL.  ``floor``
+    defaults to the per-column STATE_FLOORS for [.., 20] states and to 1 otherwise (rewards, O(1) quantities)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     if a.size == 0:
         return 0.0
+    if floor is None:
+        floor = STATE_FLOORS if (b.ndim >= 1 and b.shape[-1] == 20) else 1.0
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
 
 

@@ -103,6 +103,37 @@ def test_facade_monte_carlo_evaluate_matches_reference_rerun():
 
 
 # ------------------------------------------------------------------------------------------ Monte Carlo
+def test_device_side_monte_carlo_equals_host_loop():
+    """evaluate_batch = ONE policy-fused rollout launch in evaluator mode + one [M, 16] read-back.  It must agree with
+    the evaluation assembled from per-step launches and a numpy reduction of the recorded per-step arrays
+    (tests/mc_hostloop.py, round 1's product path; same rule as monte_carlo.py:159-189): discrete columns equal,
+    continuous columns to rounding (the fused kernel and the lane-pair step kernel order a few operations
+    differently; the running sums here are sequential, numpy's are pairwise)."""
+    from mc_hostloop import evaluate_batch_hostloop
+    from reinforcement_learning_rendezvous_b200 import evaluate_batch, _native as N
+    mc = golden("mc.npz")
+    pol = _policy()
+    dev_out = evaluate_batch(pol, mc["ic_raw"], return_raw=True)
+    host_out = evaluate_batch_hostloop(pol, mc["ic_raw"])
+    raw = dev_out.pop("raw")
+    assert raw.shape == (1000, N.MC_NCOL) and (raw[:, N.MC_END_REASON] >= 0).all()
+    same = np.asarray(dev_out["ep_len"]) == np.asarray(host_out["ep_len"])
+    # a 1e-7 action difference between the two actor launches can move an episode end: allow 2 of 1000
+    assert same.sum() >= 998, int((~same).sum())
+    for k in ("num_collisions", "collided", "num_successes", "succeeded"):
+        assert int((np.asarray(dev_out[k])[same] != np.asarray(host_out[k])[same]).sum()) <= 1, k
+    close = same & (np.asarray(dev_out["num_successes"]) == np.asarray(host_out["num_successes"]))
+    for k in ("total_reward", "total_delta_v", "min_dist_from_koz", "pos_error", "vel_error", "att_error", "rot_error"):
+        a, b = np.asarray(dev_out[k])[close], np.asarray(host_out[k])[close]
+        rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-2)
+        assert np.quantile(rel, 0.99) <= 1e-6 and np.median(rel) <= 1e-9, (k, float(np.median(rel)), float(rel.max()))
+    # the level / tail-count bookkeeping of the single running sum
+    assert set(np.unique(raw[:, N.MC_LEVEL])) <= {0.0, 1.0, 2.0, 3.0, 4.0}
+    assert (raw[:, N.MC_TAIL_COUNT] >= 1).all() and (raw[:, N.MC_TAIL_COUNT] <= raw[:, N.MC_EP_LEN] + 1).all()
+    none = raw[:, N.MC_LEVEL] == 4
+    assert (raw[none, N.MC_TAIL_COUNT] == 1).all()
+
+
 def test_monte_carlo_batch_reproduces_published_workbook():
     """All 1000 published initial conditions as one GPU batch with the shipped policy: discrete columns equal
     the reference's published results (results/data_monte_carlo_results_mlp.xlsx) up to a handful of
@@ -111,10 +142,14 @@ def test_monte_carlo_batch_reproduces_published_workbook():
     mc = golden("mc.npz")
     out = evaluate_batch(_policy(), mc["ic_raw"])
     n = 1000
-    for src, max_flips in (("workbook_", 10), ("rerun_", 10)):
+    # at most 0.5 % of the episodes (5 of 1000) may differ through a rounding flip of the fp32 policy
+    counts = {}
+    for src, max_flips in (("workbook_", 5), ("rerun_", 5)):
         for k in ("ep_len", "num_collisions", "collided", "num_successes", "succeeded"):
             flips = int((np.asarray(out[k], dtype=float) != mc[src + k]).sum())
-            assert flips <= max_flips, (src, k, flips)
+            counts[src + k] = flips
+    print("episodes differing from the published workbook / the reference re-run, per column:", counts)
+    assert max(counts.values()) <= 5, counts
     assert abs(int(out["succeeded"].sum()) - 545) <= 3
     assert abs(int(out["collided"].sum()) - 166) <= 3
     same = np.asarray(out["ep_len"], dtype=float) == mc["rerun_ep_len"]
@@ -211,6 +246,47 @@ def test_vec_env_contract():
     np.testing.assert_array_equal(venv.get_attr("rc", 4)[0], [1.0, -2.0, 3.0])
     assert venv.env_is_wrapped(object) == [False] * n
     venv.close()
+
+
+def test_vec_env_outputs_never_alias_later_steps():
+    """SB3's collect_rollouts keeps `_last_obs` / `_last_episode_starts` across the NEXT env.step and only then adds
+    them to the rollout buffer; DummyVecEnv returns copies for that reason.  The arrays a step returns must never be
+    overwritten by later steps -- however long the caller keeps them -- and every env owns its info dict."""
+    import sys
+    from reinforcement_learning_rendezvous_b200 import RendezvousVecEnv
+    n = 700
+    venv = RendezvousVecEnv(n, seed=2, t_max=9)
+    rng = np.random.default_rng(0)
+    def hoard():
+        held = []                                         # (array, its copy at the time it was returned)
+        obs0 = venv.reset()
+        held.append((obs0, obs0.copy()))
+        for k in range(14):                               # more steps than the pinned-block pool has blocks
+            obs, rew, done, infos = venv.step(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+            for a in (obs, rew, done):
+                held.append((a, a.copy()))
+            for i in np.flatnonzero(done)[:3]:
+                t = infos[i]["terminal_observation"]
+                held.append((t, t.copy()))
+            for a, c in held:
+                np.testing.assert_array_equal(a, c)
+        assert len({id(a) for a, _ in held}) == len(held)
+
+    hoard()
+    # hoarding beyond the pool's capacity degrades to real copies, never to aliasing
+    assert len(venv._pool._arrays) <= venv._pool.capacity
+    # per-env dicts: writing into one env's info does not show up anywhere else
+    obs, rew, done, infos = venv.step(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+    running = np.flatnonzero(~done)
+    infos[running[0]]["custom"] = 1
+    assert all("custom" not in infos[i] for i in running[1:50])
+    assert len({id(infos[i]) for i in range(n)}) == n
+    # a caller that drops everything lets the pool recycle its blocks
+    del obs, rew, done
+    before = len(venv._pool._arrays)
+    for k in range(20):
+        venv.step(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+    assert len(venv._pool._arrays) == before
 
 
 def test_vec_env_step_equals_batched_env():

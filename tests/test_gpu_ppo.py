@@ -34,3 +34,21 @@ def test_ppo_short_training_run(tmp_path, fused):
     mean_best, _ = algo.policy(obs)
     act = pol.forward(obs)
     assert (act - mean_best.clamp(-1, 1)).abs().max().item() < 1e-5
+
+
+def test_ppo_through_the_vecenv_drop_in():
+    """BASELINE.json configs[2]: collection through RendezvousVecEnv.step (numpy in / out, the SB3 surface), the same
+    update; the buffer rows are what the VecEnv returned and learning still happens."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import RendezvousVecEnv
+    from reinforcement_learning_rendezvous_b200.ppo import PPO, PPOConfig
+    venv = RendezvousVecEnv(2048, seed=0)
+    cfg = PPOConfig(n_steps=16, batch_size=4096, n_epochs=4, n_evals=64, seed=0)
+    algo = PPO(venv, cfg)
+    algo.learn(total_timesteps=10 * 16 * 2048, eval_every=0)
+    log = cfg.log
+    assert len(log) == 10 and all(np.isfinite(r["value_loss"]) for r in log)
+    first, last = np.mean([r["mean_step_reward"] for r in log[:2]]), np.mean([r["mean_step_reward"] for r in log[-2:]])
+    assert last > first + 0.01, (first, last)
+    st = venv.read_stats()
+    assert st["steps"] == 10 * 16 * 2048 and st["episodes"] > 0

@@ -133,3 +133,46 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "env-steps/s"
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_gae_matches_sb3_rollout_buffer_restatement():
+    """ppo.gae against a numpy restatement of Stable-Baselines3 1.6.2 ``RolloutBuffer.compute_returns_and_advantage``
+    (what the reference's ``PPO.learn`` runs, main.py:114): episode_starts[t + 1] = dones[t], the last row uses the
+    ``dones`` argument, no time-limit bootstrapping."""
+    import torch
+    from reinforcement_learning_rendezvous_b200.ppo import gae
+    rng = np.random.default_rng(0)
+    T, n, gamma, lam = 37, 50, 0.99, 0.95
+    rewards = rng.normal(size=(T, n)).astype(np.float32)
+    values = rng.normal(size=(T, n)).astype(np.float32)
+    dones_after = rng.random((T, n)) < 0.1                 # done flag returned by step t
+    last_values = rng.normal(size=n).astype(np.float32)
+    # --- SB3's buffer: episode_starts[t] marks that the observation of step t starts an episode
+    episode_starts = np.zeros((T, n), dtype=np.float32)
+    episode_starts[1:] = dones_after[:-1]
+    dones = dones_after[-1].astype(np.float32)
+    advantages = np.zeros((T, n), dtype=np.float32)
+    last_gae_lam = 0
+    for step in reversed(range(T)):
+        if step == T - 1:
+            next_non_terminal = 1.0 - dones
+            next_values = last_values
+        else:
+            next_non_terminal = 1.0 - episode_starts[step + 1]
+            next_values = values[step + 1]
+        delta = rewards[step] + gamma * next_values * next_non_terminal - values[step]
+        last_gae_lam = delta + gamma * lam * next_non_terminal * last_gae_lam
+        advantages[step] = last_gae_lam
+    returns = advantages + values
+    adv, ret = gae(torch.from_numpy(rewards), torch.from_numpy(values), torch.from_numpy(dones_after),
+                   torch.from_numpy(last_values), gamma, lam)
+    np.testing.assert_allclose(adv.numpy(), advantages, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ret.numpy(), returns, rtol=1e-5, atol=1e-6)
+
+
+def test_ppo_defaults_are_the_references():
+    """main.py:39-48: learning_rate 2e-3, batch_size 128, n_epochs 40, clip_range 0.25 (+ SB3 defaults)."""
+    from reinforcement_learning_rendezvous_b200.ppo import PPOConfig
+    c = PPOConfig()
+    assert (c.learning_rate, c.batch_size, c.n_epochs, c.clip_range) == (2e-3, 128, 40, 0.25)
+    assert (c.gamma, c.gae_lambda, c.ent_coef, c.vf_coef, c.max_grad_norm) == (0.99, 0.95, 0.0, 0.5, 0.5)
