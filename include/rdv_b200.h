@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RDV_ABI_VERSION 14
+#define RDV_ABI_VERSION 15
 #define RDV_OBS_DIM 17          /* rendezvous_env.py:133-137 Box(-1, 1, (17,), float32) */
 #define RDV_ACT_DIM 6           /* rendezvous_env.py:140-144 Box(-1, 1, (6,),  float32) */
 #define RDV_N_UNIFORMS 24       /* draws consumed by one reset(): rendezvous_env.py:229-250 */
@@ -118,6 +118,13 @@ typedef struct RdvState {
     double  *f64;     /* [RDV_NF64][ld] */
     int32_t *i32;     /* [RDV_NI32][ld] */
     int64_t  ld;      /* leading dimension (>= n), in elements */
+    /* Per-env parameter batches (the sensitivity-sweep axes of sensitivity_analysis.py:97-134 as ONE batch): a
+     * device array of derived RdvParams and, for every block of 32 consecutive envs, the index of the entry its envs
+     * use.  NULL: every env uses the RdvParams passed to the call.  With a table the call's RdvParams only selects the
+     * kernel family (all entries must share iso_c / iso_t / integrator with it); supported for the reference's
+     * isotropic bodies with the RK45 integrator. */
+    const struct RdvParams *param_table;   /* nullable, device, [entries]                       */
+    const int32_t *param_block;            /* device, [ceil(n / 32)]: entry of envs 32 b .. 32 b + 31 */
 } RdvState;
 
 /* Inputs/outputs of one batched step.  Nullable members are marked. */

@@ -35,11 +35,11 @@ def __getattr__(name):
     if name == "MlpPolicy":
         from .policy import MlpPolicy
         return MlpPolicy
-    if name in ("evaluate", "evaluate_batch", "evaluate_sweep"):
+    if name in ("evaluate", "evaluate_batch", "evaluate_sweep", "sensitivity_grid"):
         from . import monte_carlo
         return getattr(monte_carlo, name)
     raise AttributeError(name)
 
 
 __all__ = ["BatchedRendezvousEnv", "RendezvousEnv", "RendezvousVecEnv", "make_env", "make_vec_env", "copy_env",
-           "MlpPolicy", "evaluate", "evaluate_batch", "evaluate_sweep", "make_params", "build_native"]
+           "MlpPolicy", "evaluate", "evaluate_batch", "evaluate_sweep", "sensitivity_grid", "make_params", "build_native"]

@@ -27,7 +27,7 @@ HOST_LIB = os.path.join(PKG_DIR, "_rdv_host" + (sysconfig.get_config_var("EXT_SU
 SOURCES = ("rdv_b200.cu",)
 HEADERS = ("rdv_math.cuh", "rdv_env.cuh", "rdv_step.cuh", "rdv_policy.cuh", "rdv_policy_tc.cuh")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 OBS_DIM, ACT_DIM, N_UNIFORMS = 17, 6, 24
 
 # rows of RdvState.f64 / RdvState.i32, statistics slots, episode-record columns (rdv_b200.h)
@@ -78,7 +78,8 @@ class RdvParams(C.Structure):
 
 
 class RdvState(C.Structure):
-    _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p), ("ld", C.c_int64)]
+    _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p), ("ld", C.c_int64), ("param_table", C.c_void_p),
+                ("param_block", C.c_void_p)]
 
 
 class RdvStepIO(C.Structure):

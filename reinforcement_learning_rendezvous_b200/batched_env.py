@@ -31,7 +31,7 @@ def _stream_ptr(device) -> C.c_void_p:
 
 
 class ParamGroup:
-    """A contiguous env range [lo, hi) sharing one RdvParams block (one launch per group)."""
+    """A contiguous env range [lo, hi) sharing one RdvParams block."""
 
     def __init__(self, params: N.RdvParams, lo: int, hi: int):
         self.params, self.lo, self.hi = params, int(lo), int(hi)
@@ -91,6 +91,20 @@ class BatchedRendezvousEnv:
             groups = [ParamGroup(make_params(**ctor_kwargs), 0, n)]
         self.groups = groups
         self.params = groups[0].params
+        # Per-env parameter batches travel as a device table of RdvParams + one entry index per block of 32 envs, so
+        # that every method is ONE launch over the whole batch (RdvState.param_table).  The table form exists for the
+        # reference's bodies with the RK45 integrator; anything else falls back to one launch per group.
+        self.param_table = self.param_block = None
+        self._units = groups
+        if len(groups) > 1 and all(g.params.iso_c and g.params.iso_t and g.params.integrator == N.INTEGRATOR_RK45
+                                   for g in groups):
+            raw = b"".join(bytes(g.params) for g in groups)
+            self.param_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+            blocks = np.zeros((n + 31) // 32, dtype=np.int32)
+            for gi, g in enumerate(groups):
+                blocks[g.lo // 32:(g.hi + 31) // 32] = gi
+            self.param_block = torch.as_tensor(blocks, device=self.device)
+            self._units = [ParamGroup(groups[0].params, 0, n)]
 
         # leading dimension padded to 32 envs so every SoA row starts 256-byte aligned
         self.ld = ld = (n + 31) // 32 * 32 if ld is None else int(ld)
@@ -134,7 +148,10 @@ class BatchedRendezvousEnv:
         return self.reset_rows.data_ptr() + 8 * g.lo
 
     def _state_of(self, g: ParamGroup) -> N.RdvState:
-        return N.RdvState(self.f64.data_ptr() + 8 * g.lo, self.i32.data_ptr() + 4 * g.lo, self.ld)
+        if self.param_table is not None:
+            return N.RdvState(self.f64.data_ptr(), self.i32.data_ptr(), self.ld, self.param_table.data_ptr(),
+                              self.param_block.data_ptr())
+        return N.RdvState(self.f64.data_ptr() + 8 * g.lo, self.i32.data_ptr() + 4 * g.lo, self.ld, None, None)
 
     def enable_host_block(self):
         """Re-home everything one ``step`` returns to a host-side VecEnv into ONE contiguous device block, so that a
@@ -189,7 +206,7 @@ class BatchedRendezvousEnv:
         stream = _stream_ptr(self.device)
         blk = self.host_block is not None
         with torch.cuda.device(self.device):
-            for gi, g in enumerate(self.groups):
+            for gi, g in enumerate(self._units):
                 io = N.RdvStepIO(
                     actions.data_ptr() + g.lo * N.ACT_DIM * esz, act_f64, mode,
                     self.obs.data_ptr() + g.lo * N.OBS_DIM * 4, self.reward.data_ptr() + g.lo * 8,
@@ -257,12 +274,13 @@ class BatchedRendezvousEnv:
             if self.auto_reset:
                 raise ValueError("monte_carlo mode needs an env with auto_reset=False")
             mc_out = torch.empty((n, N.MC_NCOL), dtype=torch.float64, device=dev)
-        if len(self.groups) > 1 and (rew is not None or don is not None or obs_steps is not None or act_out is not None
+        if len(self._units) > 1 and (rew is not None or don is not None or obs_steps is not None or act_out is not None
                                      or actions is not None):
-            raise NotImplementedError("per-step records / tensor actions with param_batches: use step()")
+            raise NotImplementedError("per-step records / tensor actions with param_batches of general-inertia or "
+                                      "closed-form groups (one launch per group): use step()")
         stream = _stream_ptr(dev)
         with torch.cuda.device(dev):
-            for g in self.groups:
+            for g in self._units:
                 io = N.RdvRolloutIO(
                     steps, source, int(self.auto_reset), 0,
                     actions.data_ptr() if actions is not None else None,
@@ -306,7 +324,7 @@ class BatchedRendezvousEnv:
                 raise ValueError(f"uniforms must have shape ({self.num_envs}, {N.N_UNIFORMS})")
         stream = _stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            for g in self.groups:
+            for g in self._units:
                 if mask is not None:
                     m_ptr = mask.data_ptr() + g.lo
                 if uniforms is not None:
@@ -323,7 +341,7 @@ class BatchedRendezvousEnv:
         out = torch.empty((self.num_envs, N.OBS_DIM), dtype=torch.float32, device=self.device) if out is None else out
         stream = _stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            for g in self.groups:
+            for g in self._units:
                 st = self._state_of(g)
                 N.check(self.lib.rdv_observe(C.byref(g.params), C.byref(st), out.data_ptr() + g.lo * N.OBS_DIM * 4,
                                              g.n, stream), "rdv_observe")
@@ -339,7 +357,7 @@ class BatchedRendezvousEnv:
         koz = torch.empty(n, dtype=torch.float64, device=dev)
         stream = _stream_ptr(dev)
         with torch.cuda.device(dev):
-            for g in self.groups:
+            for g in self._units:
                 st = self._state_of(g)
                 N.check(self.lib.rdv_errors(C.byref(g.params), C.byref(st), err.data_ptr() + g.lo * 32,
                                             col.data_ptr() + g.lo, suc.data_ptr() + g.lo, koz.data_ptr() + g.lo * 8,
@@ -350,7 +368,7 @@ class BatchedRendezvousEnv:
         """Recompute collided/success from the current state the way reset() does (:260-261)."""
         stream = _stream_ptr(self.device)
         with torch.cuda.device(self.device):
-            for g in self.groups:
+            for g in self._units:
                 st = self._state_of(g)
                 N.check(self.lib.rdv_refresh_flags(C.byref(g.params), C.byref(st), g.n, stream), "rdv_refresh_flags")
 
@@ -433,6 +451,7 @@ class BatchedRendezvousEnv:
         other.__dict__.update(self.__dict__)
         other.groups = [ParamGroup(copy_params(g.params), g.lo, g.hi) for g in self.groups]
         other.params = other.groups[0].params
+        other._units = other.groups if self.param_table is None else [ParamGroup(other.params, 0, self.num_envs)]
         for name in ("f64", "i32", "obs", "reward", "done", "terminal_obs", "end_reason", "episode_record"):
             setattr(other, name, getattr(self, name).clone())
         if self.host_block is not None:

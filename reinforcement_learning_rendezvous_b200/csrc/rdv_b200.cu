@@ -80,6 +80,15 @@ RDV_DEV void reduce_stats(const StepStats &st, double *g_stats, double (*s_stats
     }
 }
 
+// The constants of env `env`: the call's RdvParams (constant bank), or -- per-env parameter batches -- the table entry
+// of the env's block of 32.  All lanes of a warp address envs of one block, so the loads are warp-uniform.
+template <bool TABLE>
+RDV_DEV const RdvParams &params_of(const RdvParams &Pc, const RdvState &S, const int64_t env)
+{
+    if constexpr (TABLE) return S.param_table[S.param_block[env >> 5]];
+    else return Pc;
+}
+
 RDV_DEV double pair_swap(double v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 RDV_DEV int pair_swap(int v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 
@@ -106,8 +115,8 @@ RDV_DEV int pair_swap(int v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 constexpr int EPB = RDV_EPB;        // environments per CTA
 constexpr int TPB = 2 * EPB;        // threads per CTA
 
-template <bool ISO, bool ACT_F64, bool CLOSED>
-__global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __grid_constant__ RdvParams P, const RdvState S,
+template <bool ISO, bool ACT_F64, bool CLOSED, bool TABLE = false>
+__global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __grid_constant__ RdvParams Pc, const RdvState S,
                                                       const RdvStepIO io, const int64_t n, const uint64_t seed,
                                                       const int64_t env_offset)
 {
@@ -129,6 +138,7 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
     const int64_t ld = S.ld;
     const double *f = S.f64 + i;
     StepStats st = {};
+    const RdvParams &P = params_of<TABLE>(Pc, S, i);
 
     // ---- own body: attitude quaternion and body rate ----
     const int qrow = body ? RDV_QTW : RDV_QCW, wrow = body ? RDV_WTX : RDV_WCX;
@@ -404,7 +414,8 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
             const bool valid = b + team < count;
             const int local = valid ? s_reset_idx[b + team] : 0;
             const int64_t ie = base + local < n ? base + local : n - 1;
-            team_reset(P, S, seed, env_offset + ie, ie, valid, 1, nullptr, s_team[team], s_obs + local * RDV_OBS_DIM);
+            team_reset(params_of<TABLE>(Pc, S, ie), S, seed, env_offset + ie, ie, valid, 1, nullptr, s_team[team],
+                       s_obs + local * RDV_OBS_DIM);
         }
         __syncthreads();
     }
@@ -465,9 +476,11 @@ RDV_DEV void take_reset_row(const double *rw, const int64_t rs, EnvRegs &e, EnvC
     c.step = 0; c.episode += 1; c.tdv = c.tdw = c.ep_ret = 0.0;
 }
 
-template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false, bool MC = false>
+// OBS: the float32 observation is formed every step (the actor's input, a per-step record); without it only its Box
+// test is evaluated, on the raw state (obs_in_box_state), and the observation is formed once at the end of the launch.
+template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false, bool MC = false, bool TABLE = false, bool OBS = POLICY>
 __global__ void __launch_bounds__(TPB_, 1)
-rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __grid_constant__ RdvRolloutIO io,
+rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __grid_constant__ RdvRolloutIO io,
                const int64_t n, const uint64_t seed, const int64_t env_offset)
 {
     constexpr int NW = TPB_ / 32;
@@ -497,13 +510,15 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
     // the warp's observation staging row; with the fused actor it borrows the group's activation tile, which is
     // only live between the step barrier and the end of the actor's third layer
     float *obs_stage = POLICY ? ts->al[warp >> 2] + (warp & 3) * (32 * RDV_OBS_DIM) : s_obs[POLICY ? 0 : warp];
-    // the float32 observation is formed every step only when something consumes it
-    const bool want_obs = POLICY || io.obs_steps != nullptr;
-    // this CTA's slice [lo, hi) and its passes
-    const int64_t lo = n * (int64_t)blockIdx.x / gridDim.x, hi = n * ((int64_t)blockIdx.x + 1) / gridDim.x;
+    constexpr bool want_obs = POLICY || OBS;
+    // this CTA's slice [lo, hi) and its passes; with a parameter table the slices are cut at multiples of 32 envs so
+    // that a warp never straddles two parameter blocks
+    const int64_t units = TABLE ? (n + 31) / 32 : n, unit = TABLE ? 32 : 1;
+    const int64_t lo = unit * (units * (int64_t)blockIdx.x / gridDim.x);
+    const int64_t hi_raw = unit * (units * ((int64_t)blockIdx.x + 1) / gridDim.x), hi = hi_raw < n ? hi_raw : n;
     const int64_t span = hi - lo;
     const int passes = (int)((span + TPB_ - 1) / TPB_);
-    const int64_t chunk = passes > 0 ? (span + passes - 1) / passes : 0;
+    const int64_t chunk = TABLE ? TPB_ : (passes > 0 ? (span + passes - 1) / passes : 0);
     StepStats st = {};
 
     for (int pass = 0; pass < passes; ++pass) {
@@ -514,6 +529,7 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
         const int64_t i = active ? i_raw : c_hi - 1;           // idle lanes shadow the last env (no stores)
         const int64_t env_id = env_offset + i;
         const int rows_w = (int)((c_hi - warp_base) < 32 ? ((c_hi - warp_base) > 0 ? (c_hi - warp_base) : 0) : 32);
+        const RdvParams &P = params_of<TABLE>(Pc, S, i);
 
         EnvRegs e;
         EnvCounters c;
@@ -655,8 +671,7 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
                 }
             } else {
                 env_advance<ISO, CLOSED, (TPB_ <= RDV_LOCKSTEP_MAX_TPB)>(P, e, t, rk_acc, rk_rej, fail);
-                if (want_obs) r = env_evaluate<true>(P, e, t.fuel, c, ov);
-                else r = env_evaluate<false>(P, e, t.fuel, c, ov);
+                r = env_evaluate<want_obs>(P, e, t.fuel, c, ov);
             }
             const bool done = r.done && active;
             if (active) {
@@ -711,7 +726,7 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
                 }
             }
             // ---- per-step observation record (post-reset for finished envs), coalesced via the warp's row ----
-            if (io.obs_steps) {
+            if (want_obs && io.obs_steps) {
                 float *o = obs_stage + lane * RDV_OBS_DIM;
 #pragma unroll
                 for (int j = 0; j < RDV_OBS_DIM; ++j) o[j] = ov[j];
@@ -768,7 +783,8 @@ rollout_kernel(const __grid_constant__ RdvParams P, const RdvState S, const __gr
 // reset() for masked envs (rendezvous_env.py:223-270): 8 lanes per env (team_reset), 16 envs per CTA.
 // Draws come from Philox or from the caller's uniforms (test hook).
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ RdvParams P, const RdvState S,
+template <bool TABLE>
+__global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ RdvParams Pc, const RdvState S,
                                                     const uint8_t *mask, const double *uniforms, float *obs,
                                                     int64_t n, uint64_t seed, int64_t env_offset, int bump)
 {
@@ -777,15 +793,17 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ RdvP
     const int64_t i_raw = (int64_t)blockIdx.x * (128 / RDV_TEAM) + team;
     const int64_t i = i_raw < n ? i_raw : n - 1;
     const bool valid = i_raw < n && (!mask || mask[i]);
-    team_reset(P, S, seed, env_offset + i, i, valid, bump, uniforms ? uniforms + RDV_N_UNIFORMS * i : nullptr,
+    team_reset(params_of<TABLE>(Pc, S, i), S, seed, env_offset + i, i, valid, bump, uniforms ? uniforms + RDV_N_UNIFORMS * i : nullptr,
                s_team[team], obs ? obs + RDV_OBS_DIM * i : nullptr);
 }
 
-__global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ RdvParams P, const RdvState S,
+template <bool TABLE>
+__global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ RdvParams Pc, const RdvState S,
                                                       float *obs, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const RdvParams &P = params_of<TABLE>(Pc, S, i);
     EnvRegs e;
     load_env(S, i, e);
     float ov[RDV_OBS_DIM];
@@ -795,12 +813,14 @@ __global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ Rd
 }
 
 // get_errors / check_collision / check_success / dist_from_koz for evaluators
-__global__ void __launch_bounds__(128) errors_kernel(const __grid_constant__ RdvParams P, const RdvState S,
+template <bool TABLE>
+__global__ void __launch_bounds__(128) errors_kernel(const __grid_constant__ RdvParams Pc, const RdvState S,
                                                      double *errors, uint8_t *collision, uint8_t *success,
                                                      double *koz, int64_t n, int refresh_flags)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const RdvParams &P = params_of<TABLE>(Pc, S, i);
     EnvRegs e;
     load_env(S, i, e);
     const Rot Rc = rot_from_quat(e.qc), Rt = rot_from_quat(e.qt);
@@ -939,6 +959,8 @@ static int check_state(const RdvState *s, int64_t n)
     if (!s || !s->f64 || !s->i32) return RDV_ERR_NULL;
     if (n < 0 || s->ld < n) return RDV_ERR_SIZE;
     if (((uintptr_t)s->f64 & 7) || ((uintptr_t)s->i32 & 3)) return RDV_ERR_ALIGN;
+    if (s->param_table && !s->param_block) return RDV_ERR_NULL;
+    if (((uintptr_t)s->param_table & 7) || ((uintptr_t)s->param_block & 3)) return RDV_ERR_ALIGN;
     return RDV_OK;
 }
 static int launch_status()
@@ -1146,7 +1168,12 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
     if ((uintptr_t)io->reward_f32 & 3) return RDV_ERR_ALIGN;
 #define RDV_LAUNCH(ISO_, F64_, CL_) \
     step_kernel<ISO_, F64_, CL_><<<grid, TPB, 0, st>>>(*p, *s, *io, n, seed, env_offset)
-    if (closed) { if (io->act_f64) RDV_LAUNCH(true, true, true); else RDV_LAUNCH(true, false, true); }
+    if (s->param_table) {
+        if (!iso || closed) return RDV_ERR_UNSUPPORTED;      // parameter tables: the reference's bodies, RK45
+        if (io->act_f64) step_kernel<true, true, false, true><<<grid, TPB, 0, st>>>(*p, *s, *io, n, seed, env_offset);
+        else step_kernel<true, false, false, true><<<grid, TPB, 0, st>>>(*p, *s, *io, n, seed, env_offset);
+    }
+    else if (closed) { if (io->act_f64) RDV_LAUNCH(true, true, true); else RDV_LAUNCH(true, false, true); }
     else if (iso) { if (io->act_f64) RDV_LAUNCH(true, true, false); else RDV_LAUNCH(true, false, false); }
     else { if (io->act_f64) RDV_LAUNCH(false, true, false); else RDV_LAUNCH(false, false, false); }
 #undef RDV_LAUNCH
@@ -1187,7 +1214,8 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     if (mc && (io->auto_reset || ((uintptr_t)io->mc_out & 7))) return io->auto_reset ? RDV_ERR_UNSUPPORTED : RDV_ERR_ALIGN;
     if ((uintptr_t)io->reset_rows & 7) return RDV_ERR_ALIGN;
     // development / test override of the CTA size (rdv_tune): 256 | 384 | 448 | 512; the evaluator mode has one size
-    const int force_tpb = mc ? 256 : g_tune_tpb.load(std::memory_order_relaxed);
+    const bool table = s->param_table != nullptr;
+    const int force_tpb = (mc || table) ? 256 : g_tune_tpb.load(std::memory_order_relaxed);
     const int64_t max_tpb = force_tpb > 0 ? force_tpb : 512;
     const int64_t passes = (per_cta + max_tpb - 1) / max_tpb;
     const int64_t chunk = force_tpb > 0 ? force_tpb : (per_cta + passes - 1) / passes;
@@ -1203,16 +1231,27 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     }
 #define RDV_ROWS_SMEM(T_) ((size_t)(T_ / 32) * 32 * RDV_NEXT_ROW * sizeof(double))
 #define RDV_LAUNCH_R(ISO_, CL_, T_) RDV_LAUNCH_K((rollout_kernel<ISO_, CL_, T_, false, false>), T_, RDV_ROWS_SMEM(T_))
+    // per-step observation records: one CTA shape with the observation formed every step (every shape gives the same bits)
+#define RDV_LAUNCH_OBS(ISO_, CL_) \
+    RDV_LAUNCH_K((rollout_kernel<ISO_, CL_, 256, false, false, false, true>), 256, RDV_ROWS_SMEM(256))
 #define RDV_PICK_R(ISO_, CL_)                                 \
-    if (chunk <= 256) RDV_LAUNCH_R(ISO_, CL_, 256)            \
+    if (io->obs_steps) RDV_LAUNCH_OBS(ISO_, CL_)              \
+    else if (chunk <= 256) RDV_LAUNCH_R(ISO_, CL_, 256)       \
     else if (chunk <= 384) RDV_LAUNCH_R(ISO_, CL_, 384)       \
     else if (chunk <= 448) RDV_LAUNCH_R(ISO_, CL_, 448)       \
     else RDV_LAUNCH_R(ISO_, CL_, 512)
 #define RDV_LAUNCH_P(T_) RDV_LAUNCH_K((rollout_kernel<true, false, T_, true, false>), T_, sizeof(tc::TileSmem))
-    if (mc) {
+    if (table) {
+        if (!iso || closed) return RDV_ERR_UNSUPPORTED;      // parameter tables: the reference's bodies, RK45
+        if (mc && policy) RDV_LAUNCH_K((rollout_kernel<true, false, 256, true, true, true>), 256, sizeof(tc::TileSmem))
+        else if (mc) RDV_LAUNCH_K((rollout_kernel<true, false, 256, false, true, true, true>), 256, RDV_ROWS_SMEM(256))
+        else if (policy) RDV_LAUNCH_K((rollout_kernel<true, false, 256, true, false, true>), 256, sizeof(tc::TileSmem))
+        else RDV_LAUNCH_K((rollout_kernel<true, false, 256, false, false, true, true>), 256, RDV_ROWS_SMEM(256))
+    }
+    else if (mc) {
         if (!iso || closed) return RDV_ERR_UNSUPPORTED;      // the evaluator mode is built for the reference's env
         if (policy) RDV_LAUNCH_K((rollout_kernel<true, false, 256, true, true>), 256, sizeof(tc::TileSmem))
-        else RDV_LAUNCH_K((rollout_kernel<true, false, 256, false, true>), 256, RDV_ROWS_SMEM(256))
+        else RDV_LAUNCH_K((rollout_kernel<true, false, 256, false, true, false, true>), 256, RDV_ROWS_SMEM(256))
     }
     else if (policy) {
         if (!iso || closed) return RDV_ERR_UNSUPPORTED;      // the fused policy is built for the reference's env
@@ -1223,7 +1262,8 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     }
     else if (closed) { RDV_PICK_R(true, true) }
     else if (iso) { RDV_PICK_R(true, false) }
-    else RDV_LAUNCH_R(false, false, 256)
+    else RDV_LAUNCH_OBS(false, false)                          // general inertia / held torque: one shape
+#undef RDV_LAUNCH_OBS
 #undef RDV_LAUNCH_P
 #undef RDV_PICK_R
 #undef RDV_LAUNCH_R
@@ -1240,8 +1280,13 @@ int rdv_reset(const RdvParams *p, const RdvState *s, const uint8_t *mask, const 
     if (rc) return rc;
     if (n == 0) return RDV_OK;
     const int64_t per_cta = 128 / RDV_TEAM;
-    reset_kernel<<<(unsigned)((n + per_cta - 1) / per_cta), 128, 0, (cudaStream_t)cuda_stream>>>(
-        *p, *s, mask, uniforms, obs, n, seed, env_offset, bump_episode ? 1 : 0);
+    const unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
+    if (s->param_table)
+        reset_kernel<true><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, mask, uniforms, obs, n, seed, env_offset,
+                                                                        bump_episode ? 1 : 0);
+    else
+        reset_kernel<false><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, mask, uniforms, obs, n, seed, env_offset,
+                                                                         bump_episode ? 1 : 0);
     return launch_status();
 }
 
@@ -1251,7 +1296,8 @@ int rdv_observe(const RdvParams *p, const RdvState *s, float *obs, int64_t n, vo
     int rc = check_state(s, n);
     if (rc) return rc;
     if (n == 0) return RDV_OK;
-    observe_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, obs, n);
+    if (s->param_table) observe_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, obs, n);
+    else observe_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, obs, n);
     return launch_status();
 }
 
@@ -1262,8 +1308,12 @@ int rdv_errors(const RdvParams *p, const RdvState *s, double *errors, uint8_t *c
     int rc = check_state(s, n);
     if (rc) return rc;
     if (n == 0) return RDV_OK;
-    errors_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, errors, collision,
-                                                                                       success, koz, n, 0);
+    if (s->param_table)
+        errors_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, errors, collision,
+                                                                                                 success, koz, n, 0);
+    else
+        errors_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, errors, collision,
+                                                                                                  success, koz, n, 0);
     return launch_status();
 }
 
@@ -1273,8 +1323,12 @@ int rdv_refresh_flags(const RdvParams *p, const RdvState *s, int64_t n, void *cu
     int rc = check_state(s, n);
     if (rc) return rc;
     if (n == 0) return RDV_OK;
-    errors_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, nullptr, nullptr,
-                                                                                       nullptr, nullptr, n, 1);
+    if (s->param_table)
+        errors_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, nullptr, nullptr,
+                                                                                                 nullptr, nullptr, n, 1);
+    else
+        errors_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, nullptr, nullptr,
+                                                                                                  nullptr, nullptr, n, 1);
     return launch_status();
 }
 

@@ -141,6 +141,21 @@ def mc_columns(mc: np.ndarray, dt: float) -> dict:
         att_error=np.degrees(mc[:, N.MC_ATT_ERR]), rot_error=np.degrees(mc[:, N.MC_ROT_ERR]))
 
 
+def sensitivity_grid(include_invalid: bool = False) -> list:
+    """The parameter grid of /root/reference/sensitivity_analysis.py:97-134 as a list of ``make_env`` config dicts:
+    rc0 {10..50} x wt0 rad{0, 1.25, 2.5} x koz_radius {2, 5, 10} x corridor_half_angle rad{15, 25, 30, 35, 45} x
+    h {400, 600, 800, 1000, 2000} km x dt {0.25, 0.5, 1, 2, 4}.  koz_radius = 2 violates the constructor's assertion
+    ``|rd| < koz_radius`` (rendezvous_env.py:155 -- the reference raises there), so those 1,875 of the 5,625
+    combinations are left out unless ``include_invalid``."""
+    import itertools
+    rad = np.radians
+    axes = dict(rc0=[10, 20, 30, 40, 50], wt0=[float(rad(v)) for v in (0, 1.25, 2.5)], koz_radius=[2, 5, 10],
+                corridor_half_angle=[float(rad(v)) for v in (15, 25, 30, 35, 45)],
+                h=[400e3, 600e3, 800e3, 1000e3, 2000e3], dt=[0.25, 0.5, 1, 2, 4])
+    grid = [dict(zip(axes, combo)) for combo in itertools.product(*axes.values())]
+    return grid if include_invalid else [g for g in grid if g["koz_radius"] > 2]
+
+
 def evaluate_sweep(policy, param_sets, episodes_per_set=1024, reward_kwargs=None, device="cuda", seed=0,
                    rank=0, world_size=1, **common) -> list:
     """Sensitivity sweep as ONE batch (BASELINE.json configs[4]; the axes of sensitivity_analysis.py:97-134 --

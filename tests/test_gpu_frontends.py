@@ -394,3 +394,64 @@ def test_sensitivity_sweep_as_one_batch():
     assert res[5]["success_rate"] <= nominal["success_rate"]      # 30 m out: outside what the policy was trained on
     for r in res:
         assert np.isfinite(r["mean_return"]) and 0 < r["mean_length_s"] <= 60
+
+
+def test_full_sensitivity_grid_is_one_launch_and_equals_separate_envs():
+    """BASELINE.json configs[4]: every valid combination of the grid of sensitivity_analysis.py:97-134 (3,750 parameter
+    sets) as ONE batch -- a device table of RdvParams + one entry index per block of 32 envs, so that reset, step and
+    rollout are one launch each -- gives the same bits as separate envs built with those constructor arguments, and
+    agrees with the C oracle."""
+    import torch
+    from oracle import c_oracle as CO
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, sensitivity_grid
+    from reinforcement_learning_rendezvous_b200.environment_utils import config_to_kwargs
+    grid = sensitivity_grid()
+    assert len(grid) == 3750 and len(sensitivity_grid(include_invalid=True)) == 5625
+    per = 32
+    kws = [{k: v for k, v in config_to_kwargs(g, stochastic=True).items() if v is not None} for g in grid]
+    n = per * len(grid)
+    env = BatchedRendezvousEnv(n, seed=6, auto_reset=True, param_batches=[(per, kw) for kw in kws])
+    assert env.param_table is not None and len(env._units) == 1          # one launch for the whole batch
+    env.reset()
+    g = torch.Generator(device=env.device)
+    g.manual_seed(0)
+    K = 6
+    acts = torch.rand((K, n, 6), dtype=torch.float64, device=env.device, generator=g) * 2 - 1
+    rews = []
+    for k in range(K):
+        rews.append(env.step(acts[k])[1].clone())
+    out = env.rollout(K, actions=acts, record_rewards=True, record_dones=True)      # records with a table: allowed now
+    rews2 = out["rewards"]
+    state = env.get_state()
+    rng = np.random.default_rng(1)
+    for gi in [0, 1, len(grid) - 1] + rng.choice(len(grid), 9, replace=False).tolist():
+        lo = gi * per
+        e = BatchedRendezvousEnv(per, seed=6, env_offset=lo, auto_reset=True, **kws[gi])
+        e.reset()
+        for k in range(K):
+            assert torch.equal(e.step(acts[k, lo:lo + per].contiguous())[1], rews[k][lo:lo + per]), (gi, k)
+        o2 = e.rollout(K, actions=acts[:, lo:lo + per].contiguous(), record_rewards=True)
+        assert torch.equal(o2["rewards"], rews2[:, lo:lo + per]), gi
+        assert torch.equal(e.get_state(), state[lo:lo + per]), gi
+        assert torch.equal(e.i32[:, :per], env.i32[:, lo:lo + per]), gi
+        # and against the C oracle (first step from the same reset draws)
+        orc = CO.COracleBatch(CO.make_params(**kws[gi]), per)
+        orc.reset_from_uniforms(CO.philox_uniforms(6, lo + np.arange(per), np.ones(per, dtype=np.int32)))
+        _, o_rew, _ = orc.step(acts[0, lo:lo + per].cpu().numpy())
+        assert rel_err(rews[0][lo:lo + per].cpu().numpy(), o_rew) <= REL_TOL, gi
+    st = env.read_stats()
+    assert st["steps"] == 2 * K * n and st["failures"] == 0
+
+
+def test_sweep_sharding_is_invariant():
+    """evaluate_sweep over parameter sets sharded as two ranks == the unsharded sweep (global env ids key the reset
+    streams), and its evaluator-mode launch agrees with a per-step evaluation of the same blocks."""
+    from reinforcement_learning_rendezvous_b200 import evaluate_sweep
+    pol = _policy()
+    sets = [dict(), dict(h=400e3), dict(dt=0.5), dict(koz_radius=10.0), dict(rc0=20.0), dict(corridor_half_angle=0.6)]
+    whole = evaluate_sweep(pol, sets, episodes_per_set=256, seed=3, t_max=60)
+    parts = evaluate_sweep(pol, sets, episodes_per_set=256, seed=3, t_max=60, rank=0, world_size=2) + \
+        evaluate_sweep(pol, sets, episodes_per_set=256, seed=3, t_max=60, rank=1, world_size=2)
+    assert len(parts) == len(whole) == len(sets)
+    for a, b in zip(whole, parts):
+        assert a == b

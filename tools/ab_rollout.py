@@ -47,11 +47,13 @@ def main():
         if a == "--policy":
             policy = "1"
     for rep in range(2):
-        for lib in libs:
+        for spec in libs:
+            lib, *sets = spec.split(":")                      # build/x.so:RDV_RESET_REFILL=16
             env = dict(os.environ, RDV_B200_LIB=os.path.abspath(lib))
+            env.update(dict(kv.split("=", 1) for kv in sets))
             out = subprocess.run([sys.executable, "-c", CHILD, str(n), policy], env=env, capture_output=True, text=True)
             line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-600:]
-            print(f"{os.path.basename(lib):28s} {line}", flush=True)
+            print(f"{os.path.basename(spec):44s} {line}", flush=True)
 
 
 if __name__ == "__main__":
