@@ -190,7 +190,7 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, RendezvousVecEnv, _native as N
-    from reinforcement_learning_rendezvous_b200.distributed import all_reduce_stats
+    from reinforcement_learning_rendezvous_b200.distributed import OverlappedStatsReducer, all_reduce_stats
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device for its own arm (there is no CPU fallback); "
@@ -229,28 +229,24 @@ def run_cuda(args):
     W_eff = max(W, 3)
     env.rollout(W_eff, action_seed=args.seed + 1, step_base=0)
     done_steps = W_eff
-    stats_bufs = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
-    snaps = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
-    total_stats = torch.zeros(N.NSTATS, dtype=torch.float64, device=dev)
+    red = OverlappedStatsReducer(dev)
     # calibration (untimed; doubles as warm-up of the K-step launch shape and of every torch op and the collective
     # the timed loop issues): how long is one repeat?
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for warm in range(2):
         barrier()
         c0.record()
-        stats_bufs[0].zero_()
-        for kl in launches:
-            env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
-            done_steps += kl
-        snaps[0].copy_(stats_bufs[0])
-        w = all_reduce_stats(snaps[0], async_op=True)
-        if w is not None:
-            w.wait()
-        total_stats += snaps[0]
+        for rr in range(2):
+            env.stats = red.begin()
+            for kl in launches:
+                env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
+                done_steps += kl
+            red.end()
+        red.finish()
         c1.record()
         torch.cuda.synchronize()
-    total_stats.zero_()
-    t_rep = max_over_ranks(c0.elapsed_time(c1))
+    red.reset()
+    t_rep = max_over_ranks(c0.elapsed_time(c1)) / 2
     n_l = len(launches)
     R = max(1, math.ceil(args.min_region_ms / max(t_rep, 1e-3)), math.ceil(25 / n_l))
     R = min(R, 4000)
@@ -261,33 +257,19 @@ def run_cuda(args):
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(R * n_l + 1)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pending = None                                     # (work handle, snapshot) of the previous rollout's reduction
     barrier()
     e0.record()
     ev[0].record()
     j = 0
     for r in range(R):
-        buf = stats_bufs[r & 1]
-        buf.zero_()
-        env.stats = buf
+        env.stats = red.begin()
         for kl in launches:
             env.rollout(kl, action_seed=args.seed + 1, step_base=done_steps)
             done_steps += kl
             j += 1
             ev[j].record()
-        # the reduction of the PREVIOUS rollout was issued before this rollout's launches: it ran beside them
-        if pending is not None:
-            work, snap = pending
-            if work is not None:
-                work.wait()
-            total_stats += snap
-        snap = snaps[r & 1]
-        snap.copy_(buf)
-        pending = (all_reduce_stats(snap, async_op=True), snap)    # NCCL when N > 1 (sum over ranks), else a no-op
-    work, snap = pending
-    if work is not None:
-        work.wait()
-    total_stats += snap
+        red.end()          # waits for rollout r - 1's all-reduce (it ran beside this rollout), issues rollout r's
+    total_stats = red.finish()
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -301,7 +283,7 @@ def run_cuda(args):
     full = [ev[q].elapsed_time(ev[q + 1]) for q in range(R * n_l) if launches[q % n_l] == KL]
     t_launch = sum(full) / len(full)
     t_step = t_launch / KL
-    env.stats = stats_bufs[0]
+    env.stats = red.bufs[0]
 
     # fp64 peak: DFMA probe, best of 6
     blocks, threads, iters = 148 * 8, 256, 4096
@@ -434,21 +416,14 @@ def run_cuda(args):
                 rt = torch.tensor([reps], dtype=torch.int64, device=dev)
                 dist.all_reduce(rt, op=dist.ReduceOp.MAX)
                 reps = int(rt[0])
-            bufs = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
-            snp = [torch.zeros(N.NSTATS, dtype=torch.float64, device=dev) for _ in range(2)]
-            pend = None
+            pred = OverlappedStatsReducer(dev)
             barrier()
             q0.record()
             for r in range(reps):
-                penv.stats = bufs[r & 1]
-                penv.stats.zero_()
+                penv.stats = pred.begin()
                 penv.rollout(kl, policy=pol)
-                if pend is not None and pend is not False:
-                    pend.wait()
-                snp[r & 1].copy_(penv.stats)
-                pend = all_reduce_stats(snp[r & 1], async_op=True) or False
-            if pend:
-                pend.wait()
+                pred.end()
+            pred.finish()
             q1.record()
             barrier()
             pms = max_over_ranks(q0.elapsed_time(q1))
@@ -457,7 +432,6 @@ def run_cuda(args):
                     "steps": reps * kl, "steps_per_launch": kl, "repeats": reps, "envs_per_gpu": m,
                     "total_envs": world * m, "policy": what}
 
-        env.stats = stats_bufs[0]
         policy_rollout = policy_leg(env, min(KL, max(K, 16)))
         big = BatchedRendezvousEnv(2 * n, device=dev, seed=args.seed, env_offset=rank * 2 * n, auto_reset=True)
         big.reset()

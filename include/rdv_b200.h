@@ -279,7 +279,7 @@ int rdv_policy_forward_ffma(const RdvPolicy *pi, const float *obs, float *action
 
 /* Development / test knobs that used to be environment variables (read once at load as defaults):
  * RDV_TUNE_ROLLOUT_TPB forces the rollout CTA size (256 | 384 | 448 | 512, 0 = automatic), RDV_TUNE_RESET_REFILL sets
- * the reset prefetch period in steps (0 = reset on demand only; default 8).  Returns the previous value, or
+ * the reset prefetch period in steps (0 = reset on demand only; default 12).  Returns the previous value, or
  * RDV_ERR_SIZE for an unknown key. */
 enum { RDV_TUNE_ROLLOUT_TPB = 0, RDV_TUNE_RESET_REFILL = 1 };
 int rdv_tune(int key, int value);

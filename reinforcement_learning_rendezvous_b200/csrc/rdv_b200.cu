@@ -589,71 +589,41 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
             mc_sample(P, d, c.collided, mc);
         }
 
-        for (int k = 0; k < io.steps; ++k) {
-            // Keep the CTA's warps in the same code region (instruction-cache locality).  With the first, ~60 KB
-            // step a barrier every step was best (every 2 / 4 steps: 1 % / 8 % slower); the plane solver's step is
-            // smaller and tolerates drift: every step 12.06, every 4-8 steps 11.66, every 32 steps 11.77, never
-            // 12.1-12.2 us per step.  The fused actor keeps the barrier of every step (its staging rows alias the
-            // activation tiles of the next step's actor).
-#if RDV_SYNC_PERIOD == 1
-            __syncthreads();
-#elif RDV_SYNC_PERIOD > 1
-            if (POLICY || (k % RDV_SYNC_PERIOD) == 0) __syncthreads();
-#else
-            if (POLICY) __syncthreads();
-#endif
-            // ---- action ----
-            ActionTerms t;
+        // One env step = an action phase (actor on the tensor cores, or a tensor / Philox action) and a step phase
+        // (propagation, evaluation, in-warp reset, records), written as lambdas over the pass's registers.
+        ActionTerms t;
+        auto policy_action = [&](const int k) {
             const int64_t row = (int64_t)k * n + i;
-            if (POLICY) {
-                // the CTA's threads form groups of 128 (the last one may be smaller); a group runs its tile of envs
-                // through the actor on the tensor cores: thread = row = TMEM lane
-                float a[RDV_ACT_DIM];
-                const int g = threadIdx.x >> 7;
-                tc::tile_forward(*ts, g, threadIdx.x & 127, TPB_ - 128 * g < 128 ? TPB_ - 128 * g : 128, ov,
-                                 tmem_all + (uint32_t)g * tc::GROUP_COLS, mma_phase, a, [] {});
-                const bool sample = src == RDV_ACTIONS_POLICY_SAMPLE;
-                if (sample) {                                     // a ~ N(mean, exp(log_std)^2)
-                    float z[RDV_ACT_DIM];
-                    philox_normals(io.action_seed, env_id, io.step_base + k, z);
+            // the CTA's threads form groups of 128 (the last one may be smaller); a group runs its tile of envs
+            // through the actor on the tensor cores: thread = row = TMEM lane
+            float a[RDV_ACT_DIM];
+            const int g = threadIdx.x >> 7;
+            tc::tile_forward(*ts, g, threadIdx.x & 127, TPB_ - 128 * g < 128 ? TPB_ - 128 * g : 128, ov,
+                             tmem_all + (uint32_t)g * tc::GROUP_COLS, mma_phase, a, [] {});
+            const bool sample = src == RDV_ACTIONS_POLICY_SAMPLE;
+            if (sample) {                                     // a ~ N(mean, exp(log_std)^2)
+                float z[RDV_ACT_DIM];
+                philox_normals(io.action_seed, env_id, io.step_base + k, z);
 #pragma unroll
-                    for (int j = 0; j < RDV_ACT_DIM; ++j) a[j] = fmaf(ts->std[j], z[j], a[j]);
-                }
-                float ac[RDV_ACT_DIM];
-#pragma unroll
-                for (int j = 0; j < RDV_ACT_DIM; ++j) ac[j] = fminf(1.0f, fmaxf(-1.0f, a[j]));   // np.clip to the Box
-                if (io.actions_out && active) {
-                    // sampling: the unclipped draw (what SB3's rollout buffer stores); deterministic: the clipped
-                    // action model.predict returns
-                    const float *rec = sample ? a : ac;
-                    float2 *op = reinterpret_cast<float2 *>(reinterpret_cast<float *>(io.actions_out) + 6 * row);
-                    op[0] = make_float2(rec[0], rec[1]); op[1] = make_float2(rec[2], rec[3]);
-                    op[2] = make_float2(rec[4], rec[5]);
-                }
-#pragma unroll
-                for (int j = 0; j < RDV_ACT_DIM; ++j) a[j] = ac[j];
-                if (!MC || alive) ingest_action_f32(P, a, c, t);
-            } else if (src == RDV_ACTIONS_F32) {
-                const float2 *ap = reinterpret_cast<const float2 *>(static_cast<const float *>(io.actions) + 6 * row);
-                const float2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
-                const float a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
-                if (!MC || alive) ingest_action_f32(P, a, c, t);
-            } else {
-                double a[6];
-                if (src == RDV_ACTIONS_F64) {
-                    const double2 *ap = reinterpret_cast<const double2 *>(static_cast<const double *>(io.actions) + 6 * row);
-                    const double2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
-                    a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y; a[4] = a45.x; a[5] = a45.y;
-                } else {
-                    philox_actions(io.action_seed, env_id, io.step_base + k, a);
-                    if (io.actions_out && active) {
-                        double2 *op = reinterpret_cast<double2 *>(io.actions_out + 6 * row);
-                        op[0] = make_double2(a[0], a[1]); op[1] = make_double2(a[2], a[3]);
-                        op[2] = make_double2(a[4], a[5]);
-                    }
-                }
-                if (!MC || alive) ingest_action_f64(P, a, c, t);
+                for (int j = 0; j < RDV_ACT_DIM; ++j) a[j] = fmaf(ts->std[j], z[j], a[j]);
             }
+            float ac[RDV_ACT_DIM];
+#pragma unroll
+            for (int j = 0; j < RDV_ACT_DIM; ++j) ac[j] = fminf(1.0f, fmaxf(-1.0f, a[j]));   // np.clip to the Box
+            if (io.actions_out && active) {
+                // sampling: the unclipped draw (what SB3's rollout buffer stores); deterministic: the clipped
+                // action model.predict returns
+                const float *rec = sample ? a : ac;
+                float2 *op = reinterpret_cast<float2 *>(reinterpret_cast<float *>(io.actions_out) + 6 * row);
+                op[0] = make_float2(rec[0], rec[1]); op[1] = make_float2(rec[2], rec[3]);
+                op[2] = make_float2(rec[4], rec[5]);
+            }
+#pragma unroll
+            for (int j = 0; j < RDV_ACT_DIM; ++j) a[j] = ac[j];
+            if (!MC || alive) ingest_action_f32(P, a, c, t);
+        };
+        auto step_phase = [&](const int k) {
+            const int64_t row = (int64_t)k * n + i;
             // ---- step ----
             int rk_acc = 0, rk_rej = 0, fail = 0;
             StepResult r;
@@ -734,6 +704,56 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                 float *dst = io.obs_steps + ((int64_t)k * n + warp_base) * RDV_OBS_DIM;
                 for (int j = lane; j < rows_w * RDV_OBS_DIM; j += 32) dst[j] = obs_stage[j];
                 __syncwarp();
+            }
+        };
+
+        if constexpr (POLICY) {
+            // The fused actor keeps the CTA barrier of every step: its staging rows alias the activation tiles of the
+            // next step's actor, and the groups run best in phase.  Measured alternatives at 65,536 envs: no barrier
+            // (groups drift) 24.0 us per step against 22.7; odd groups shifted by half a step behind a barrier per
+            // half-phase (half of the warps in the actor, half in the solver at any time, so that the tiles' MMAs do
+            // not queue on the one tensor pipe) 29.2 against 22.9 -- with only half of the SM's warps in the solver
+            // the fp64 latency is no longer hidden, which costs more than the MMA queueing it removes.
+            for (int k = 0; k < io.steps; ++k) {
+                __syncthreads();
+                policy_action(k);
+                step_phase(k);
+            }
+        } else {
+            for (int k = 0; k < io.steps; ++k) {
+                // Keep the CTA's warps in the same code region (instruction-cache locality).  With the first, ~60 KB
+                // step a barrier every step was best (every 2 / 4 steps: 1 % / 8 % slower); the plane solver's step is
+                // smaller and tolerates drift: every step 12.06, every 4-8 steps 11.66, every 32 steps 11.77, never
+                // 12.1-12.2 us per step.
+#if RDV_SYNC_PERIOD == 1
+                __syncthreads();
+#elif RDV_SYNC_PERIOD > 1
+                if ((k % RDV_SYNC_PERIOD) == 0) __syncthreads();
+#endif
+                // ---- action ----
+                const int64_t row = (int64_t)k * n + i;
+                if (src == RDV_ACTIONS_F32) {
+                    const float2 *ap = reinterpret_cast<const float2 *>(static_cast<const float *>(io.actions) + 6 * row);
+                    const float2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
+                    const float a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+                    if (!MC || alive) ingest_action_f32(P, a, c, t);
+                } else {
+                    double a[6];
+                    if (src == RDV_ACTIONS_F64) {
+                        const double2 *ap = reinterpret_cast<const double2 *>(static_cast<const double *>(io.actions) + 6 * row);
+                        const double2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
+                        a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y; a[4] = a45.x; a[5] = a45.y;
+                    } else {
+                        philox_actions(io.action_seed, env_id, io.step_base + k, a);
+                        if (io.actions_out && active) {
+                            double2 *op = reinterpret_cast<double2 *>(io.actions_out + 6 * row);
+                            op[0] = make_double2(a[0], a[1]); op[1] = make_double2(a[2], a[3]);
+                            op[2] = make_double2(a[4], a[5]);
+                        }
+                    }
+                    if (!MC || alive) ingest_action_f64(P, a, c, t);
+                }
+                step_phase(k);
             }
         }
 
@@ -1003,7 +1023,7 @@ static int env_int(const char *name, int fallback)
     return v ? atoi(v) : fallback;
 }
 static std::atomic<int> g_tune_tpb{env_int("RDV_ROLLOUT_TPB", 0)};
-static std::atomic<int> g_tune_refill{env_int("RDV_RESET_REFILL", 8)};
+static std::atomic<int> g_tune_refill{env_int("RDV_RESET_REFILL", 12)};
 
 extern "C" {
 

@@ -48,6 +48,55 @@ def all_reduce_stats(stats: torch.Tensor, group=None, async_op: bool = False):
     return dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+class OverlappedStatsReducer:
+    """Per-rollout statistics summed over ranks with the collective of rollout r running BESIDE rollout r + 1.
+
+    The rollout kernels accumulate into the buffer ``begin()`` returns; ``end()`` -- called once the rollout's
+    launches are enqueued -- first waits for the PREVIOUS rollout's all-reduce (issued one rollout ago, so it had a
+    whole rollout to finish), adds it to ``total``, then snapshots this rollout's buffer and issues its all-reduce
+    asynchronously (NCCL runs it on its own stream; the two buffers / snapshots alternate so nothing is overwritten
+    while in flight).  Let the rollout leave one SM free (``BatchedRendezvousEnv.sm_reserve = 1``) so that the
+    collective's kernel does not queue behind a launch that fills every SM.  Without a process group it degrades to a
+    local running sum."""
+
+    def __init__(self, device, group=None):
+        self.group = group
+        self.bufs = [torch.zeros(N.NSTATS, dtype=torch.float64, device=device) for _ in range(2)]
+        self.snaps = [torch.zeros(N.NSTATS, dtype=torch.float64, device=device) for _ in range(2)]
+        self.total = torch.zeros(N.NSTATS, dtype=torch.float64, device=device)
+        self._pending = None
+        self._r = 0
+
+    def begin(self) -> torch.Tensor:
+        buf = self.bufs[self._r & 1]
+        buf.zero_()
+        return buf
+
+    def _drain(self):
+        if self._pending is not None:
+            work, snap = self._pending
+            if work is not None:
+                work.wait()
+            self.total += snap
+            self._pending = None
+
+    def end(self):
+        self._drain()
+        snap = self.snaps[self._r & 1]
+        snap.copy_(self.bufs[self._r & 1])
+        self._pending = (all_reduce_stats(snap, group=self.group, async_op=True), snap)
+        self._r += 1
+
+    def finish(self) -> torch.Tensor:
+        """Wait for the last collective; returns the running total over all rollouts and ranks."""
+        self._drain()
+        return self.total
+
+    def reset(self):
+        self._drain()
+        self.total.zero_()
+
+
 def stats_to_dict(stats: torch.Tensor) -> dict:
     v = stats.detach().cpu().tolist()
     d = dict(zip(N.STAT_NAMES, v))

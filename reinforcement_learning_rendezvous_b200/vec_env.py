@@ -218,14 +218,14 @@ class RendezvousVecEnv(_Base):
         ``end_reason`` (0 obs, 1 time, 2 bubble, 3 attitude).  Same data as the ``infos`` of ``step``."""
         self.step_async(actions)
         obs, rew, done, rows = self._launch_and_fetch()
-        rows = rows[np.argsort(rows["env"])]            # ascending env index; the gather also takes own memory
-        rec = rows["record"]
+        order = np.argsort(rows["env"])                 # ascending env index; every gather below takes own memory,
+        rec = rows["record"][order]                     # so no view of the pinned block outlives this call
         finished = {
-            "index": rows["env"].astype(np.int64), "terminal_observation": rows["terminal_obs"],
+            "index": rows["env"][order].astype(np.int64), "terminal_observation": rows["terminal_obs"][order],
             "episode_return": rec[:, N.EP_RETURN], "episode_length": rec[:, N.EP_LENGTH].astype(np.int64),
             "is_success": rec[:, N.EP_SUCCESS] > 0, "collided": rec[:, N.EP_COLLIDED] > 0,
             "total_delta_v": rec[:, N.EP_DELTA_V], "total_delta_w": rec[:, N.EP_DELTA_W],
-            "end_reason": rows["end_reason"].astype(np.int8),
+            "end_reason": rows["end_reason"][order].astype(np.int8),
         }
         return obs, rew, done, finished
 

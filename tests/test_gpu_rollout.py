@@ -206,7 +206,7 @@ def test_reset_prefetch_is_bit_identical():
                 for key, v in ref[4].items():  # counters exact; the fp64 sums are atomically reduced over CTAs in any order
                     assert got[4][key] == v if float(v).is_integer() else abs(got[4][key] - v) <= 1e-12 * abs(v), key
     finally:
-        _tune(N.TUNE_RESET_REFILL, 8)
+        _tune(N.TUNE_RESET_REFILL, 12)
 
 
 def test_reset_rows_carried_over_many_short_launches():

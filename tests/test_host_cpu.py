@@ -102,6 +102,16 @@ stats[2] = 10.0 * (rank + 1)  # return_sum
 all_reduce_stats(stats)
 d = stats_to_dict(stats)
 assert d["steps"] == 1001 and d["episodes"] == 3 and abs(d["mean_return"] - 10.0) < 1e-12, d
+# the overlapped per-rollout reduction of the benchmark / trainer: 5 "rollouts", collective r waited for after r + 1
+from reinforcement_learning_rendezvous_b200.distributed import OverlappedStatsReducer
+red = OverlappedStatsReducer("cpu")
+for r in range(5):
+    buf = red.begin()
+    buf[0] += 100 * (rank + 1) + r          # what this rank's rollout kernel would have accumulated
+    buf[1] += 1
+    red.end()
+total = red.finish()
+assert total[0] == sum(100 * 1 + r + 100 * 2 + r for r in range(5)) and total[1] == 10, total
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
