@@ -165,6 +165,9 @@ typedef struct RdvFinishedRow {
 /* -- constants ------------------------------------------------------------------------------ */
 int  rdv_abi_version(void);
 int  rdv_sizeof_params(void);
+/* sizeof of the ABI structs as this build sees them (a binding checks its own mirrors against these):
+ * 0 RdvParams, 1 RdvState, 2 RdvStepIO, 3 RdvRolloutIO, 4 RdvPolicy, 5 RdvFinishedRow; -1 for anything else. */
+int  rdv_sizeof(int which);
 const char *rdv_strerror(int status);
 
 /* Defaults of RendezvousEnv.__init__ (rendezvous_env.py:17-70). */

@@ -130,6 +130,7 @@ ACTIONS_F32, ACTIONS_F64, ACTIONS_PHILOX, ACTIONS_POLICY, ACTIONS_POLICY_SAMPLE 
 PROTOTYPES = {
     "rdv_abi_version": (C.c_int, []),
     "rdv_sizeof_params": (C.c_int, []),
+    "rdv_sizeof": (C.c_int, [C.c_int]),
     "rdv_strerror": (C.c_char_p, [C.c_int]),
     "rdv_tune": (C.c_int, [C.c_int, C.c_int]),
     "rdv_params_default": (None, [C.POINTER(RdvParams)]),
@@ -224,8 +225,10 @@ def lib():
             fn.restype, fn.argtypes = res, args
         if L.rdv_abi_version() != ABI_VERSION:
             raise RuntimeError(f"librdv_b200.so ABI {L.rdv_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
-        if L.rdv_sizeof_params() != C.sizeof(RdvParams):
-            raise RuntimeError("RdvParams layout mismatch between include/rdv_b200.h and _native.py")
+        for which, mirror in enumerate((RdvParams, RdvState, RdvStepIO, RdvRolloutIO, RdvPolicy, RdvFinishedRow)):
+            if L.rdv_sizeof(which) != C.sizeof(mirror):
+                raise RuntimeError(f"{mirror.__name__} layout mismatch between include/rdv_b200.h "
+                                   f"({L.rdv_sizeof(which)} B) and _native.py ({C.sizeof(mirror)} B)")
         _lib = L
     return _lib
 

@@ -1036,6 +1036,18 @@ int rdv_tune(int key, int value)
     return RDV_ERR_SIZE;
 }
 int rdv_sizeof_params(void) { return (int)sizeof(RdvParams); }
+int rdv_sizeof(int which)
+{
+    switch (which) {
+        case 0: return (int)sizeof(RdvParams);
+        case 1: return (int)sizeof(RdvState);
+        case 2: return (int)sizeof(RdvStepIO);
+        case 3: return (int)sizeof(RdvRolloutIO);
+        case 4: return (int)sizeof(RdvPolicy);
+        case 5: return (int)sizeof(RdvFinishedRow);
+        default: return -1;
+    }
+}
 
 const char *rdv_strerror(int status)
 {

@@ -186,3 +186,47 @@ def test_ppo_defaults_are_the_references():
     c = PPOConfig()
     assert (c.learning_rate, c.batch_size, c.n_epochs, c.clip_range) == (2e-3, 128, 40, 0.25)
     assert (c.gamma, c.gae_lambda, c.ent_coef, c.vf_coef, c.max_grad_norm) == (0.99, 0.95, 0.0, 0.5, 0.5)
+
+
+def test_info_dict_builder_cpu():
+    """csrc/rdv_host.c (the VecEnv's per-env info dicts, built with the C API): fresh dicts for last step's finished
+    envs, {"terminal_observation", "episode": {"r", "l", "t"}} (+ the rich keys) for this step's, errors on bad rows."""
+    from reinforcement_learning_rendezvous_b200 import _native as N
+    N.build_host()
+    h = N.host()
+    fin = np.dtype([("env", "<i4"), ("end_reason", "<i4"), ("terminal_obs", "<f4", (17,)), ("pad", "<f4"),
+                    ("record", "<f8", (6,))])
+    assert fin.itemsize == 128
+    n, m = 1000, 37
+    rng = np.random.default_rng(0)
+    rows = np.zeros(m, dtype=fin)
+    rows["env"] = rng.permutation(n)[:m]
+    rows["end_reason"] = rng.integers(0, 4, m)
+    rows["terminal_obs"] = rng.random((m, 17))
+    rows["record"] = rng.random((m, 6)) * 50
+    rows["record"][:, 1] = rng.integers(1, 120, m)
+    rows["record"][:, 2] = rng.integers(0, 2, m)
+    rows["record"][:, 3] = rng.integers(0, 2, m)
+    infos = [{} for _ in range(n)]
+    keep = list(infos)
+    term = np.ascontiguousarray(rows["terminal_obs"])
+    dirty = h.build_infos(infos, [], rows, term, 12.5, True, N.END_REASONS)
+    assert sorted(dirty) == sorted(rows["env"].tolist())
+    for j in range(m):
+        d = infos[int(rows["env"][j])]
+        np.testing.assert_array_equal(d["terminal_observation"], rows["terminal_obs"][j])
+        assert d["episode"] == {"r": round(float(rows["record"][j, 0]), 6), "l": int(rows["record"][j, 1]), "t": 12.5}
+        assert d["is_success"] == bool(rows["record"][j, 2] > 0) and d["collided"] == bool(rows["record"][j, 3] > 0)
+        assert d["end_reason"] == N.END_REASONS[int(rows["end_reason"][j])]
+        assert d["total_delta_v"] == rows["record"][j, 4] and d["total_delta_w"] == rows["record"][j, 5]
+    untouched = set(range(n)) - set(rows["env"].tolist())
+    assert all(infos[i] is keep[i] for i in untouched)                 # running envs keep their own dict
+    # next step: nothing finished -> last step's slots get fresh empty dicts
+    dirty2 = h.build_infos(infos, dirty, rows[:0], term[:0], 13.0, False, N.END_REASONS)
+    assert dirty2 == [] and all(infos[i] == {} for i in dirty) and len({id(d) for d in infos}) == n
+    bad = rows[:1].copy()
+    bad["env"] = n + 5
+    with pytest.raises(IndexError):
+        h.build_infos(infos, [], bad, term[:1], 0.0, False, N.END_REASONS)
+    with pytest.raises(ValueError):
+        h.build_infos(infos, [], np.zeros(100, dtype=np.uint8), term[:0], 0.0, False, N.END_REASONS)
