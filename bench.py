@@ -539,7 +539,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--integrator", choices=("rk45", "closed_form"), default="rk45")
     ap.add_argument("--e2e-steps", type=int, default=1000)
-    ap.add_argument("--min-region-ms", type=float, default=60.0, help="minimum length of a timed region")
+    ap.add_argument("--min-region-ms", type=float, default=80.0, help="minimum length of a timed region")
     ap.add_argument("--ref-min-seconds", type=float, default=8.0, help="time floor of the reference arm")
     ap.add_argument("--steps-per-launch", type=int, default=250, help="env steps fused into one rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

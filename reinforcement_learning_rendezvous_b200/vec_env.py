@@ -218,14 +218,14 @@ class RendezvousVecEnv(_Base):
         ``end_reason`` (0 obs, 1 time, 2 bubble, 3 attitude).  Same data as the ``infos`` of ``step``."""
         self.step_async(actions)
         obs, rew, done, rows = self._launch_and_fetch()
-        order = np.argsort(rows["env"])                 # ascending env index; every gather below takes own memory,
-        rec = rows["record"][order]                     # so no view of the pinned block outlives this call
-        finished = {
-            "index": rows["env"][order].astype(np.int64), "terminal_observation": rows["terminal_obs"][order],
+        rows = np.take(rows, np.argsort(rows["env"]))   # ascending env index; ONE gather of whole 128-byte rows into
+        rec = rows["record"]                            # own memory, the fields below are views of it (no view of the
+        finished = {                                    # pinned block outlives this call)
+            "index": rows["env"].astype(np.int64), "terminal_observation": rows["terminal_obs"],
             "episode_return": rec[:, N.EP_RETURN], "episode_length": rec[:, N.EP_LENGTH].astype(np.int64),
             "is_success": rec[:, N.EP_SUCCESS] > 0, "collided": rec[:, N.EP_COLLIDED] > 0,
             "total_delta_v": rec[:, N.EP_DELTA_V], "total_delta_w": rec[:, N.EP_DELTA_W],
-            "end_reason": rows["end_reason"][order].astype(np.int8),
+            "end_reason": rows["end_reason"].astype(np.int8),
         }
         return obs, rew, done, finished
 
