@@ -147,45 +147,6 @@ RDV_DEV double koz_distance(const RdvParams &P, double r, double th)
 // `row` is a team-private scratch of RDV_TEAM_ROW doubles in shared memory.  Every lane of the warp
 // must call the function (teams with valid == false compute on env i but store nothing).
 // ---------------------------------------------------------------------------------
-// sin and cos of the half-angle of a reset deviation (rot2quat, quaternions.py:11-27).  The angle is at most
-// range / 2 -- 0.39 rad for the default 45 degree target range -- so no argument reduction is needed: for |x| <= 0.8
-// the Taylor polynomials to x^19 / x^18 are exact to below 1 ulp (next terms: 0.8^21 / 21! = 2e-22, 0.8^20 / 20! =
-// 5e-21); larger ranges take the library sincos.  (The library form drags its Payne-Hanek slow path and ~100
-// instructions into every reset pass.)
-#ifndef RDV_FAST_SINCOS
-#define RDV_FAST_SINCOS 0
-#endif
-RDV_DEV void sincos_half_angle(const double x, double &sn, double &cs)
-{
-#if RDV_FAST_SINCOS
-    if (fabs(x) <= 0.8) {
-        const double z = x * x;
-        double ps = -1.0 / 121645100408832000.0;                      // -1/19!
-        ps = fma(ps, z, 1.0 / 355687428096000.0);                     //  1/17!
-        ps = fma(ps, z, -1.0 / 1307674368000.0);                      // -1/15!
-        ps = fma(ps, z, 1.0 / 6227020800.0);                          //  1/13!
-        ps = fma(ps, z, -1.0 / 39916800.0);                           // -1/11!
-        ps = fma(ps, z, 1.0 / 362880.0);                              //  1/9!
-        ps = fma(ps, z, -1.0 / 5040.0);                               // -1/7!
-        ps = fma(ps, z, 1.0 / 120.0);                                 //  1/5!
-        ps = fma(ps, z, -1.0 / 6.0);                                  // -1/3!
-        sn = fma(x * z, ps, x);
-        double pc = 1.0 / 6402373705728000.0;                         //  1/18!
-        pc = fma(pc, z, -1.0 / 20922789888000.0);                     // -1/16!
-        pc = fma(pc, z, 1.0 / 87178291200.0);                         //  1/14!
-        pc = fma(pc, z, -1.0 / 479001600.0);                          // -1/12!
-        pc = fma(pc, z, 1.0 / 3628800.0);                             //  1/10!
-        pc = fma(pc, z, -1.0 / 40320.0);                              // -1/8!
-        pc = fma(pc, z, 1.0 / 720.0);                                 //  1/6!
-        pc = fma(pc, z, -1.0 / 24.0);                                 // -1/4!
-        pc = fma(pc, z, 0.5);                                         //  1/2!
-        cs = fma(-z, pc, 1.0);
-        return;
-    }
-#endif
-    sincos(x, &sn, &cs);
-}
-
 constexpr int RDV_TEAM = 8;
 constexpr int RDV_TEAM_ROW = 24;
 
@@ -222,7 +183,7 @@ RDV_DEV void team_reset_core(const RdvParams &P, uint64_t seed, int64_t env_id, 
         } else {
             // rot2quat (quaternions.py:11-27) then quat_product(dev, nominal) (:149-170); both normalise
             double sn, cs;
-            sincos_half_angle(0.5 * mag, sn, cs);
+            sincos(0.5 * mag, &sn, &cs);
             const double ra = fast_rsqrt(dot3(dir, dir));
             double qa[4] = {cs, dir[0] * ra * sn, dir[1] * ra * sn, dir[2] * ra * sn};
             const double rq = fast_rsqrt(dot4(qa, qa));

@@ -501,32 +501,14 @@ RDV_RK_FN int rk45_attitude(double (&y)[7], const double dt, const BodyConst &b,
 // exact arithmetic) at 159 instead of 307 fp64 operations per attempted step.  No division by omega occurs:
 // w = 0 gives p = 0 and a constant quaternion.
 // ---------------------------------------------------------------------------------
-#ifndef RDV_RHS_FOLD
-#define RDV_RHS_FOLD 0
-#endif
 // Slope of y = a q0 + b p in plane coordinates.  The basis is scaled so that |q0| drops out: p = (M / |q0|) q0 and
 // om2 = omega^2 / |q0|^2, hence y' = M y / |y| = (M / |q0|) y / sqrt(a^2 + om2 b^2).
 RDV_DEV void rhs_plane(const double a, const double b, const double om2, double &ka, double &kb)
 {
     const double t = om2 * b;
-#if RDV_RHS_FOLD
-    // The step is a latency chain, not a throughput problem: the two products with g = rsqrt(s) are
-    // folded into the last refinement level of the reciprocal square root -- with r the MUFU seed, e = 1 - s r^2 and
-    // q = 1/2 + 3e/8,  g = r + (r e) q,  so  a g = (a r) + (a r e) q  and  t g = (t r) + (t r e) q -- two more
-    // multiplications, one dependent level less per slope.
-    const double s = fma(t, b, a * a);
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
-    const double m = s * r, ar = a * r, tr = t * r;
-    const double e = fma(-m, r, 1.0);
-    const double q = fma(0.375, e, 0.5);
-    kb = fma(ar * e, q, ar);
-    ka = -fma(tr * e, q, tr);
-#else
     const double g = fast_rsqrt(fma(t, b, a * a));                // |q0| / |y|
     ka = -(t * g);
     kb = a * g;
-#endif
 }
 
 // What the controller sees of one attempted step, in float32 (RDV_CTRL_F32 rationale above): the candidate state
