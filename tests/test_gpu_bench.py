@@ -30,6 +30,10 @@ def test_bench_json_line_contract():
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in r, key
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0 < r["frac"] < 1.5
+    # the timed region is long enough and holds enough launches whatever --steps is
+    assert r["launches_timed"] >= 25 and d["config"]["timed_region_ms"] >= 50.0
+    assert d["config"]["repeats"] * d["steps"] == d["config"]["steps_timed"]
+    assert d["gpu_launches"] == r["launches_timed"]
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 8192 * 6 * 4 and e["d2h_bytes_per_step"] > 8192 * 17 * 4
     assert e["value"] < d["value"]                    # the end-to-end number is not the device-timed one
