@@ -229,7 +229,7 @@ def run_cuda(args):
     W_eff = max(W, 3)
     env.rollout(W_eff, action_seed=args.seed + 1, step_base=0)
     done_steps = W_eff
-    red = OverlappedStatsReducer(dev)
+    red = OverlappedStatsReducer(dev, capacity=4096)
     # calibration (untimed; doubles as warm-up of the K-step launch shape and of every torch op and the collective
     # the timed loop issues): how long is one repeat?
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -268,7 +268,7 @@ def run_cuda(args):
             done_steps += kl
             j += 1
             ev[j].record()
-        red.end()          # waits for rollout r - 1's all-reduce (it ran beside this rollout), issues rollout r's
+        red.end()          # issues this rollout's all-reduce (async, in place on its row); nothing waits for it here
     total_stats = red.finish()
     e1.record()
     barrier()
@@ -283,7 +283,7 @@ def run_cuda(args):
     full = [ev[q].elapsed_time(ev[q + 1]) for q in range(R * n_l) if launches[q % n_l] == KL]
     t_launch = sum(full) / len(full)
     t_step = t_launch / KL
-    env.stats = red.bufs[0]
+    env.stats = torch.zeros(N.NSTATS, dtype=torch.float64, device=dev)
 
     # fp64 peak: DFMA probe, best of 6
     blocks, threads, iters = 148 * 8, 256, 4096
@@ -498,9 +498,9 @@ def run_cuda(args):
                    "steps_per_launch": KL, "repeats": R, "steps_timed": K * R, "timed_region_ms": ms,
                    "timing": "the timed region is `repeats` x (one `steps`-step rollout + its statistics reduction), "
                              "sized to last >= %g ms whatever --steps is" % args.min_region_ms,
-                   "stats_all_reduce": ("one 16-double NCCL all-reduce per rollout, issued asynchronously and waited "
-                                        "for after the next rollout is enqueued; the rollout leaves 1 SM free for it"
-                                        if world > 1 else "no-op at N = 1"),
+                   "stats_all_reduce": ("one 16-double NCCL all-reduce per rollout, issued asynchronously in place on the "
+                                        "rollout's own statistics row and waited for once at the end of the region; "
+                                        "the rollout leaves 1 SM free for it" if world > 1 else "no-op at N = 1"),
                    "l2": "state lives in registers for the steps of a launch and is re-read from memory once per "
                          "launch; ms_per_step_l2_flushed repeats the launches with a 256 MB L2 flush before each; "
                          "ms_per_step_no_auto_reset = 16-step launches right after a batch reset, auto_reset off "

@@ -1384,8 +1384,8 @@ int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, in
     if (dev < 0) return RDV_ERR_CUDA;
     static std::atomic<uint64_t> attr_mask{0};
     if (!ensure_smem(tc::policy_tc_kernel, attr_mask, dev, sizeof(tc::Smem))) return RDV_ERR_CUDA;
-    const int64_t pairs = ((n + tc::TM - 1) / tc::TM + tc::GROUPS - 1) / tc::GROUPS;
-    const unsigned grid = (unsigned)(pairs < sm_count ? pairs : sm_count);
+    const int64_t tiles = (n + tc::TM - 1) / tc::TM;              // tile t -> CTA t % grid, group (t / grid) % GROUPS
+    const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
     tc::policy_tc_kernel<<<grid, tc::GROUPS * tc::TM, sizeof(tc::Smem), (cudaStream_t)cuda_stream>>>(*pi, obs, actions, n);
     return launch_status();
 }

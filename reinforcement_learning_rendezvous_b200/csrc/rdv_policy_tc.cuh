@@ -410,8 +410,11 @@ __global__ void __launch_bounds__(GROUPS * TM, 1) policy_tc_kernel(const RdvPoli
     Smem &s = *reinterpret_cast<Smem *>(raw);
     const int g = threadIdx.x / TM, r = threadIdx.x % TM;                  // group, row in tile
     uint64_t *obs_bar = &s.obs_bar[g];
+    // tile t belongs to CTA t % grid and, there, to group (t / grid) % GROUPS: consecutive tiles go to different SMs, so
+    // the per-SM tile counts differ by at most one (131,072 rows = 1,024 tiles over 148 SMs: 6 or 7 tiles each; the
+    // group-major order of round 1 gave 108 SMs 8 tiles and 40 SMs 4)
     const int64_t tiles = (n + TM - 1) / TM, stride = (int64_t)gridDim.x * GROUPS;
-    const int64_t first = (int64_t)blockIdx.x * GROUPS + g;
+    const int64_t first = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
     const bool bulk_ok = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;        // cp.async.bulk needs 16-byte alignment
 
     // the first observation tile is in flight while the weights are split

@@ -51,49 +51,49 @@ def all_reduce_stats(stats: torch.Tensor, group=None, async_op: bool = False):
 class OverlappedStatsReducer:
     """Per-rollout statistics summed over ranks with the collective of rollout r running BESIDE rollout r + 1.
 
-    The rollout kernels accumulate into the buffer ``begin()`` returns; ``end()`` -- called once the rollout's
-    launches are enqueued -- first waits for the PREVIOUS rollout's all-reduce (issued one rollout ago, so it had a
-    whole rollout to finish), adds it to ``total``, then snapshots this rollout's buffer and issues its all-reduce
-    asynchronously (NCCL runs it on its own stream; the two buffers / snapshots alternate so nothing is overwritten
-    while in flight).  Let the rollout leave one SM free (``BatchedRendezvousEnv.sm_reserve = 1``) so that the
-    collective's kernel does not queue behind a launch that fills every SM.  Without a process group it degrades to a
-    local running sum."""
+    Rollout r accumulates into its own zeroed row of a preallocated ``[capacity, RDV_NSTATS]`` matrix (``begin()``
+    returns the row).  ``end()`` -- called once the rollout's launches are enqueued -- issues the row's all-reduce in
+    place with ``async_op=True``: NCCL runs it on its own stream as soon as the rollout has finished, while the host
+    has already enqueued the next rollout, which writes another row.  Nothing on the compute stream waits for a
+    collective until ``finish()`` (or until the matrix is full and gets folded into ``total``), and no bookkeeping
+    kernel (zeroing, snapshot, running sum) sits between two rollout launches.  Let the rollout leave one SM free
+    (``BatchedRendezvousEnv.sm_reserve = 1``) so that the collective's kernel does not queue behind a launch that
+    fills every SM.  Without a process group it degrades to a local sum."""
 
-    def __init__(self, device, group=None):
+    def __init__(self, device, group=None, capacity: int = 1024):
         self.group = group
-        self.bufs = [torch.zeros(N.NSTATS, dtype=torch.float64, device=device) for _ in range(2)]
-        self.snaps = [torch.zeros(N.NSTATS, dtype=torch.float64, device=device) for _ in range(2)]
+        self.rows = torch.zeros((int(capacity), N.NSTATS), dtype=torch.float64, device=device)
         self.total = torch.zeros(N.NSTATS, dtype=torch.float64, device=device)
-        self._pending = None
+        self._last = None                   # handle of the most recent collective (NCCL executes them in issue order)
         self._r = 0
 
     def begin(self) -> torch.Tensor:
-        buf = self.bufs[self._r & 1]
-        buf.zero_()
-        return buf
-
-    def _drain(self):
-        if self._pending is not None:
-            work, snap = self._pending
-            if work is not None:
-                work.wait()
-            self.total += snap
-            self._pending = None
+        if self._r == self.rows.shape[0]:
+            self._fold()
+        return self.rows[self._r]
 
     def end(self):
-        self._drain()
-        snap = self.snaps[self._r & 1]
-        snap.copy_(self.bufs[self._r & 1])
-        self._pending = (all_reduce_stats(snap, group=self.group, async_op=True), snap)
+        work = all_reduce_stats(self.rows[self._r], group=self.group, async_op=True)
+        if work is not None:
+            self._last = work
         self._r += 1
 
+    def _fold(self):
+        if self._last is not None:
+            self._last.wait()               # the compute stream waits for the last collective, hence for all of them
+            self._last = None
+        if self._r:
+            self.total += self.rows[:self._r].sum(dim=0)
+            self.rows[:self._r].zero_()
+            self._r = 0
+
     def finish(self) -> torch.Tensor:
-        """Wait for the last collective; returns the running total over all rollouts and ranks."""
-        self._drain()
+        """Wait for the outstanding collectives; returns the running total over all rollouts and ranks."""
+        self._fold()
         return self.total
 
     def reset(self):
-        self._drain()
+        self._fold()
         self.total.zero_()
 
 
