@@ -109,7 +109,6 @@ def evaluate_batch(policy, initial_states, config=None, reward_kwargs=None, devi
     accumulated in registers until the env's first done.  Returns a dict of length-M arrays with the columns of the
     reference's results workbook.  ``config`` defaults to the evaluator's ``dict(dt=1, t_max=60)`` with
     ``stochastic=False`` (monte_carlo.py:26-27)."""
-    from . import _native as N
     ics = np.array(initial_states, dtype=np.float64, copy=True).reshape(-1, 20)
     if normalize_quaternions:                                   # monte_carlo.py:66-67
         ics[:, 6:10] /= np.linalg.norm(ics[:, 6:10], axis=1, keepdims=True)
