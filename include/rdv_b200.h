@@ -284,7 +284,9 @@ int rdv_policy_forward_ffma(const RdvPolicy *pi, const float *obs, float *action
  * RDV_TUNE_ROLLOUT_TPB forces the rollout CTA size (256 | 384 | 448 | 512, 0 = automatic), RDV_TUNE_RESET_REFILL sets
  * the reset prefetch period in steps (0 = reset on demand only; default 12).  Returns the previous value, or
  * RDV_ERR_SIZE for an unknown key. */
-enum { RDV_TUNE_ROLLOUT_TPB = 0, RDV_TUNE_RESET_REFILL = 1 };
+enum { RDV_TUNE_ROLLOUT_TPB = 0, RDV_TUNE_RESET_REFILL = 1,
+       RDV_TUNE_ROLLOUT_PDL = 2 };   /* 1 (default): rdv_rollout launches with programmatic stream serialisation, so the *
+                                      * prologue of a launch overlaps the tail of the previous kernel; 0: plain launch  */
 int rdv_tune(int key, int value);
 
 /* Test hook: y[i] = f(x[i]) for the device math helpers the step is built from.  op 0: 1/sqrt(x), 1: 1/x,

@@ -520,6 +520,13 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     const int passes = (int)((span + TPB_ - 1) / TPB_);
     const int64_t chunk = TABLE ? TPB_ : (passes > 0 ? (span + passes - 1) / passes : 0);
     StepStats st = {};
+    // Programmatic dependent launch: when rdv_rollout launches with the stream-serialisation attribute, this grid may
+    // become resident while the previous kernel of the stream is still draining (its CTAs finish at different times),
+    // and everything above -- parameter loads, the actor's weight split and TMEM allocation -- runs in that shadow.
+    // Nothing written by an earlier kernel is read before this point; the wait returns once the previous grid has
+    // completed and its writes are visible.  Dependents of THIS grid may be scheduled as soon as its CTAs start to exit.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
 
     for (int pass = 0; pass < passes; ++pass) {
         const int64_t c_lo = lo + pass * chunk, c_hi = (c_lo + chunk < hi) ? c_lo + chunk : hi;
@@ -1024,6 +1031,7 @@ static int env_int(const char *name, int fallback)
 }
 static std::atomic<int> g_tune_tpb{env_int("RDV_ROLLOUT_TPB", 0)};
 static std::atomic<int> g_tune_refill{env_int("RDV_RESET_REFILL", 12)};
+static std::atomic<int> g_tune_pdl{env_int("RDV_ROLLOUT_PDL", 1)};
 
 extern "C" {
 
@@ -1033,6 +1041,7 @@ int rdv_tune(int key, int value)
 {
     if (key == RDV_TUNE_ROLLOUT_TPB) return g_tune_tpb.exchange(value);
     if (key == RDV_TUNE_RESET_REFILL) return g_tune_refill.exchange(value);
+    if (key == RDV_TUNE_ROLLOUT_PDL) return g_tune_pdl.exchange(value);
     return RDV_ERR_SIZE;
 }
 int rdv_sizeof_params(void) { return (int)sizeof(RdvParams); }
@@ -1259,7 +1268,20 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     {                                                                                                             \
         static std::atomic<uint64_t> attr_mask{0};                                                                \
         if (!ensure_smem(KERNEL, attr_mask, dev, SMEM)) return RDV_ERR_CUDA;                                      \
-        KERNEL<<<(unsigned)grid, T_, SMEM, st>>>(*p, *s, io_k, n, seed, env_offset);                              \
+        if (g_tune_pdl.load(std::memory_order_relaxed)) {                                                         \
+            cudaLaunchConfig_t cfg = {};                                                                          \
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T_); cfg.dynamicSmemBytes = SMEM; cfg.stream = st; \
+            cudaLaunchAttribute at[1];                                                                            \
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                        \
+            at[0].val.programmaticStreamSerializationAllowed = 1;                                                 \
+            cfg.attrs = at; cfg.numAttrs = 1;                                                                     \
+            if (cudaLaunchKernelEx(&cfg, KERNEL, *p, *s, io_k, n, seed, env_offset) != cudaSuccess) {             \
+                cudaGetLastError();                                                                               \
+                return RDV_ERR_CUDA;                                                                              \
+            }                                                                                                     \
+        } else {                                                                                                  \
+            KERNEL<<<(unsigned)grid, T_, SMEM, st>>>(*p, *s, io_k, n, seed, env_offset);                          \
+        }                                                                                                         \
     }
 #define RDV_ROWS_SMEM(T_) ((size_t)(T_ / 32) * 32 * RDV_NEXT_ROW * sizeof(double))
 #define RDV_LAUNCH_R(ISO_, CL_, T_) RDV_LAUNCH_K((rollout_kernel<ISO_, CL_, T_, false, false>), T_, RDV_ROWS_SMEM(T_))

@@ -455,3 +455,26 @@ def test_sweep_sharding_is_invariant():
     assert len(parts) == len(whole) == len(sets)
     for a, b in zip(whole, parts):
         assert a == b
+
+
+@pytest.mark.parametrize("n", [1, 33])
+def test_vec_env_tiny_batches(n):
+    """The one-block host path at sizes where the finished-row bound exceeds the batch."""
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, RendezvousVecEnv
+    import torch
+    venv = RendezvousVecEnv(n, seed=5, t_max=4)
+    benv = BatchedRendezvousEnv(n, seed=5, t_max=4)
+    np.testing.assert_array_equal(venv.reset(), benv.reset().cpu().numpy())
+    rng = np.random.default_rng(0)
+    ends = 0
+    for _ in range(12):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        obs, rew, done, infos = venv.step(a)
+        o2, r2, d2 = benv.step(torch.as_tensor(a, device=benv.device))
+        np.testing.assert_array_equal(obs, o2.cpu().numpy())
+        np.testing.assert_array_equal(done, d2.bool().cpu().numpy())
+        for i in np.flatnonzero(done):
+            np.testing.assert_array_equal(infos[i]["terminal_observation"], benv.terminal_obs[i].cpu().numpy())
+            assert infos[i]["episode"]["l"] <= 4
+            ends += 1
+    assert ends >= 2 * n

@@ -379,3 +379,94 @@ def test_stochastic_policy_rollout_statistics_and_determinism():
     assert not torch.equal(other["actions"][0], out["actions"][0])
     with pytest.raises(ValueError):
         env.rollout(2, policy=pol, stochastic=True)
+
+
+def test_sm_reserve_and_ragged_parameter_table_do_not_change_results():
+    """Leaving SMs free for a concurrent collective (sm_reserve) only changes how the batch is cut into CTA slices, and a
+    parameter table whose last group is not a multiple of 32 envs behaves like separate envs."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    a = BatchedRendezvousEnv(5000, seed=4, t_max=20)
+    b = BatchedRendezvousEnv(5000, seed=4, t_max=20)
+    b.sm_reserve = 3
+    for e in (a, b):
+        e.reset()
+        e.rollout(45, action_seed=9)
+        e.rollout(10, action_seed=9, step_base=45)
+    assert torch.equal(a.get_state(), b.get_state()) and torch.equal(a.i32, b.i32) and torch.equal(a.obs, b.obs)
+    with pytest.raises(RuntimeError):
+        b.sm_reserve = 100000
+        b.rollout(1, action_seed=1)
+    # ragged table: groups of 64, 32 and 19 envs
+    batches = [(64, dict(dt=0.5, t_max=10)), (32, dict(koz_radius=8.0, t_max=10)), (19, dict(h=500e3, t_max=10))]
+    env = BatchedRendezvousEnv(115, seed=2, param_batches=batches)
+    assert env.param_table is not None
+    env.reset()
+    out = env.rollout(30, action_seed=5, record_rewards=True, record_dones=True, record_obs=True)
+    lo = 0
+    for count, kw in batches:
+        e = BatchedRendezvousEnv(count, seed=2, env_offset=lo, **kw)
+        e.reset()
+        o = e.rollout(30, action_seed=5, record_rewards=True, record_dones=True, record_obs=True)
+        assert torch.equal(o["rewards"], out["rewards"][:, lo:lo + count])
+        assert torch.equal(o["dones"], out["dones"][:, lo:lo + count])
+        assert torch.equal(o["obs_steps"], out["obs_steps"][:, lo:lo + count])
+        assert torch.equal(e.get_state(), env.get_state()[lo:lo + count])
+        lo += count
+    # masked reset and the evaluator queries go through the table too
+    mask = torch.zeros(115, dtype=torch.uint8, device=env.device)
+    mask[60:100] = 1
+    env.reset(mask=mask)
+    err, col, suc, koz = env.errors()
+    assert bool(torch.isfinite(err).all()) and int(env.step_count[60:100].max()) == 0
+
+
+def test_evaluator_mode_with_tensor_actions_matches_per_step_accumulation():
+    """RdvRolloutIO.mc_out without the fused actor (given actions): the device-side accumulators of
+    monte_carlo.evaluate against the same quantities accumulated on the host from rdv_step + rdv_errors."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, _native as N
+    from reinforcement_learning_rendezvous_b200.monte_carlo import _terminal_errors_batch
+    n, K = 600, 40
+    # starts around the docking point (|rd| = 2 m on the target's -y axis), inside the entry corridor, with a target that
+    # barely moves: the four errors cross their limits in both directions, so every level of the first-index rule occurs
+    kw = dict(t_max=40, rc0=np.array([0.0, -2.3, 0.0]), rc0_range=0.5, vc0_range=0.05, qt0_range=0.1, wt0_range=0.01)
+    rng = np.random.default_rng(3)
+    acts = torch.as_tensor(rng.uniform(-0.3, 0.3, (K, n, 6)), device="cuda")
+    a = BatchedRendezvousEnv(n, seed=1, auto_reset=False, **kw)
+    b = BatchedRendezvousEnv(n, seed=1, auto_reset=False, **kw)
+    a.reset(); b.reset()
+    mc = a.rollout(K, actions=acts, monte_carlo=True)["mc"].cpu().numpy()
+    err, col, suc, koz = b.errors()
+    errs = np.full((K + 1, n, 4), np.nan)
+    errs[0] = err.cpu().numpy()
+    n_col, n_suc = col.cpu().numpy().astype(int), suc.cpu().numpy().astype(int)
+    min_koz, total, length = koz.cpu().numpy().copy(), np.zeros(n), np.zeros(n, dtype=int)
+    alive = np.ones(n, dtype=bool)
+    tdv = np.zeros(n)
+    for k in range(K):
+        _, rew, done = b.step(acts[k])
+        err, col, suc, koz = (t.cpu().numpy() for t in b.errors())
+        errs[k + 1][alive] = err[alive]
+        n_col += (col.astype(bool) & alive)
+        n_suc += (suc.astype(bool) & alive)
+        min_koz = np.where(alive & (koz < min_koz), koz, min_koz)
+        total += np.where(alive, rew.cpu().numpy(), 0.0)
+        length += alive
+        fin = alive & done.cpu().numpy().astype(bool)
+        tdv = np.where(fin, b.total_delta_v.cpu().numpy(), tdv)
+        alive &= ~done.cpu().numpy().astype(bool)
+    p = b.params
+    te = _terminal_errors_batch(errs, length, (p.max_rd_error, p.max_vd_error, p.max_qd_error, p.max_wd_error))
+    np.testing.assert_array_equal(mc[:, N.MC_EP_LEN], length)
+    np.testing.assert_array_equal(mc[:, N.MC_NUM_COLLISIONS], n_col)
+    np.testing.assert_array_equal(mc[:, N.MC_NUM_SUCCESSES], n_suc)
+    assert rel_err(mc[:, N.MC_MIN_KOZ], min_koz) <= 1e-10 and rel_err(mc[:, N.MC_TOTAL_REWARD], total) <= 1e-10
+    done_rows = mc[:, N.MC_END_REASON] >= 0
+    assert done_rows.sum() > n // 2
+    assert rel_err(mc[done_rows, N.MC_TOTAL_DELTA_V], tdv[done_rows]) <= 1e-12
+    got = mc[:, [N.MC_POS_ERR, N.MC_VEL_ERR, N.MC_ATT_ERR, N.MC_ROT_ERR]].copy()
+    got[:, 2:] = np.degrees(got[:, 2:])
+    assert np.max(np.abs(got - te) / np.maximum(np.abs(te), 1e-3)) <= 1e-9
+    assert len(np.unique(mc[:, N.MC_LEVEL])) >= 3                  # several branches of the first-index rule ran
+    assert mc[:, N.MC_NUM_SUCCESSES].max() > 0 and mc[:, N.MC_TAIL_COUNT].max() > 1
