@@ -8,3 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
     python tools/rollout_one.py 65536 20 > gpurun_out/${TAG}_ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 3 -c 1 -o gpurun_out/${TAG}_rollout -f \
     python tools/rollout_one.py 65536 20 > gpurun_out/${TAG}_ncu_full.log 2>&1
+# the same for the policy-fused variant (16-step launches of tools/policy_one.py)
+python tools/policy_one.py > gpurun_out/${TAG}_policy_one.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 2 -c 1 -o gpurun_out/${TAG}_policy_rollout -f \
+    python tools/policy_one.py > gpurun_out/${TAG}_ncu_policy.log 2>&1

@@ -25,6 +25,8 @@ def ncu(rep, *args):
 
 def main():
     rep, tag, envs, steps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+    write_traffic = "notraffic" not in sys.argv[5:]          # captures of other variants must not feed bench.py
+    what = " ".join(a for a in sys.argv[5:] if a != "notraffic") or "Philox actions, reset rows carried in the device scratch"
     raw = ncu(rep, "--page", "raw", "--csv")
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -81,6 +83,7 @@ def main():
         "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
@@ -104,8 +107,7 @@ def main():
         f.write(f"# {tag} -- `rollout_kernel` (the dominant kernel of bench.py's timed region), ncu --set full, B200\n\n")
         f.write(f"Capture: `tools/ncu_rollout.sh {tag}` (`ncu --set full --clock-control none --import-source on -k "
                 f"regex:rollout_kernel -s 3 -c 1 python tools/rollout_one.py {envs} {steps}`), run after the same script "
-                f"had exited 0 without ncu: one launch of {envs:,} envs x {steps} steps, Philox actions, reset rows "
-                f"carried in the device scratch.  Full dump: `{tag}_rollout_kernel_ncu_raw.csv`; launch list of the same "
+                f"had exited 0 without ncu: one launch of {envs:,} envs x {steps} steps, {what}.  Full dump: `{tag}_rollout_kernel_ncu_raw.csv`; launch list of the same "
                 f"command: `{tag}_launches.csv`.\n\n| metric | value | unit |\n|---|---|---|\n")
         for nme in names:
             if nme in m:
@@ -146,8 +148,9 @@ def main():
         "source": f"profiles/{tag}_rollout_kernel_ncu_raw.csv (ncu --set full --clock-control none, one {steps}-step launch of "
                   f"tools/rollout_one.py) and the source page of the same capture (profiles/{tag}_rollout_instmix.md)",
     }
-    with open(os.path.join(ROOT, "profiles", "rollout_traffic.json"), "w") as f:
-        json.dump(traffic, f, indent=1)
+    if write_traffic:
+        with open(os.path.join(ROOT, "profiles", "rollout_traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
     print(json.dumps(traffic, indent=1))
 
 
