@@ -488,7 +488,12 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     tc::TileSmem *ts = reinterpret_cast<tc::TileSmem *>(dyn_smem);
     uint32_t tmem_all = 0, mma_phase = 0;
     if (POLICY) tmem_all = tc::tile_setup<TPB_>(io.policy, *ts);
-    __shared__ __align__(16) float s_obs[POLICY ? 1 : NW][32 * RDV_OBS_DIM];
+    // Staging rows of the observation write-out.  Only the variant that records an observation every step owns them;
+    // the others stage the ONE observation of a launch in memory that is dead by then (below), which keeps the CTA under
+    // 100 KiB of shared memory and leaves 156 KiB of L1 for the ~140 KB of register spills of 448 threads (with the
+    // rows the carve-out was 132 KiB and one spill load in ten went to the L2).
+    constexpr bool own_stage = !POLICY && OBS;
+    __shared__ __align__(16) float s_obs[own_stage ? NW : 1][own_stage ? 32 * RDV_OBS_DIM : 4];
     __shared__ double s_stats[NW][RDV_NSTATS];
     __shared__ double s_team[NW][4][RDV_TEAM_ROW];
     const unsigned full = 0xffffffffu;
@@ -509,7 +514,10 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     double *next_rows = reinterpret_cast<double *>(dyn_smem) + (size_t)warp * 32 * RDV_NEXT_ROW;
     // the warp's observation staging row; with the fused actor it borrows the group's activation tile, which is
     // only live between the step barrier and the end of the actor's third layer
-    float *obs_stage = POLICY ? ts->al[warp >> 2] + (warp & 3) * (32 * RDV_OBS_DIM) : s_obs[POLICY ? 0 : warp];
+    // (without per-step records: the warp's reset rows, 32 x 22 doubles, which have gone back to the scratch -- or are
+    // simply not needed any more -- when the final observation is written)
+    float *obs_stage = POLICY ? ts->al[warp >> 2] + (warp & 3) * (32 * RDV_OBS_DIM)
+                              : own_stage ? s_obs[own_stage ? warp : 0] : reinterpret_cast<float *>(next_rows);
     constexpr bool want_obs = POLICY || OBS;
     // this CTA's slice [lo, hi) and its passes; with a parameter table the slices are cut at multiples of 32 envs so
     // that a warp never straddles two parameter blocks
