@@ -457,6 +457,12 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 #ifndef RDV_SYNC_PERIOD
 #define RDV_SYNC_PERIOD 8             /* steps between the CTA barriers that keep the warps in one code region */
 #endif
+#ifndef RDV_TMEM_STASH
+#define RDV_TMEM_STASH 1              /* fused actor: park the cold per-env registers in tensor memory across the solves */
+#endif
+#ifndef RDV_TMEM_STASH_MAIN
+#define RDV_TMEM_STASH_MAIN 1         /* the same for the variants without the actor (they then allocate the TMEM) */
+#endif
 #ifndef RDV_LOCKSTEP_MAX_TPB
 #define RDV_LOCKSTEP_MAX_TPB 256      /* CTAs up to this size interleave the two attitude solves (rk45_iso_plane_pair) */
 #endif
@@ -488,6 +494,21 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     tc::TileSmem *ts = reinterpret_cast<tc::TileSmem *>(dyn_smem);
     uint32_t tmem_all = 0, mma_phase = 0;
     if (POLICY) tmem_all = tc::tile_setup<TPB_>(io.policy, *ts);
+    // Without the actor the tensor memory (256 KB per SM) is entirely idle; the variant for the reference's bodies
+    // allocates it as a parking area for cold registers (see the step phase): 128 columns for every thread.
+    constexpr bool main_stash = !POLICY && !MC && ISO && !CLOSED && (RDV_TMEM_STASH_MAIN != 0);
+    __shared__ uint32_t s_tmem_base;
+    if constexpr (main_stash) {
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(tc::smem_u32(&s_tmem_base)), "r"(tc::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        tmem_all = s_tmem_base;
+    }
     // Staging rows of the observation write-out.  Only the variant that records an observation every step owns them;
     // the others stage the ONE observation of a launch in memory that is dead by then (below), which keeps the CTA under
     // 100 KiB of shared memory and leaves 156 KiB of L1 for the ~140 KB of register spills of 448 threads (with the
@@ -654,6 +675,60 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                     mc.len += 1;
                     if (r.done) { alive = false; mc_reason = r.reason; }
                 }
+            } else if constexpr ((POLICY && RDV_TMEM_STASH) || main_stash) {
+                // The fused actor owns 196 KiB of shared memory, which leaves 60 KiB of L1 for 136 KB of register
+                // spills (local loads hit 58 %, and the misses cost an L2 round trip: 22 % of this variant's issue
+                // latency were long-scoreboard stalls).  During the env step the group's tensor memory is idle -- D and
+                // the A operand are only live inside the actor -- so everything the two attitude solves do not touch
+                // (position, velocity, totals, counters, the statistics accumulators: 45 words per env) is parked in
+                // the thread's own TMEM lane across them instead of being spilled: three tcgen05.st / three
+                // tcgen05.ld per step instead of ~50 local stores and loads.
+                env_translate(P, e, t);
+                // a warp reaches the 32 lanes of its quadrant (warp id mod 4); warps of one quadrant take different
+                // column blocks.  With the actor: the group's own 128 columns (thread = TMEM lane there anyway).
+                const uint32_t lane_addr = tmem_all + (uint32_t)(threadIdx.x >> 7) * tc::GROUP_COLS +
+                                           ((uint32_t)(threadIdx.x & 96) << 16);
+                {
+                    uint32_t w[48];
+                    int q = 0;
+                    auto put = [&](double v) { w[q++] = (uint32_t)__double2loint(v); w[q++] = (uint32_t)__double2hiint(v); };
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { put(e.rc[j]); put(e.vc[j]); }
+                    put(c.tdv); put(c.tdw); put(c.ep_ret); put(t.fuel);
+                    put(st.ep_return); put(st.ep_length); put(st.delta_v); put(st.delta_w); put(st.reward);
+                    w[q++] = (uint32_t)c.step; w[q++] = (uint32_t)c.success; w[q++] = (uint32_t)c.collided;
+                    w[q++] = (uint32_t)c.episode;
+                    w[q++] = st.steps; w[q++] = st.episodes; w[q++] = st.succeeded; w[q++] = st.collided;
+                    w[q++] = st.end0; w[q++] = st.end1; w[q++] = st.end2; w[q++] = st.end3;
+                    w[q++] = st.rk_acc; w[q++] = st.rk_rej; w[q++] = st.fail;
+                    while (q < 48) w[q++] = 0u;
+                    tc::tmem_st16(lane_addr, reinterpret_cast<const uint32_t (&)[16]>(w[0]));
+                    tc::tmem_st16(lane_addr + 16, reinterpret_cast<const uint32_t (&)[16]>(w[16]));
+                    tc::tmem_st16(lane_addr + 32, reinterpret_cast<const uint32_t (&)[16]>(w[32]));
+                    tc::tmem_st_wait();
+                }
+                // (parking, in addition, the body that is not being propagated around each solve measured no faster)
+                env_attitude<ISO, CLOSED, (TPB_ <= RDV_LOCKSTEP_MAX_TPB)>(P, e, t, rk_acc, rk_rej, fail);
+                {
+                    uint32_t w[48];
+                    tc::tmem_ld16_issue(lane_addr, reinterpret_cast<uint32_t (&)[16]>(w[0]));
+                    tc::tmem_ld16_issue(lane_addr + 16, reinterpret_cast<uint32_t (&)[16]>(w[16]));
+                    tc::tmem_ld16_issue(lane_addr + 32, reinterpret_cast<uint32_t (&)[16]>(w[32]));
+                    tc::tmem_ld_wait(reinterpret_cast<uint32_t (&)[16]>(w[0]));
+                    tc::tmem_ld_wait(reinterpret_cast<uint32_t (&)[16]>(w[16]));
+                    tc::tmem_ld_wait(reinterpret_cast<uint32_t (&)[16]>(w[32]));
+                    int q = 0;
+                    auto get = [&]() { const double v = __hiloint2double((int)w[q + 1], (int)w[q]); q += 2; return v; };
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { e.rc[j] = get(); e.vc[j] = get(); }
+                    c.tdv = get(); c.tdw = get(); c.ep_ret = get(); t.fuel = get();
+                    st.ep_return = get(); st.ep_length = get(); st.delta_v = get(); st.delta_w = get(); st.reward = get();
+                    c.step = (int)w[q++]; c.success = (int)w[q++]; c.collided = (int)w[q++]; c.episode = (int)w[q++];
+                    st.steps = w[q++]; st.episodes = w[q++]; st.succeeded = w[q++]; st.collided = w[q++];
+                    st.end0 = w[q++]; st.end1 = w[q++]; st.end2 = w[q++]; st.end3 = w[q++];
+                    st.rk_acc = w[q++]; st.rk_rej = w[q++]; st.fail = w[q++];
+                }
+                r = env_evaluate<want_obs>(P, e, t.fuel, c, ov);
             } else {
                 env_advance<ISO, CLOSED, (TPB_ <= RDV_LOCKSTEP_MAX_TPB)>(P, e, t, rk_acc, rk_rej, fail);
                 r = env_evaluate<want_obs>(P, e, t.fuel, c, ov);
@@ -811,7 +886,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
         __syncwarp();
     }
     if (io.stats) reduce_stats<NW>(st, io.stats, s_stats);
-    if (POLICY) tc::tile_teardown(tmem_all);
+    if (POLICY || main_stash) tc::tile_teardown(tmem_all);
 }
 
 // ---------------------------------------------------------------------------------

@@ -49,23 +49,27 @@ RDV_DEV void ingest_action_f32(const RdvParams &P, const float (&a)[6], EnvCount
 // (rk45_iso_plane_pair, 2x ILP) -- the right choice with <= 2 warps per SM sub-partition; otherwise one solve after
 // the other through a single copy of the solver (rk45_iso_plane, 128 registers), which wins once 3-4 warps per
 // sub-partition hide the latency instead.
-template <bool ISO, bool CLOSED, bool LOCKSTEP>
-RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, int &rk_acc, int &rk_rej, int &fail)
+// first half of env_advance: the impulse rotated by the OLD chaser attitude, then the CW transition
+RDV_DEV void env_translate(const RdvParams &P, EnvRegs &e, const ActionTerms &t)
 {
-    {
-        const Rot Rc_old = rot_from_quat(e.qc);
-        double dv[3];
-        rot_apply(Rc_old, t.dvb, dv);
-        const double r0 = e.rc[0], r1 = e.rc[1], r2 = e.rc[2];
-        const double v0 = e.vc[0] + dv[0], v1 = e.vc[1] + dv[1], v2 = e.vc[2] + dv[2];
-        const double *c = P.cw;
-        e.rc[0] = fma(c[2], v1, fma(c[1], v0, c[0] * r0));
-        e.rc[1] = fma(c[6], v1, fma(c[5], v0, fma(c[3], r0, c[4] * r1)));
-        e.rc[2] = fma(c[8], v2, c[7] * r2);
-        e.vc[0] = fma(c[11], v1, fma(c[10], v0, c[9] * r0));
-        e.vc[1] = fma(c[14], v1, fma(c[13], v0, c[12] * r0));
-        e.vc[2] = fma(c[16], v2, c[15] * r2);
-    }
+    const Rot Rc_old = rot_from_quat(e.qc);
+    double dv[3];
+    rot_apply(Rc_old, t.dvb, dv);
+    const double r0 = e.rc[0], r1 = e.rc[1], r2 = e.rc[2];
+    const double v0 = e.vc[0] + dv[0], v1 = e.vc[1] + dv[1], v2 = e.vc[2] + dv[2];
+    const double *c = P.cw;
+    e.rc[0] = fma(c[2], v1, fma(c[1], v0, c[0] * r0));
+    e.rc[1] = fma(c[6], v1, fma(c[5], v0, fma(c[3], r0, c[4] * r1)));
+    e.rc[2] = fma(c[8], v2, c[7] * r2);
+    e.vc[0] = fma(c[11], v1, fma(c[10], v0, c[9] * r0));
+    e.vc[1] = fma(c[14], v1, fma(c[13], v0, c[12] * r0));
+    e.vc[2] = fma(c[16], v2, c[15] * r2);
+}
+
+// second half: the two attitude propagations (rendezvous_env.py:180-184, :552-604)
+template <bool ISO, bool CLOSED, bool LOCKSTEP>
+RDV_DEV void env_attitude(const RdvParams &P, EnvRegs &e, const ActionTerms &t, int &rk_acc, int &rk_rej, int &fail)
+{
     double y[7] = {e.qc[0], e.qc[1], e.qc[2], e.qc[3], e.wc[0] + t.dw[0], e.wc[1] + t.dw[1], e.wc[2] + t.dw[2]};
     double z[7] = {e.qt[0], e.qt[1], e.qt[2], e.qt[3], e.wt[0], e.wt[1], e.wt[2]};
     if (CLOSED) {
@@ -98,6 +102,13 @@ RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, i
     for (int k = 0; k < 4; ++k) { e.qc[k] = y[k] * ry; e.qt[k] = z[k] * rz; }
 #pragma unroll
     for (int k = 0; k < 3; ++k) { e.wc[k] = y[4 + k]; e.wt[k] = z[4 + k]; }
+}
+
+template <bool ISO, bool CLOSED, bool LOCKSTEP>
+RDV_DEV void env_advance(const RdvParams &P, EnvRegs &e, const ActionTerms &t, int &rk_acc, int &rk_rej, int &fail)
+{
+    env_translate(P, e, t);
+    env_attitude<ISO, CLOSED, LOCKSTEP>(P, e, t, rk_acc, rk_rej, fail);
 }
 
 struct StepResult { double rew; int done, reason; };
