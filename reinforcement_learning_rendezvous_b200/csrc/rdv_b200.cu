@@ -803,7 +803,9 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
             // (groups drift) 24.0 us per step against 22.7; odd groups shifted by half a step behind a barrier per
             // half-phase (half of the warps in the actor, half in the solver at any time, so that the tiles' MMAs do
             // not queue on the one tensor pipe) 29.2 against 22.9 -- with only half of the SM's warps in the solver
-            // the fp64 latency is no longer hidden, which costs more than the MMA queueing it removes.
+            // the fp64 latency is no longer hidden, which costs more than the MMA queueing it removes; a named barrier
+            // per 128-thread group instead of the CTA barrier (the staging rows only alias the group's own tile)
+            // 21.5 against 21.1; a second CTA barrier between the actor and the env step 21.6 against 21.1.
             for (int k = 0; k < io.steps; ++k) {
                 __syncthreads();
                 policy_action(k);
