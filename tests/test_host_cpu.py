@@ -120,18 +120,27 @@ print("rank", rank, "ok")
 
 def test_stats_all_reduce_world_size_2_gloo(tmp_path):
     import socket
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, port=port))
-    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
-                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
-    outs = [p.communicate(timeout=240)[0] for p in procs]
-    for r, (p, out) in enumerate(zip(procs, outs)):
-        assert p.returncode == 0, out
-        assert f"rank {r} ok" in out
+    last = ""
+    for attempt in range(3):                   # a free port can be taken between probing and binding: try another one
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        script = tmp_path / f"worker{attempt}.py"
+        script.write_text(WORKER.format(root=ROOT, port=port))
+        procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True) for r in range(2)]
+        try:
+            outs = [p.communicate(timeout=600)[0] for p in procs]
+        except subprocess.TimeoutExpired:
+            for p in procs:
+                p.kill()
+            last = "timeout"
+            continue
+        if all(p.returncode == 0 and f"rank {r} ok" in out for r, (p, out) in enumerate(zip(procs, outs))):
+            return
+        last = "\n".join(outs)
+    raise AssertionError(last[-3000:])
 
 
 def test_bench_reference_arm_runs_on_cpu():
