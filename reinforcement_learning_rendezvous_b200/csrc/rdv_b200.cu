@@ -529,7 +529,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     // with io.reset_rows they are loaded at entry and stored at exit, so they survive from launch to launch and a
     // 16-step launch runs at the rate of a 250-step one.  Without the scratch, launches of < 2 refill periods and the
     // fused actor reset on demand.
-    const bool persist = io.reset_rows != nullptr && io.auto_reset && !MC;
+    const bool persist = io.reset_rows != nullptr && io.auto_reset && !MC && io.reserved > 0;   // (period 0: on demand only)
     const int refill = (!MC && io.auto_reset && io.reserved > 0 && (persist || (!POLICY && io.steps >= 2 * io.reserved)))
                            ? io.reserved : 0;
     double *next_rows = reinterpret_cast<double *>(dyn_smem) + (size_t)warp * 32 * RDV_NEXT_ROW;

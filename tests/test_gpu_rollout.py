@@ -189,7 +189,7 @@ def test_reset_prefetch_is_bit_identical():
     try:
         for kw in (dict(t_max=25), dict(t_max=3)):
             ref = None
-            for period, carry in ((0, False), (2, True), (3, False), (8, True), (8, False), (16, True)):
+            for period, carry in ((0, False), (0, True), (2, True), (3, False), (8, True), (8, False), (16, True)):
                 _tune(N.TUNE_RESET_REFILL, period)
                 env = BatchedRendezvousEnv(2500, seed=5, **kw)
                 env.reset()
