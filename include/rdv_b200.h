@@ -280,13 +280,16 @@ int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n
 int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
 int rdv_policy_forward_ffma(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
 
-/* Development / test knobs that used to be environment variables (read once at load as defaults):
- * RDV_TUNE_ROLLOUT_TPB forces the rollout CTA size (256 | 384 | 448 | 512, 0 = automatic), RDV_TUNE_RESET_REFILL sets
- * the reset prefetch period in steps (0 = reset on demand only; default 12).  Returns the previous value, or
- * RDV_ERR_SIZE for an unknown key. */
-enum { RDV_TUNE_ROLLOUT_TPB = 0, RDV_TUNE_RESET_REFILL = 1,
-       RDV_TUNE_ROLLOUT_PDL = 2 };   /* 1 (default): rdv_rollout launches with programmatic stream serialisation, so the *
-                                      * prologue of a launch overlaps the tail of the previous kernel; 0: plain launch  */
+/* Development / test knobs that used to be environment variables (read once at load as defaults); every setting gives
+ * the same bits.  Returns the previous value, or RDV_ERR_SIZE for an unknown key.
+ *   RDV_TUNE_ROLLOUT_TPB      forces the rollout CTA size (256 | 384 | 448 | 512, 0 = automatic)
+ *   RDV_TUNE_RESET_REFILL     reset prefetch period in steps (0 = reset on demand only; default 12)
+ *   RDV_TUNE_ROLLOUT_PDL      1 (default): rdv_rollout launches with programmatic stream serialisation, so the
+ *                             prologue of a launch overlaps the tail of the previous kernel; 0: plain launch
+ *   RDV_TUNE_ROLLOUT_HELPERS  1 (default): launches of 385..448 envs per SM in one pass (65,536 envs on a B200) run
+ *                             with two helper warps per CTA that recompute the used reset rows beside the 14 worker
+ *                             warps; 0: the workers refill their rows themselves every RESET_REFILL steps */
+enum { RDV_TUNE_ROLLOUT_TPB = 0, RDV_TUNE_RESET_REFILL = 1, RDV_TUNE_ROLLOUT_PDL = 2, RDV_TUNE_ROLLOUT_HELPERS = 3 };
 int rdv_tune(int key, int value);
 
 /* Test hook: y[i] = f(x[i]) for the device math helpers the step is built from.  op 0: 1/sqrt(x), 1: 1/x,

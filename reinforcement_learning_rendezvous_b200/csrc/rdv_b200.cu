@@ -457,6 +457,12 @@ __global__ void __launch_bounds__(TPB, RDV_STEP_MIN_CTAS) step_kernel(const __gr
 #ifndef RDV_SYNC_PERIOD
 #define RDV_SYNC_PERIOD 8             /* steps between the CTA barriers that keep the warps in one code region */
 #endif
+#ifndef RDV_HELP_POST_PERIOD
+#define RDV_HELP_POST_PERIOD 3        /* helper-warp variant: steps between the workers' request posts (1: 12 % slower, 2-4 alike) */
+#endif
+#ifndef RDV_HELP_IDLE_NS
+#define RDV_HELP_IDLE_NS 500          /* helper-warp variant: sleep of an idle helper between polls */
+#endif
 #ifndef RDV_TMEM_STASH
 #define RDV_TMEM_STASH 1              /* fused actor: park the cold per-env registers in tensor memory across the solves */
 #endif
@@ -484,12 +490,20 @@ RDV_DEV void take_reset_row(const double *rw, const int64_t rs, EnvRegs &e, EnvC
 
 // OBS: the float32 observation is formed every step (the actor's input, a per-step record); without it only its Box
 // test is evaluated, on the raw state (obs_in_box_state), and the observation is formed once at the end of the launch.
-template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false, bool MC = false, bool TABLE = false, bool OBS = POLICY>
-__global__ void __launch_bounds__(TPB_, 1)
+// HELP: the CTA carries two more warps than its TPB_ / 32 worker warps.  65,536 envs are 13.84 worker warps per SM,
+// which the hardware deals out 4-4-3-3 over the four schedulers: two schedulers set the pace, two idle a quarter of the
+// time.  The helper warps land on those two (warp id mod 4) and take the one piece of the step that does not depend on
+// the trajectory off the workers: recomputing the reset rows that were used.  Workers post (lane, episode) requests in
+// shared memory and never wait -- a row that is not ready when its lane finishes is computed on the spot, as before.
+template <bool ISO, bool CLOSED, int TPB_, bool POLICY = false, bool MC = false, bool TABLE = false, bool OBS = POLICY,
+          bool HELP = false>
+__global__ void __launch_bounds__(TPB_ + (HELP ? 64 : 0), 1)
 rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __grid_constant__ RdvRolloutIO io,
                const int64_t n, const uint64_t seed, const int64_t env_offset)
 {
-    constexpr int NW = TPB_ / 32;
+    static_assert(!HELP || (!POLICY && !MC && !TABLE && !OBS), "helper warps: plain variant only");
+    constexpr int NW = TPB_ / 32;                       // worker warps
+    constexpr int NWT = NW + (HELP ? 2 : 0);            // all warps of the CTA
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     tc::TileSmem *ts = reinterpret_cast<tc::TileSmem *>(dyn_smem);
     uint32_t tmem_all = 0, mma_phase = 0;
@@ -515,10 +529,22 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     // rows the carve-out was 132 KiB and one spill load in ten went to the L2).
     constexpr bool own_stage = !POLICY && OBS;
     __shared__ __align__(16) float s_obs[own_stage ? NW : 1][own_stage ? 32 * RDV_OBS_DIM : 4];
-    __shared__ double s_stats[NW][RDV_NSTATS];
-    __shared__ double s_team[NW][4][RDV_TEAM_ROW];
+    __shared__ double s_stats[NWT][RDV_NSTATS];
+    __shared__ double s_team[NWT][4][RDV_TEAM_ROW];
+    // helper protocol: episode each lane's row in shared memory was computed for (-1: none), episode a row is wanted
+    // for, lanes with an open request, and the end-of-launch flag
+    __shared__ int s_row_ep[HELP ? NW : 1][32], s_ep_req[HELP ? NW : 1][32];
+    __shared__ unsigned s_todo[HELP ? NW : 1];
+    __shared__ unsigned s_cancel;                       // worker warps that are leaving the step loop
+    __shared__ int s_inflight[2];                       // 1 + the worker warp each helper is serving (0: none)
+    __shared__ int s_ndone;                             // worker warps that have left the step loop
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (HELP) {
+        if (threadIdx.x < NW) s_todo[threadIdx.x] = 0u;
+        if (threadIdx.x == 0) { s_ndone = 0; s_cancel = 0u; s_inflight[0] = s_inflight[1] = 0; }
+        __syncthreads();
+    }
     const int src = io.action_source;
     const int64_t ld = S.ld;
     // Reset prefetch: the reset state of (env, episode + 1) does not depend on the trajectory, so every lane keeps its
@@ -557,7 +583,52 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
 
-    for (int pass = 0; pass < passes; ++pass) {
+    if constexpr (HELP) {
+        if (warp >= NW && passes > 0) {
+            // ---- helper warp h serves worker warps h, h + 2, ... until all of them have left the step loop (the host
+            //      launches this variant only when every CTA has a single pass, so env (ww, l) is
+            //      env_offset + lo + 32 ww + l).  (Handing the four teams of a pass requests of different warps, so
+            //      that every pass is full, measured slower: 3.9 us per pass against 2.5.)
+            const RdvParams &P = Pc;
+            const int h = warp - NW;
+            for (;;) {
+                bool worked = false;
+                for (int ww = h; ww < NW; ww += 2) {
+                    if (!*(volatile unsigned *)&s_todo[ww]) continue;
+                    // publish the warp, then take its requests: a leaving warp either finds its requests still there
+                    // (and takes them back) or sees this flag and waits for the pass in flight
+                    unsigned m = 0;
+                    if (lane == 0) {
+                        *(volatile int *)&s_inflight[h] = ww + 1;
+                        __threadfence_block();
+                        m = atomicExch(&s_todo[ww], 0u);
+                    }
+                    m = __shfl_sync(full, m, 0);
+                    worked = true;
+                    double *rows = reinterpret_cast<double *>(dyn_smem) + (size_t)ww * 32 * RDV_NEXT_ROW;
+                    while (m && !((*(volatile unsigned *)&s_cancel >> ww) & 1u)) {
+                        const int team = lane >> 3;
+                        const unsigned src_bit = __fns(m, 0, team + 1);
+                        const int src_lane = src_bit < 32 ? (int)src_bit : 0;
+                        const int r_episode = *(volatile int *)&s_ep_req[ww][src_lane];
+                        team_reset_core(P, seed, env_offset + lo + ww * 32 + src_lane, r_episode, nullptr,
+                                        src_bit < 32 ? rows + src_lane * RDV_NEXT_ROW : s_team[warp][team]);
+                        __threadfence_block();                           // row before tag
+                        if (src_bit < 32 && (lane & 7) == 0) *(volatile int *)&s_row_ep[ww][src_lane] = r_episode;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) m &= m - 1;
+                    }
+                    __syncwarp();
+                    __threadfence_block();
+                    if (lane == 0) *(volatile int *)&s_inflight[h] = 0;
+                }
+                if (*(volatile int *)&s_ndone >= NW) break;
+                if (!worked) __nanosleep(RDV_HELP_IDLE_NS);
+            }
+        }
+    }
+
+    for (int pass = 0; pass < ((HELP && warp >= NW) ? 0 : passes); ++pass) {
         const int64_t c_lo = lo + pass * chunk, c_hi = (c_lo + chunk < hi) ? c_lo + chunk : hi;
         const int64_t warp_base = c_lo + warp * 32;
         const int64_t i_raw = warp_base + lane;
@@ -574,7 +645,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
         float ov[RDV_OBS_DIM];
         if (want_obs) make_obs(e, obs_scale(P), ov);
         unsigned fresh = 0;                                    // lanes whose next reset row is ready
-        int countdown = refill;                                // steps until the next refill of the rows
+        int countdown = HELP ? RDV_HELP_POST_PERIOD : refill;  // steps until the next refill of the rows (HELP: next post)
         // where this lane's row lives
         double *my_row = POLICY ? io.reset_rows + i : next_rows + lane * RDV_NEXT_ROW;
         const int64_t row_stride = POLICY ? ld : 1;
@@ -586,6 +657,21 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                 for (int j = 0; j < RDV_NEXT_ROW; ++j) my_row[j] = io.reset_rows[j * ld + i];
             }
             __syncwarp();
+        }
+        // posts a request for every active lane whose row is not the one its NEXT reset needs
+        auto post_requests = [&]() {
+            if constexpr (HELP) {
+                const bool want = active && *(volatile int *)&s_row_ep[warp][lane] != c.episode + 1;
+                if (want) s_ep_req[warp][lane] = c.episode + 1;
+                const unsigned wm = __ballot_sync(full, want);
+                __threadfence_block();
+                if (lane == 0 && wm) atomicOr(&s_todo[warp], wm);
+            }
+        };
+        if constexpr (HELP) {
+            s_row_ep[warp][lane] = ((fresh >> lane) & 1u) ? c.episode + 1 : -1;
+            __syncwarp();
+            post_requests();
         }
         // rows for the lanes of `todo`, four per pass of the warp's teams
         auto fill_rows = [&](unsigned todo) {
@@ -748,7 +834,35 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                 }
             }
             // ---- auto-reset inside the warp ----
-            if (!MC && io.auto_reset && refill) {
+            if constexpr (HELP) {
+                // rows come from the helper warps; what is not ready is computed here, four lanes per pass
+                const unsigned m = __ballot_sync(full, done);
+                if (m) {
+                    const bool have = done && *(volatile int *)&s_row_ep[warp][lane] == c.episode + 1;
+                    unsigned need = m & ~__ballot_sync(full, have);
+                    if (have) {
+                        __threadfence_block();                                   // tag before row
+                        take_reset_row(my_row, 1, e, c);
+                    }
+                    while (need) {
+                        const int team = lane >> 3;
+                        const unsigned src_bit = __fns(need, 0, team + 1);
+                        const int src_lane = src_bit < 32 ? (int)src_bit : lane;
+                        const int64_t r_env = __shfl_sync(full, env_id, src_lane);
+                        const int r_episode = __shfl_sync(full, c.episode, src_lane) + 1;
+                        team_reset_core(P, seed, r_env, r_episode, nullptr, s_team[warp][team]);
+                        const int rank = __popc(need & ((1u << lane) - 1));
+                        if (((need >> lane) & 1u) && rank < 4) take_reset_row(s_team[warp][rank], 1, e, c);
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) need &= need - 1;
+                    }
+                }
+                if (--countdown <= 0) {
+                    countdown = RDV_HELP_POST_PERIOD;
+                    post_requests();
+                }
+            } else if (!MC && io.auto_reset && refill) {
                 // prefetched rows: compute what is missing right now (rare), consume, refill periodically
                 const unsigned m = __ballot_sync(full, done);
                 const unsigned need = m & ~fresh;
@@ -817,10 +931,11 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                 // step a barrier every step was best (every 2 / 4 steps: 1 % / 8 % slower); the plane solver's step is
                 // smaller and tolerates drift: every step 12.06, every 4-8 steps 11.66, every 32 steps 11.77, never
                 // 12.1-12.2 us per step.
-#if RDV_SYNC_PERIOD == 1
-                __syncthreads();
-#elif RDV_SYNC_PERIOD > 1
-                if ((k % RDV_SYNC_PERIOD) == 0) __syncthreads();
+#if RDV_SYNC_PERIOD >= 1
+                if ((k % RDV_SYNC_PERIOD) == 0) {
+                    if constexpr (HELP) asm volatile("bar.sync 2, %0;" :: "n"(TPB_) : "memory");   // the workers only
+                    else __syncthreads();
+                }
 #endif
                 // ---- action ----
                 const int64_t row = (int64_t)k * n + i;
@@ -851,13 +966,33 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
 
         // ---- the rows that were used since the last refill are recomputed before they go back to the scratch,
         //      so the next launch starts with every row ready ----
+        if constexpr (HELP) {
+            // leave: no more requests of this warp are picked up, a pass that is working on one of its rows is waited
+            // for (under 3 us, one time in ten), and what is not ready is computed below.  No CTA barrier: the warps
+            // leave at their own pace, as in the plain variant.
+            if (lane == 0) {
+                atomicOr(&s_cancel, 1u << warp);
+                atomicExch(&s_todo[warp], 0u);
+                __threadfence_block();
+                while (*(volatile int *)&s_inflight[warp & 1] == warp + 1) { }
+                atomicAdd(&s_ndone, 1);
+            }
+            __syncwarp();
+            __threadfence_block();
+            fresh = __ballot_sync(full, active && *(volatile int *)&s_row_ep[warp][lane] == c.episode + 1);
+        }
         if (persist) {
-            const unsigned todo = __ballot_sync(full, active) & ~fresh;
+            // (helper variant: what is not ready stays not ready -- the tag says so -- and is the helpers' first work
+            //  of the next launch, when they would otherwise idle)
+            const unsigned todo = HELP ? 0u : __ballot_sync(full, active) & ~fresh;
             fill_rows(todo);
             if (!POLICY && active) {
+                const bool ready = !HELP || ((fresh >> lane) & 1u);
+                if (ready) {
 #pragma unroll
-                for (int j = 0; j < RDV_NEXT_ROW; ++j) io.reset_rows[j * ld + i] = my_row[j];
-                io.reset_rows[RDV_ROW_TAG * ld + i] = (double)(c.episode + 1);
+                    for (int j = 0; j < RDV_NEXT_ROW; ++j) io.reset_rows[j * ld + i] = my_row[j];
+                }
+                io.reset_rows[RDV_ROW_TAG * ld + i] = ready ? (double)(c.episode + 1) : -1.0;
             }
             __syncwarp();
         }
@@ -887,7 +1022,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
         for (int j = lane; j < rows_w * RDV_OBS_DIM; j += 32) dst[j] = obs_stage[j];
         __syncwarp();
     }
-    if (io.stats) reduce_stats<NW>(st, io.stats, s_stats);
+    if (io.stats) reduce_stats<NWT>(st, io.stats, s_stats);
     if (POLICY || main_stash) tc::tile_teardown(tmem_all);
 }
 
@@ -1117,6 +1252,7 @@ static int env_int(const char *name, int fallback)
 static std::atomic<int> g_tune_tpb{env_int("RDV_ROLLOUT_TPB", 0)};
 static std::atomic<int> g_tune_refill{env_int("RDV_RESET_REFILL", 12)};
 static std::atomic<int> g_tune_pdl{env_int("RDV_ROLLOUT_PDL", 1)};
+static std::atomic<int> g_tune_helpers{env_int("RDV_ROLLOUT_HELPERS", 1)};
 
 extern "C" {
 
@@ -1127,6 +1263,7 @@ int rdv_tune(int key, int value)
     if (key == RDV_TUNE_ROLLOUT_TPB) return g_tune_tpb.exchange(value);
     if (key == RDV_TUNE_RESET_REFILL) return g_tune_refill.exchange(value);
     if (key == RDV_TUNE_ROLLOUT_PDL) return g_tune_pdl.exchange(value);
+    if (key == RDV_TUNE_ROLLOUT_HELPERS) return g_tune_helpers.exchange(value);
     return RDV_ERR_SIZE;
 }
 int rdv_sizeof_params(void) { return (int)sizeof(RdvParams); }
@@ -1373,11 +1510,17 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     // per-step observation records: one CTA shape with the observation formed every step (every shape gives the same bits)
 #define RDV_LAUNCH_OBS(ISO_, CL_) \
     RDV_LAUNCH_K((rollout_kernel<ISO_, CL_, 256, false, false, false, true>), 256, RDV_ROWS_SMEM(256))
+    // 14 worker warps + 2 helper warps (see rollout_kernel): single-pass launches of the 448-env shape with auto-reset
+    const bool helpers = g_tune_helpers.load(std::memory_order_relaxed) && io->auto_reset && io_k.reserved > 0 &&
+                         (io_k.reset_rows != nullptr || io->steps >= 2 * io_k.reserved) &&
+                         passes == 1 && chunk > 384 && chunk <= 448;
+#define RDV_LAUNCH_H(ISO_, CL_) \
+    RDV_LAUNCH_K((rollout_kernel<ISO_, CL_, 448, false, false, false, false, true>), 512, RDV_ROWS_SMEM(448))
 #define RDV_PICK_R(ISO_, CL_)                                 \
     if (io->obs_steps) RDV_LAUNCH_OBS(ISO_, CL_)              \
     else if (chunk <= 256) RDV_LAUNCH_R(ISO_, CL_, 256)       \
     else if (chunk <= 384) RDV_LAUNCH_R(ISO_, CL_, 384)       \
-    else if (chunk <= 448) RDV_LAUNCH_R(ISO_, CL_, 448)       \
+    else if (chunk <= 448) { if (helpers && ISO_ && !CL_) RDV_LAUNCH_H(true, false) else RDV_LAUNCH_R(ISO_, CL_, 448) } \
     else RDV_LAUNCH_R(ISO_, CL_, 512)
 #define RDV_LAUNCH_P(T_) RDV_LAUNCH_K((rollout_kernel<true, false, T_, true, false>), T_, sizeof(tc::TileSmem))
     if (table) {
@@ -1405,6 +1548,7 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
 #undef RDV_LAUNCH_OBS
 #undef RDV_LAUNCH_P
 #undef RDV_PICK_R
+#undef RDV_LAUNCH_H
 #undef RDV_LAUNCH_R
 #undef RDV_ROWS_SMEM
 #undef RDV_LAUNCH_K

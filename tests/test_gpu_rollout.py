@@ -256,6 +256,55 @@ def test_reset_rows_carried_over_many_short_launches():
     assert p1.read_stats()["episodes"] == p2.read_stats()["episodes"] > n
 
 
+def test_helper_warps_are_bit_identical():
+    """65,536 envs on 148 SMs run as 14 worker warps + 2 helper warps per CTA; the helpers recompute used reset rows on
+    request and the workers never wait for them (a row that is not ready is computed on the spot).  Same bits as the
+    plain kernel: long and short episodes (t_max = 4: envs finish again before their row is back), rows handed from
+    launch to launch in both directions (a helper launch leaves not-ready rows tagged as such), caller interventions
+    between launches, one SM left free, and forced onto small CTAs."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv, _native as N
+
+    def run(n, helpers_of_launch, **kw):
+        env = BatchedRendezvousEnv(n, seed=3, **kw)
+        env.reset()
+        base, outs = 0, []
+        for j, (steps, carry, reserve) in enumerate(((37, True, 0), (20, True, 0), (5, True, 1), (20, True, 0),
+                                                     (9, False, 0), (16, True, 0))):
+            _tune(N.TUNE_ROLLOUT_HELPERS, helpers_of_launch(j))
+            env.sm_reserve = reserve
+            out = env.rollout(steps, action_seed=5, step_base=base, record_rewards=True, record_dones=True,
+                              carry_reset_rows=carry)
+            outs += [out["rewards"].clone(), out["dones"].clone()]
+            base += steps
+            if j == 2:
+                mask = torch.zeros(n, dtype=torch.uint8, device=env.device)
+                mask[::5] = 1
+                env.reset(mask=mask)                    # bumps episode indices: carried rows of those envs are stale
+        return [env.get_state().clone(), env.i32.clone(), env.obs.clone()] + outs, env.read_stats()
+
+    try:
+        for n, kw in ((65536, dict()), (65536, dict(t_max=4)), (62000, dict(t_max=9))):
+            ref, ref_stats = run(n, lambda j: 0, **kw)
+            assert ref_stats["episodes"] > n
+            for pattern in (lambda j: 1, lambda j: j % 2, lambda j: (j + 1) % 2):
+                got, got_stats = run(n, pattern, **kw)
+                for a, b in zip(ref, got):
+                    assert torch.equal(a, b), (n, kw)
+                for key in ("steps", "episodes", "rk_accepted", "rk_rejected", "end_attitude", "end_time"):
+                    assert ref_stats[key] == got_stats[key], key
+        # small batch forced onto the 448-thread shape: mostly idle lanes, helpers on
+        _tune(N.TUNE_ROLLOUT_TPB, 448)
+        small = []
+        for h in (0, 1):
+            small.append(run(3000, lambda j: h, t_max=6)[0])
+        for a, b in zip(*small):
+            assert torch.equal(a, b)
+    finally:
+        _tune(N.TUNE_ROLLOUT_TPB, 0)
+        _tune(N.TUNE_ROLLOUT_HELPERS, 1)
+
+
 def _policy():
     import os
     from helpers import GOLDEN
