@@ -399,7 +399,7 @@ def run_cuda(args):
         from reinforcement_learning_rendezvous_b200 import MlpPolicy
         pol = MlpPolicy.load(pol_path, device=dev)
         what = ("SB3 MlpPolicy actor 17-64-64-6 tanh (models/mlp_model_best weights), deterministic, "
-                "3xTF32 tcgen05.mma (TMEM-resident activations) inside rollout_kernel")
+                "split-fp16 (3 MMAs per product, fp32-level accuracy) tcgen05.mma with TMEM-resident activations inside rollout_kernel")
 
         def policy_leg(penv, kl):
             penv.sm_reserve = 1 if world > 1 else 0

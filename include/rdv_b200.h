@@ -275,7 +275,7 @@ int rdv_frame_transform(const double *q, const double *v, double *out, int64_t n
 
 /* -- stand-alone policy forward (model.predict of an SB3 MlpPolicy, monte_carlo.py:128-133) ----------------
  * obs [n][17] float32 -> actions [n][6] float32, deterministic mean clipped to [-1,1].
- * rdv_policy_forward: tcgen05 tensor-core kernel (TMEM accumulators, 3xTF32 = fp32-level accuracy).
+ * rdv_policy_forward: tcgen05 tensor-core kernel (TMEM accumulators, every product as three MMAs of fp16 halves = fp32-level accuracy).
  * rdv_policy_forward_ffma: the same op as plain fp32 FMAs, one thread per env (numerics reference). */
 int rdv_policy_forward(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);
 int rdv_policy_forward_ffma(const RdvPolicy *pi, const float *obs, float *actions, int64_t n, void *cuda_stream);

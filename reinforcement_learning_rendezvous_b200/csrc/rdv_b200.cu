@@ -563,7 +563,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     // only live between the step barrier and the end of the actor's third layer
     // (without per-step records: the warp's reset rows, 32 x 22 doubles, which have gone back to the scratch -- or are
     // simply not needed any more -- when the final observation is written)
-    float *obs_stage = POLICY ? ts->al[warp >> 2] + (warp & 3) * (32 * RDV_OBS_DIM)
+    float *obs_stage = POLICY ? reinterpret_cast<float *>(ts->al[warp >> 2]) + (warp & 3) * (32 * RDV_OBS_DIM)
                               : own_stage ? s_obs[own_stage ? warp : 0] : reinterpret_cast<float *>(next_rows);
     constexpr bool want_obs = POLICY || OBS;
     // this CTA's slice [lo, hi) and its passes; with a parameter table the slices are cut at multiples of 32 envs so

@@ -1,5 +1,5 @@
 // rdv_policy.cuh -- small pieces shared by the actor kernels (the SB3 MlpPolicy actor 17 -> 64 -> 64 -> 6, tanh;
-// main.py:39-48): the TF32 split of a float and the Gaussian head's Philox / Box-Muller noise.  The tensor-core
+// main.py:39-48): the TF32 rounding of a float (TF32 build of the actor) and the Gaussian head's Philox / Box-Muller noise.  The tensor-core
 // forward itself (tcgen05 / TMEM, stand-alone and inside the rollout kernel) lives in rdv_policy_tc.cuh, the
 // plain fp32-FMA numerics reference in rdv_b200.cu (policy_kernel).
 #pragma once

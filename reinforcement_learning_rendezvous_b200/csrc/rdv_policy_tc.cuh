@@ -7,18 +7,24 @@
 // A group of 128 threads owns tiles of 128 environments (UMMA M = 128, one env per thread / TMEM lane):
 //
 //   obs tile: one 8.7 KB bulk copy (cp.async.bulk, mbarrier complete_tx) into shared memory, prefetched one tile
-//             ahead; every thread splits its row into TF32 hi / lo
-//   layer 1: D[128x64] = A0[128x24] W0^T    3 K-steps x 3 products (3xTF32); the bias rides in a padding column
+//             ahead; every thread splits its row into two fp16 halves, hi = fp16(x) and lo = fp16(x - hi)
+//   layer 1: D[128x64] = A0[128x32] W0^T    2 K-steps x 3 products; the bias rides in a padding column
 //   tcgen05.ld D -> registers, tanh, split -> A1 hi to TMEM (tcgen05.st), A1 lo to shared memory
-//   layer 2: D[128x64] = A1 W1^T            8 K-steps x 3
+//   layer 2: D[128x64] = A1 W1^T            4 K-steps x 3
 //   tcgen05.ld D -> + bias, tanh, split -> A2
-//   layer 3: D[128x16] = A2 W2^T            8 K-steps x 3 (6 outputs padded to N = 16)
+//   layer 3: D[128x16] = A2 W2^T            4 K-steps x 3 (6 outputs padded to N = 16)
 //   tcgen05.ld D -> + bias, clip -> actions
 //
-// Every product is 3xTF32 (a_lo b_hi + a_hi b_lo + a_hi b_hi) so the result has fp32-level accuracy, like the
-// reference's torch policy.  The hi part of the activations never leaves the tensor-memory: the two products that
-// use it are issued in the "TS" form of tcgen05.mma (A from TMEM, lane = row, one 32-bit column per K element);
-// only the lo part goes through shared memory (K-major, no swizzle).  That halves the shared-memory footprint of
+// Every product is three MMAs of halves (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulation) so the result has
+// fp32-level accuracy, like the reference's torch policy: 11 + 11 significant bits per operand.  The halves are
+// fp16 (kind::f16, K = 16 per MMA): observations, tanh outputs and weights are O(1), far inside the fp16 range, lo
+// is exact down to 2^-24 in absolute terms, and a layer costs half the MMAs of the TF32 split (kind::tf32, K = 8;
+// RDV_ACTOR_F16 = 0 builds it) -- the small-N MMAs of this MLP are issue-rate bound, so that is half the tensor time:
+// [B200] 19.5 us against 23.2 for 131,072 rows, worst deviation from an fp64 evaluation 2.7e-6 against 5.0e-6 (the
+// MMA truncates the TF32 lo half; the fp16 halves are rounded to nearest).  The hi part of the activations never
+// leaves the tensor-memory: the two products that use it are issued in the "TS" form of tcgen05.mma (A from TMEM,
+// lane = row, one 32-bit column per pair of K elements, k even in the low half); only the lo part goes through
+// shared memory (K-major, no swizzle).  That halves the shared-memory footprint of
 // a tile, so a CTA runs FOUR 128-thread groups side by side (512 threads, shared weights; private mbarriers,
 // named barriers, 128 TMEM columns each: D @ +0..63, A hi @ +64..127): while one group waits for its MMAs or its
 // TMEM loads, three others run their tanh epilogues.  Per group a single thread issues the MMAs and commits them
@@ -27,21 +33,35 @@
 // and the split.
 //
 // Shared-memory operands use the canonical no-swizzle K-major UMMA layout: 8-row x 16-byte core matrices, rows of
-// a core matrix 16 B apart, 8-row groups SBO = 128 B apart, the two 16-byte K-chunks of a K = 8 step
-// LBO = rows*16 B apart, i.e. element (r, k) lives at ((k / 4) * rows + r) * 16 + (k % 4) * 4 bytes.
+// a core matrix 16 B apart, 8-row groups SBO = 128 B apart, the two 16-byte K-chunks of a K-step
+// LBO = rows*16 B apart, i.e. with CHUNK = 8 fp16 (4 TF32) elements per 16 bytes element (r, k) lives at
+// ((k / CHUNK) * rows + r) * 16 + (k % CHUNK) * sizeof(element) bytes.
 // (Descriptor bit layouts: CUTLASS cute/arch/mma_sm100_desc.hpp; instruction forms: cute/arch/mma_sm100_umma.hpp.)
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "rdv_b200.h"
 #include "rdv_policy.cuh"
+
+#ifndef RDV_ACTOR_F16
+#define RDV_ACTOR_F16 1      /* 1: operands split into two fp16 halves (kind::f16, K = 16); 0: TF32 halves (kind::tf32, K = 8) */
+#endif
 
 namespace rdv {
 namespace tc {
 
 constexpr int TM = 128;                 // envs per tile = UMMA M = threads per group
 constexpr int H = 64;                   // hidden width
+#if RDV_ACTOR_F16
+typedef uint16_t elem_t;                // operand element in shared memory: fp16 bits
+constexpr int KSTEP = 16, CHUNK = 8;    // K of one MMA; elements of one 16-byte chunk of a core-matrix row
+constexpr int K0 = 32;                  // 17 inputs + 1 bias column, padded to 2 K-steps of 16
+#else
+typedef float elem_t;
+constexpr int KSTEP = 8, CHUNK = 4;
 constexpr int K0 = 24;                  // 17 inputs + 1 bias column, padded to 3 K-steps of 8
+#endif
 constexpr int N3 = 16;                  // 6 outputs padded to the smallest legal UMMA N for M = 128
 constexpr int GROUPS = 4;               // independent 128-thread tile pipelines per CTA
 constexpr uint32_t GROUP_COLS = 128;    // TMEM columns per group: D @ +0..63 (D3 @ +0..15), A hi @ +64..127
@@ -52,10 +72,10 @@ constexpr float TANH_SCALE = 2.8853900817779268f;       // 2 log2(e)
 
 // what a tile forward needs: lo activations per group, split weights, biases, MMA mbarriers, the TMEM base
 struct TileSmem {
-    float al[GROUPS][(H / 4) * TM * 4];                          // lo part of the activations, [group][chunk][row][4]
-    float w0h[(K0 / 4) * H * 4], w0l[(K0 / 4) * H * 4];          // [chunk][n][4]
-    float w1h[(H / 4) * H * 4], w1l[(H / 4) * H * 4];
-    float w2h[(H / 4) * N3 * 4], w2l[(H / 4) * N3 * 4];
+    alignas(16) elem_t al[GROUPS][H * TM];                       // lo part of the activations, [group][chunk][row][CHUNK]
+    alignas(16) elem_t w0h[K0 * H], w0l[K0 * H];                 // [chunk][n][CHUNK]
+    alignas(16) elem_t w1h[H * H], w1l[H * H];
+    alignas(16) elem_t w2h[H * N3], w2l[H * N3];
     float b1[H], b2[N3], std[8];                                 // std = exp(log_std) (0 without a Gaussian head)
     uint64_t mma_bar[GROUPS];
     uint32_t tmem_base, pad[3];
@@ -79,17 +99,22 @@ __device__ __forceinline__ uint64_t umma_desc(const void *p, uint32_t lbo_bytes,
     d |= (uint64_t)1 << 46;                                        // descriptor version of sm_100
     return d;
 }
-// 32-bit instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n.
+// 32-bit instruction descriptor: D = F32, A = B = TF32 (format 2) or F16 (format 0), both K-major, M = 128, N = n.
 __device__ __forceinline__ uint32_t umma_idesc(int n)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t fmt = RDV_ACTOR_F16 ? 0u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 // D += A B with A described in shared memory ("SS")
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+#if RDV_ACTOR_F16
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+#else
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+#endif
         :: "r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // D += A B with A read from tensor memory ("TS"): 128 lanes x 8 columns at tmem_a
@@ -97,7 +122,11 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+#if RDV_ACTOR_F16
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+#else
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+#endif
         :: "r"(tmem_d), "r"(tmem_a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
@@ -147,6 +176,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// the two halves of a float: hi = the value rounded to the operand format, lo = what is left, rounded likewise
+// (fp16: 11 + 11 significant bits, lo exact down to 2^-24 in absolute terms; TF32: 11 + 11 bits, lo truncated by the MMA)
+#if RDV_ACTOR_F16
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+#endif
+
 // bulk copy global -> shared, completion counted in bytes on an mbarrier (one thread issues both)
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -175,33 +217,41 @@ struct WeightTile {
             }
         }
     }
-    __device__ __forceinline__ void store(float scale, float *wh, float *wl) const
+    __device__ __forceinline__ void store(float scale, elem_t *wh, elem_t *wl) const
     {
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int idx = threadIdx.x + i * NT;
             if (idx < N_PAD * K_PAD) {
                 const int nn = idx / K_PAD, k = idx % K_PAD;
-                const float v = x[i] * scale, hi = tf32_hi(v);
-                const int o = ((k >> 2) * N_PAD + nn) * 4 + (k & 3);
+                const int o = ((k / CHUNK) * N_PAD + nn) * CHUNK + (k % CHUNK);
+                const float v = x[i] * scale;
+#if RDV_ACTOR_F16
+                const __half hi = __float2half_rn(v);
+                wh[o] = __half_as_ushort(hi);
+                wl[o] = __half_as_ushort(__float2half_rn(v - __half2float(hi)));
+#else
+                const float hi = tf32_hi(v);
                 wh[o] = hi;
                 wl[o] = v - hi;
+#endif
             }
         }
     }
 };
 
-// one layer: D[128 x n] (TMEM column d_col) = A[128 x 8*ksteps] W^T, 3xTF32, issued by the calling thread.
-// A hi: TMEM columns a_hi + 8 kk .. + 7; A lo: shared memory.
-__device__ __forceinline__ void issue_layer(uint32_t a_hi, const float *al, uint32_t tmem_d, const float *wh, const float *wl,
-                                            int n, int ksteps, uint64_t *bar)
+// one layer: D[128 x n] (TMEM column d_col) = A[128 x KSTEP*ksteps] W^T, three products of halves, issued by the
+// calling thread.  A hi: TMEM columns a_hi + 8 kk .. + 7 (one 32-bit column per TF32 element / per pair of fp16
+// elements); A lo: shared memory.  A K-step is two 16-byte chunks per row whatever the element size.
+__device__ __forceinline__ void issue_layer(uint32_t a_hi, const elem_t *al, uint32_t tmem_d, const elem_t *wh,
+                                            const elem_t *wl, int n, int ksteps, uint64_t *bar)
 {
     const uint32_t idesc = umma_idesc(n);
     const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)n * 16;
     for (int kk = 0; kk < ksteps; ++kk) {
-        const uint64_t a_lo = umma_desc(al + (size_t)kk * 2 * TM * 4, lbo_a, 128);
-        const uint64_t b_hi = umma_desc(wh + (size_t)kk * 2 * n * 4, lbo_b, 128);
-        const uint64_t b_lo = umma_desc(wl + (size_t)kk * 2 * n * 4, lbo_b, 128);
+        const uint64_t a_lo = umma_desc(al + (size_t)kk * 2 * TM * CHUNK, lbo_a, 128);
+        const uint64_t b_hi = umma_desc(wh + (size_t)kk * 2 * n * CHUNK, lbo_b, 128);
+        const uint64_t b_lo = umma_desc(wl + (size_t)kk * 2 * n * CHUNK, lbo_b, 128);
         umma_ss(tmem_d, a_lo, b_hi, idesc, kk > 0 ? 1u : 0u);
         umma_ts(tmem_d, a_hi + 8 * kk, b_lo, idesc, 1u);
         umma_ts(tmem_d, a_hi + 8 * kk, b_hi, idesc, 1u);
@@ -241,7 +291,7 @@ __device__ __forceinline__ void tanh_scaled4(const float (&z)[4], float (&t)[4])
 // hidden-layer epilogue: D (64 columns of this thread's lane) -> tanh -> A hi (TMEM) / A lo (shared), the TMEM load
 // of the next 16 columns in flight while the current 16 are processed
 template <bool BIAS>
-__device__ __forceinline__ void hidden_epilogue(uint32_t lane_addr, const float *bias, float *al, int r)
+__device__ __forceinline__ void hidden_epilogue(uint32_t lane_addr, const float *bias, elem_t *al, int r)
 {
     uint32_t va[16], vb[16];
     tmem_ld16_issue(lane_addr, va);
@@ -251,24 +301,39 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t lane_addr, const float 
         uint32_t (&cur)[16] = (q & 1) ? vb : va;
         uint32_t (&nxt)[16] = (q & 1) ? va : vb;
         if (q < 3) tmem_ld16_issue(lane_addr + 16 * (q + 1), nxt);
-        uint32_t hi[16];
+        float t[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            float z[4], t[4], lo[4];
+            float z[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 z[j] = __uint_as_float(cur[4 * c + j]);
                 if (BIAS) z[j] += bias[16 * q + 4 * c + j];
             }
-            tanh_scaled4(z, t);
+            tanh_scaled4(z, reinterpret_cast<float (&)[4]>(t[4 * c]));
+        }
+#if RDV_ACTOR_F16
+        // 16 activations = 8 packed TMEM columns (hi) and two 16-byte chunks of this row (lo)
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split2(t[2 * j], t[2 * j + 1], hi[j], lo[j]);
+        reinterpret_cast<uint4 *>(al)[(2 * q) * TM + r] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        reinterpret_cast<uint4 *>(al)[(2 * q + 1) * TM + r] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        tmem_st8(lane_addr + A_COL + 8 * q, hi);
+#else
+        uint32_t hi[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                hi[4 * c + j] = __float_as_uint(t[j]) & 0xffffe000u;
-                lo[j] = t[j] - __uint_as_float(hi[4 * c + j]);
+                hi[4 * c + j] = __float_as_uint(t[4 * c + j]) & 0xffffe000u;
+                lo[j] = t[4 * c + j] - __uint_as_float(hi[4 * c + j]);
             }
             reinterpret_cast<float4 *>(al)[(4 * q + c) * TM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
         tmem_st16(lane_addr + A_COL + 16 * q, hi);
+#endif
         if (q < 3) tmem_ld_wait(nxt);
     }
     tmem_st_wait();
@@ -329,10 +394,32 @@ template <class F>
 __device__ __forceinline__ void tile_forward(TileSmem &s, int g, int r, int threads, const float (&x)[RDV_OBS_DIM],
                                              uint32_t tmem, uint32_t &phase, float (&out)[RDV_ACT_DIM], F &&after_issue)
 {
-    float *al = s.al[g];
+    elem_t *al = s.al[g];
     uint64_t *bar = &s.mma_bar[g];
     const uint32_t lane_addr = tmem + ((uint32_t)(r & ~31) << 16);         // this warp's 32 TMEM lanes
     // ---- A0: the observation row and the constant 1 of the bias column, hi -> TMEM, lo -> shared ----
+#if RDV_ACTOR_F16
+    {
+        // (values beyond the fp16 range are clamped: the first layer's tanh is saturated long before)
+        uint32_t hi[K0 / 2], lo[K0 / 2];
+#pragma unroll
+        for (int j = 0; j < K0 / 2; ++j) {
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = 2 * j + u;
+                v[u] = k < RDV_OBS_DIM ? fminf(60000.0f, fmaxf(-60000.0f, x[k < RDV_OBS_DIM ? k : 0]))
+                                       : (k == RDV_OBS_DIM ? 1.0f : 0.0f);
+            }
+            split2(v[0], v[1], hi[j], lo[j]);
+        }
+#pragma unroll
+        for (int c = 0; c < K0 / CHUNK; ++c)
+            reinterpret_cast<uint4 *>(al)[c * TM + r] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        tmem_st16(lane_addr + A_COL, hi);
+        tmem_st_wait();
+    }
+#else
     {
         uint32_t hi[K0];
 #pragma unroll
@@ -356,13 +443,14 @@ __device__ __forceinline__ void tile_forward(TileSmem &s, int g, int r, int thre
         tmem_st8(lane_addr + A_COL + 16, h1);
         tmem_st_wait();
     }
+#endif
     fence_async_smem();
     tc_fence_before();
     group_sync(g, threads);
     // ---- layer 1 ----
     if (r == 0) {
         tc_fence_after();
-        issue_layer(tmem + A_COL, al, tmem, s.w0h, s.w0l, H, K0 / 8, bar);
+        issue_layer(tmem + A_COL, al, tmem, s.w0h, s.w0l, H, K0 / KSTEP, bar);
         after_issue();
     }
     mbar_wait(bar, phase);
@@ -375,7 +463,7 @@ __device__ __forceinline__ void tile_forward(TileSmem &s, int g, int r, int thre
     // ---- layer 2 (D is reused: the layer-1 epilogue has drained it) ----
     if (r == 0) {
         tc_fence_after();
-        issue_layer(tmem + A_COL, al, tmem, s.w1h, s.w1l, H, H / 8, bar);
+        issue_layer(tmem + A_COL, al, tmem, s.w1h, s.w1l, H, H / KSTEP, bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -387,7 +475,7 @@ __device__ __forceinline__ void tile_forward(TileSmem &s, int g, int r, int thre
     // ---- layer 3 ----
     if (r == 0) {
         tc_fence_after();
-        issue_layer(tmem + A_COL, al, tmem, s.w2h, s.w2l, N3, H / 8, bar);
+        issue_layer(tmem + A_COL, al, tmem, s.w2h, s.w2l, N3, H / KSTEP, bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;

@@ -162,7 +162,7 @@ def test_monte_carlo_batch_reproduces_published_workbook():
 
 # ------------------------------------------------------------------------------------------ policy
 def test_policy_forward_matches_torch_fp32():
-    """rdv_policy_forward (tcgen05 / TMEM, 3xTF32) and rdv_policy_forward_ffma (plain fp32 FMAs) against an fp64
+    """rdv_policy_forward (tcgen05 / TMEM, products of fp16 halves) and rdv_policy_forward_ffma (plain fp32 FMAs) against an fp64
     evaluation of the same network, at tile-ragged sizes; tolerance = fp32 accumulation error of a 64-wide MLP."""
     import torch
     pol = _policy()
@@ -182,12 +182,20 @@ def test_policy_forward_matches_torch_fp32():
     act_tc = pol.forward(dev_obs).cpu().numpy()
     act_ff = pol.forward(dev_obs, ffma=True).cpu().numpy()
     assert np.abs(act_ff - ref).max() < 5e-6                    # fp32 accumulation vs an fp64 evaluation
-    assert np.abs(act_tc - ref).max() < 8e-6                    # 3xTF32: fp32-level, not TF32-level (1e-3)
+    assert np.abs(act_tc - ref).max() < 8e-6                    # split operands: fp32-level, not fp16/TF32-level (1e-3)
     rng = np.random.default_rng(0)
     for n in (1, 31, 127, 128, 129, 300, 4096 + 77):            # partial tiles, several tiles per CTA
         x = rng.uniform(-1, 1, (n, 17)).astype(np.float32)
         a = pol.forward(torch.as_tensor(x, device=pol.device)).cpu().numpy()
         assert a.shape == (n, 6) and np.abs(a - reference(x)).max() < 8e-6, n
+    # operand range of the fp16 halves: tiny observations (lo underflows to fp16 subnormals: absolute error 2^-25 per
+    # term), observations far outside the Box, and beyond the fp16 range (clamped; every first-layer tanh is saturated)
+    x = rng.uniform(-1, 1, (1000, 17)).astype(np.float32)
+    for scale, tol in ((1e-6, 8e-6), (1e-3, 8e-6), (30.0, 2e-5), (3000.0, 2e-5)):
+        a = pol.forward(torch.as_tensor(x * np.float32(scale), device=pol.device)).cpu().numpy()
+        assert np.abs(a - reference(x * np.float32(scale))).max() < tol, scale
+    a = pol.forward(torch.as_tensor(x * np.float32(1e7), device=pol.device)).cpu().numpy()
+    assert np.isfinite(a).all() and np.abs(a).max() <= 1.0
     a1, state = pol.predict(obs[0], deterministic=True)
     assert a1.shape == (6,) and a1.dtype == np.float32 and state is None
     np.testing.assert_array_equal(a1, act_tc[0])

@@ -313,7 +313,7 @@ def _policy():
 
 
 def test_fused_policy_rollout_matches_policy_kernel_and_step():
-    """Closed-loop rollout with the actor evaluated inside the launch (3xTF32 tensor-core MLP) vs the same loop
+    """Closed-loop rollout with the actor evaluated inside the launch (split-fp16 tensor-core MLP) vs the same loop
     assembled from rdv_policy_forward (fp32 FFMA) + rdv_step.  Actions agree to fp32 rounding; the closed loops
     are compared while that difference has not been amplified (12 steps) and statistically afterwards."""
     import torch

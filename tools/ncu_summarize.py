@@ -38,7 +38,10 @@ def main():
         return float(m[name][1].replace(",", ""))
 
     grid, block = int(val("launch__grid_size")), int(val("launch__block_size"))
-    warps = grid * (block // 32)
+    # the 512-thread CTA of the 448-env shape is 14 worker warps + 2 helper warps: the per-warp-step figures are per
+    # WORKER warp (one lane = one env), with the helpers' instructions included in the totals
+    helpers = 2 if (block == 512 and envs <= grid * 448) else 0
+    warps = grid * (block // 32 - helpers)
     div = warps * steps
     sass = list(csv.reader(io.StringIO(ncu(rep, "--page", "source", "--csv", "--print-source", "sass"))))
     h2 = sass[1]
