@@ -530,7 +530,10 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     constexpr bool own_stage = !POLICY && OBS;
     __shared__ __align__(16) float s_obs[own_stage ? NW : 1][own_stage ? 32 * RDV_OBS_DIM : 4];
     __shared__ double s_stats[NWT][RDV_NSTATS];
-    __shared__ double s_team[NWT][4][RDV_TEAM_ROW];
+    // scratch rows of the warps' four reset teams; with the fused actor they borrow the group's lo-activation tile
+    // (behind the observation staging rows), like those dead outside the actor: the CTA then fits in 100 KiB of
+    // shared memory and the L1 carve-out is 156 KiB instead of 124
+    __shared__ double s_team_static[POLICY ? 1 : NWT][4][RDV_TEAM_ROW];
     // helper protocol: episode each lane's row in shared memory was computed for (-1: none), episode a row is wanted
     // for, lanes with an open request, and the end-of-launch flag
     __shared__ int s_row_ep[HELP ? NW : 1][32], s_ep_req[HELP ? NW : 1][32];
@@ -565,6 +568,12 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     // simply not needed any more -- when the final observation is written)
     float *obs_stage = POLICY ? reinterpret_cast<float *>(ts->al[warp >> 2]) + (warp & 3) * (32 * RDV_OBS_DIM)
                               : own_stage ? s_obs[own_stage ? warp : 0] : reinterpret_cast<float *>(next_rows);
+    double (*s_team_w)[RDV_TEAM_ROW] =
+        POLICY ? reinterpret_cast<double (*)[RDV_TEAM_ROW]>(reinterpret_cast<char *>(ts->al[warp >> 2]) +
+                                                             4 * 32 * RDV_OBS_DIM * sizeof(float)) + (warp & 3) * 4
+               : s_team_static[POLICY ? 0 : warp];
+    static_assert(4 * 32 * RDV_OBS_DIM * sizeof(float) + 4 * 4 * RDV_TEAM_ROW * sizeof(double) <= sizeof(ts->al[0]),
+                  "staging rows + team rows must fit the group's activation tile");
     constexpr bool want_obs = POLICY || OBS;
     // this CTA's slice [lo, hi) and its passes; with a parameter table the slices are cut at multiples of 32 envs so
     // that a warp never straddles two parameter blocks
@@ -612,7 +621,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                         const int src_lane = src_bit < 32 ? (int)src_bit : 0;
                         const int r_episode = *(volatile int *)&s_ep_req[ww][src_lane];
                         team_reset_core(P, seed, env_offset + lo + ww * 32 + src_lane, r_episode, nullptr,
-                                        src_bit < 32 ? rows + src_lane * RDV_NEXT_ROW : s_team[warp][team]);
+                                        src_bit < 32 ? rows + src_lane * RDV_NEXT_ROW : s_team_w[team]);
                         __threadfence_block();                           // row before tag
                         if (src_bit < 32 && (lane & 7) == 0) *(volatile int *)&s_row_ep[ww][src_lane] = r_episode;
 #pragma unroll
@@ -683,7 +692,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                 const int r_episode = __shfl_sync(full, c.episode, src_lane) + 1;
                 if (POLICY) {
                     // computed in the team's scratch row, then copied to the env's column of the global scratch
-                    double *tr = s_team[warp][team];
+                    double *tr = s_team_w[team];
                     team_reset_core(P, seed, r_env, r_episode, nullptr, tr);
                     if (src_bit < 32) {
                         double *dst = io.reset_rows + (r_env - env_offset);
@@ -693,7 +702,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                     __syncwarp();
                 } else {
                     team_reset_core(P, seed, r_env, r_episode, nullptr,
-                                    src_bit < 32 ? next_rows + src_lane * RDV_NEXT_ROW : s_team[warp][team]);
+                                    src_bit < 32 ? next_rows + src_lane * RDV_NEXT_ROW : s_team_w[team]);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) todo &= todo - 1;                  // drop the four handled lanes
@@ -850,9 +859,9 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                         const int src_lane = src_bit < 32 ? (int)src_bit : lane;
                         const int64_t r_env = __shfl_sync(full, env_id, src_lane);
                         const int r_episode = __shfl_sync(full, c.episode, src_lane) + 1;
-                        team_reset_core(P, seed, r_env, r_episode, nullptr, s_team[warp][team]);
+                        team_reset_core(P, seed, r_env, r_episode, nullptr, s_team_w[team]);
                         const int rank = __popc(need & ((1u << lane) - 1));
-                        if (((need >> lane) & 1u) && rank < 4) take_reset_row(s_team[warp][rank], 1, e, c);
+                        if (((need >> lane) & 1u) && rank < 4) take_reset_row(s_team_w[rank], 1, e, c);
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 4; ++j) need &= need - 1;
@@ -888,10 +897,10 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
                     const int src_lane = src_bit < 32 ? (int)src_bit : lane;
                     const int64_t r_env = __shfl_sync(full, env_id, src_lane);
                     const int r_episode = __shfl_sync(full, c.episode, src_lane) + 1;
-                    team_reset_core(P, seed, r_env, r_episode, nullptr, s_team[warp][team]);
+                    team_reset_core(P, seed, r_env, r_episode, nullptr, s_team_w[team]);
                     const int rank = __popc(m & ((1u << lane) - 1));
                     if (((m >> lane) & 1u) && rank < 4) {
-                        take_reset_row(s_team[warp][rank], 1, e, c);
+                        take_reset_row(s_team_w[rank], 1, e, c);
                         if (want_obs) make_obs(e, obs_scale(P), ov);           // post-reset observation
                     }
                     __syncwarp();
