@@ -507,7 +507,12 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     tc::TileSmem *ts = reinterpret_cast<tc::TileSmem *>(dyn_smem);
     uint32_t tmem_all = 0, mma_phase = 0;
-    if (POLICY) tmem_all = tc::tile_setup<TPB_>(io.policy, *ts);
+    if (POLICY) {
+        // the actor's weights may have been written by the previous kernel of the stream (an optimiser step), so the
+        // dependency wait of a programmatic launch (below) comes before they are read
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        tmem_all = tc::tile_setup<TPB_>(io.policy, *ts);
+    }
     // Without the actor the tensor memory (256 KB per SM) is entirely idle; the variant for the reference's bodies
     // allocates it as a parking area for cold registers (see the step phase): 128 columns for every thread.
     constexpr bool main_stash = !POLICY && !MC && ISO && !CLOSED && (RDV_TMEM_STASH_MAIN != 0);
@@ -586,7 +591,7 @@ rollout_kernel(const __grid_constant__ RdvParams Pc, const RdvState S, const __g
     StepStats st = {};
     // Programmatic dependent launch: when rdv_rollout launches with the stream-serialisation attribute, this grid may
     // become resident while the previous kernel of the stream is still draining (its CTAs finish at different times),
-    // and everything above -- parameter loads, the actor's weight split and TMEM allocation -- runs in that shadow.
+    // and everything above -- parameter loads, the TMEM allocation -- runs in that shadow.
     // Nothing written by an earlier kernel is read before this point; the wait returns once the previous grid has
     // completed and its writes are visible.  Dependents of THIS grid may be scheduled as soon as its CTAs start to exit.
     asm volatile("griddepcontrol.wait;" ::: "memory");
