@@ -24,8 +24,9 @@ static PyObject *k_term, *k_episode, *k_r, *k_l, *k_t, *k_success, *k_collided, 
 
 /* build_infos(infos: list, dirty: list[int], rows: buffer of m 128-byte rows, term: [m,17] array, elapsed: float,
  *             rich: bool, reasons: tuple[str]) -> list[int]
- * Slots named by `dirty` (last step's episode-end dicts) get a fresh empty dict; slot rows[j].env gets the
- * episode-end dict of row j.  Returns the env indices of this step's rows (the next call's `dirty`). */
+ * Slots named by `dirty` (last step's episode-end dicts) become empty dicts; slot rows[j].env gets the
+ * episode-end dict of row j.  A slot's dict is reused when the list holds the only reference to it and replaced by a
+ * new one otherwise, so a dict the caller kept is never changed behind its back.  Returns the env indices of this step's rows (the next call's `dirty`). */
 static PyObject *build_infos(PyObject *self, PyObject *args)
 {
     PyObject *infos, *dirty, *rows_obj, *term, *reasons;
@@ -41,9 +42,16 @@ static PyObject *build_infos(PyObject *self, PyObject *args)
             if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "dirty index out of range");
             return NULL;
         }
-        PyObject *d = PyDict_New();
-        if (!d) return NULL;
-        PyList_SetItem(infos, i, d);                                 /* steals d, releases the old dict */
+        /* a dict nobody else holds is emptied in place (no one can tell it from a fresh one); one the caller kept a
+         * reference to is left alone and replaced */
+        PyObject *old = PyList_GET_ITEM(infos, i);
+        if (PyDict_CheckExact(old) && Py_REFCNT(old) == 1) {
+            PyDict_Clear(old);
+        } else {
+            PyObject *d = PyDict_New();
+            if (!d) return NULL;
+            PyList_SetItem(infos, i, d);                             /* steals d, releases the old dict */
+        }
     }
     Py_buffer view;
     if (PyObject_GetBuffer(rows_obj, &view, PyBUF_SIMPLE) < 0) return NULL;
@@ -65,7 +73,10 @@ static PyObject *build_infos(PyObject *self, PyObject *args)
             goto fail;
         }
         PyObject *obs = PySequence_GetItem(term, j);                 /* row view of the caller's own [m,17] array */
-        PyObject *ep = PyDict_New(), *d = PyDict_New();
+        PyObject *slot = PyList_GET_ITEM(infos, row.env);
+        const int reuse = PyDict_CheckExact(slot) && Py_REFCNT(slot) == 1;   /* the env's own dict, held by nobody else */
+        PyObject *ep = PyDict_New(), *d = reuse ? slot : PyDict_New();
+        if (reuse && PyDict_GET_SIZE(d)) PyDict_Clear(d);
         PyObject *r = PyFloat_FromDouble(rint(row.record[0] * 1e6) / 1e6);     /* Monitor rounds the return to 6 places */
         PyObject *l = PyLong_FromLong((long)row.record[1]);
         int bad = !obs || !ep || !d || !r || !l;
@@ -87,8 +98,8 @@ static PyObject *build_infos(PyObject *self, PyObject *args)
             Py_XDECREF(dv); Py_XDECREF(dw);
         }
         Py_XDECREF(obs); Py_XDECREF(ep); Py_XDECREF(r); Py_XDECREF(l);
-        if (bad) { Py_XDECREF(d); goto fail; }
-        PyList_SetItem(infos, row.env, d);                           /* steals d */
+        if (bad) { if (!reuse) Py_XDECREF(d); goto fail; }
+        if (!reuse) PyList_SetItem(infos, row.env, d);               /* steals d */
         PyObject *idx = PyLong_FromLong(row.env);
         if (!idx) goto fail;
         PyList_SET_ITEM(out, j, idx);

@@ -46,6 +46,7 @@ except Exception:                                      # noqa: BLE001
 _NO_TERM = np.zeros((0, N.OBS_DIM), dtype=np.float32)
 FINISHED_ROW = np.dtype([("env", "<i4"), ("end_reason", "<i4"), ("terminal_obs", "<f4", (N.OBS_DIM,)), ("pad", "<f4"),
                          ("record", "<f8", (N.EP_NCOL,))])
+_NO_ROWS = np.zeros(0, dtype=FINISHED_ROW)
 assert FINISHED_ROW.itemsize == 128
 
 
@@ -147,7 +148,15 @@ class RendezvousVecEnv(_Base):
         self.d2h_bytes_total = 0
         self.extra_fetches = 0                             # steps that needed a second copy for their finished rows
         if gc_freeze:
-            gc.freeze()      # the long-lived objects above (65,536 dicts ...) never need another walk by the cyclic GC
+            # The long-lived objects above never need another walk by the cyclic GC.  An empty dict is not tracked by
+            # the collector yet -- it would start being tracked, as a YOUNG object, when its env's first episode-end
+            # dict goes in -- so each per-env dict is made to hold a container once; then all 65,536 of them are frozen
+            # into the permanent generation, and the generation-1 / -2 passes of a long run (6 ms each otherwise: they
+            # walk every per-env dict) have nothing left to walk.
+            for d in self._infos:
+                d[0] = d
+                del d[0]
+            gc.freeze()
 
     # ------------------------------------------------------------------ VecEnv API
     def _views(self, base: np.ndarray, shared: bool):
@@ -181,9 +190,11 @@ class RendezvousVecEnv(_Base):
             self._d_act32.copy_(self._h_act32, non_blocking=True)
             self._pending = self._d_act32
 
-    def _launch_and_fetch(self):
+    def _launch_and_fetch(self, renew_infos: bool = False):
         """One launch, one device-to-host copy, one synchronise.  Returns (obs, rew, done, rows) with ``rows`` the
-        finished envs' records (structured view of the pinned block, in the order the kernel appended them)."""
+        finished envs' records (structured view of the pinned block, in the order the kernel appended them).
+        ``renew_infos``: the dicts of the envs that finished LAST step are replaced by fresh ones while the GPU works
+        (host work that does not depend on this step's results, done in the shadow of the kernel and the copy)."""
         if self._pending is None:
             raise RuntimeError("step_wait() called without step_async()")
         env, L = self.env, self.layout
@@ -194,6 +205,8 @@ class RendezvousVecEnv(_Base):
         nbytes = L["rows"] + self._d2h_row * guess
         stream = torch.cuda.current_stream(env.device)
         t[:nbytes].copy_(env.host_block[:nbytes], non_blocking=True)
+        if renew_infos and self._dirty:
+            self._dirty = self._host.build_infos(self._infos, self._dirty, _NO_ROWS, _NO_TERM, 0.0, False, N.END_REASONS)
         stream.synchronize()
         m = int(base[0:4].view(np.int32)[0])
         fetched = guess
@@ -230,7 +243,6 @@ class RendezvousVecEnv(_Base):
         return obs, rew, done, finished
 
     def step_wait(self):
-        obs, rew, done, rows = self._launch_and_fetch()
         # The cyclic garbage collector is paused while the per-env objects are created: a step at 65,536 envs
         # allocates ~6,500 small dicts, none of them cyclic, and the generation-0 passes they trigger cost more
         # than building them.
@@ -238,6 +250,7 @@ class RendezvousVecEnv(_Base):
         if paused:
             gc.disable()
         try:
+            obs, rew, done, rows = self._launch_and_fetch(renew_infos=True)
             infos = self._build_infos(rows)
         finally:
             if paused:

@@ -233,6 +233,17 @@ def test_info_dict_builder_cpu():
     # next step: nothing finished -> last step's slots get fresh empty dicts
     dirty2 = h.build_infos(infos, dirty, rows[:0], term[:0], 13.0, False, N.END_REASONS)
     assert dirty2 == [] and all(infos[i] == {} for i in dirty) and len({id(d) for d in infos}) == n
+    # dicts the caller kept a reference to are never changed behind its back: they are replaced in the list ...
+    assert all(keep[i] == {} for i in range(n)) and all(infos[i] is not keep[i] for i in dirty)
+    # ... while a dict only the list holds is reused in place (finished -> filled, next step -> emptied)
+    del keep
+    ids = [id(d) for d in infos]
+    dirty3 = h.build_infos(infos, [], rows, term, 14.0, False, N.END_REASONS)
+    assert [id(d) for d in infos] == ids and set(infos[int(rows["env"][0])]) == {"terminal_observation", "episode"}
+    held = infos[int(rows["env"][0])]                                  # the caller keeps one episode-end dict
+    h.build_infos(infos, dirty3, rows[:0], term[:0], 15.0, False, N.END_REASONS)
+    assert held["episode"]["t"] == 14.0 and infos[int(rows["env"][0])] == {} and infos[int(rows["env"][0])] is not held
+    assert all(infos[i] == {} for i in dirty3) and len({id(d) for d in infos}) == n
     bad = rows[:1].copy()
     bad["env"] = n + 5
     with pytest.raises(IndexError):
