@@ -16,6 +16,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <atomic>
+#include <mutex>
 #include "rdv_step.cuh"
 #include "rdv_policy.cuh"
 #include "rdv_policy_tc.cuh"
@@ -1257,6 +1258,39 @@ static bool ensure_smem(K kernel, std::atomic<uint64_t> &mask, int dev, size_t b
     return true;
 }
 
+// The angle table of rounded_angle_from (rdv_math.cuh), filled once per device before the first kernel that reads it.
+// The fill runs on the caller's stream and is waited for (once per device and process), so that launches on other
+// streams find it complete; a stream that is being captured into a graph cannot be waited for -- the first call on a
+// device has to come from outside a capture (any reset / step / rollout does).
+#if RDV_ACOS_TABLE
+__global__ void acos_table_kernel()
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= 2 * ACOS_TABLE_HALF) g_acos_table[i] = acos_of_rounded((double)(i - ACOS_TABLE_HALF));
+}
+#endif
+static bool ensure_tables(cudaStream_t st)
+{
+#if RDV_ACOS_TABLE
+    static std::atomic<uint64_t> mask{0};
+    static std::mutex mtx;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= RDV_MAX_DEVICES) return false;
+    const uint64_t bit = 1ull << dev;
+    if (mask.load(std::memory_order_acquire) & bit) return true;
+    std::lock_guard<std::mutex> lock(mtx);
+    if (mask.load(std::memory_order_acquire) & bit) return true;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return false;
+    acos_table_kernel<<<(2 * ACOS_TABLE_HALF + 256) / 256, 256, 0, st>>>();
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return false;
+    mask.fetch_or(bit, std::memory_order_release);
+#else
+    (void)st;
+#endif
+    return true;
+}
+
 // development / test knobs: the environment variables are read once, rdv_tune changes them at run time
 static int env_int(const char *name, int fallback)
 {
@@ -1443,6 +1477,7 @@ int rdv_step(const RdvParams *p, const RdvState *s, const RdvStepIO *io, int64_t
         if (!io->fin_append && cudaMemsetAsync(io->fin_count, 0, sizeof(int32_t), st) != cudaSuccess) return RDV_ERR_CUDA;
     }
     if ((uintptr_t)io->reward_f32 & 3) return RDV_ERR_ALIGN;
+    if (!ensure_tables(st)) return RDV_ERR_CUDA;
 #define RDV_LAUNCH(ISO_, F64_, CL_) \
     step_kernel<ISO_, F64_, CL_><<<grid, TPB, 0, st>>>(*p, *s, *io, n, seed, env_offset)
     if (s->param_table) {
@@ -1482,7 +1517,7 @@ int rdv_rollout(const RdvParams *p, const RdvState *s, const RdvRolloutIO *io, i
     // one CTA per SM; the CTA size is the smallest instantiated one that covers a slice in the fewest passes
     int sm_count = 0;
     const int dev = current_device(&sm_count);
-    if (dev < 0) return RDV_ERR_CUDA;
+    if (dev < 0 || !ensure_tables(st)) return RDV_ERR_CUDA;
     if (io->sm_reserve < 0 || io->sm_reserve >= sm_count) return RDV_ERR_SIZE;
     const int64_t sms = sm_count - io->sm_reserve;
     const int64_t grid = n < sms ? n : sms;
@@ -1605,6 +1640,7 @@ int rdv_errors(const RdvParams *p, const RdvState *s, double *errors, uint8_t *c
     int rc = check_state(s, n);
     if (rc) return rc;
     if (n == 0) return RDV_OK;
+    if (!ensure_tables((cudaStream_t)cuda_stream)) return RDV_ERR_CUDA;
     if (s->param_table)
         errors_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, errors, collision,
                                                                                                  success, koz, n, 0);
@@ -1620,6 +1656,7 @@ int rdv_refresh_flags(const RdvParams *p, const RdvState *s, int64_t n, void *cu
     int rc = check_state(s, n);
     if (rc) return rc;
     if (n == 0) return RDV_OK;
+    if (!ensure_tables((cudaStream_t)cuda_stream)) return RDV_ERR_CUDA;
     if (s->param_table)
         errors_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(*p, *s, nullptr, nullptr,
                                                                                                  nullptr, nullptr, n, 1);
@@ -1676,6 +1713,7 @@ int rdv_math_probe(const double *x, double *y, int64_t n, int op, void *cuda_str
     if (!x || !y) return RDV_ERR_NULL;
     if (n < 0 || op < 0 || op > 5) return RDV_ERR_SIZE;
     if (n == 0) return RDV_OK;
+    if (!ensure_tables((cudaStream_t)cuda_stream)) return RDV_ERR_CUDA;
     math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x, y, n, op);
     return launch_status();
 }

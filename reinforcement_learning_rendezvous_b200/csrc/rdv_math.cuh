@@ -106,12 +106,29 @@ RDV_DEV double fast_sqrt(double x) { return x > 0.0 ? x * fast_rsqrt(x) : 0.0; }
 // angle_between_vectors (utils/general.py:163-181): acos(round(cos, 5)), with numpy's
 // round == rint(x*1e5)/1e5.  k/1e5 is formed as k*1e-5 plus one Markstein correction step, which equals the
 // IEEE quotient for every integer |k| <= 1e5 (checked exhaustively) -- in particular +-1 stay exactly +-1.
+RDV_DEV double acos_of_rounded(double k)
+{
+    const double x0 = k * 1e-5;
+    return acos(fma(fma(-x0, 1e5, k), 1e-5, x0));
+}
+// The rounded cosine takes only 200,001 values, so the angle is a table look-up (1.6 MB, resident in the L2): one
+// load instead of the ~85 instructions of acos().  The table is filled by acos_table_kernel with acos_of_rounded
+// itself, once per device, before the first kernel that reads it (ensure_tables in rdv_b200.cu).
+#ifndef RDV_ACOS_TABLE
+#define RDV_ACOS_TABLE 1
+#endif
+constexpr int ACOS_TABLE_HALF = 100000;
+#if RDV_ACOS_TABLE
+__device__ double g_acos_table[2 * ACOS_TABLE_HALF + 1];
+#endif
 RDV_DEV double rounded_angle_from(double dot, double n1sq, double n2sq)
 {
     const double c = dot * fast_rsqrt(n1sq * n2sq);
     const double k = rint(c * 1e5);
-    const double x0 = k * 1e-5;
-    return acos(fma(fma(-x0, 1e5, k), 1e-5, x0));
+#if RDV_ACOS_TABLE
+    if (fabs(k) <= (double)ACOS_TABLE_HALF) return g_acos_table[(int)k + ACOS_TABLE_HALF];
+#endif
+    return acos_of_rounded(k);                       // NaN (a zero vector) or out of range: the library's answer
 }
 
 // ---------------------------------------------------------------------------------

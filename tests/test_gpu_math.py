@@ -50,3 +50,10 @@ def test_rounded_acos_matches_numpy_rounding():
     assert np.isfinite(got).all()
     assert np.abs(got - want).max() < 4e-15 * np.pi + 1e-7 * 0      # same rounded argument -> same angle
     assert got[300000] == 0.0 and abs(got[300001] - np.pi) < 1e-15
+    # the angle is a 200,001-entry table look-up (filled by the same acos on the device): every entry, and the
+    # arguments that have no entry (a cosine beyond +-1 by more than the rounding, NaN) take the library path
+    k = np.arange(-100000, 100001, dtype=np.float64)
+    got = _probe(k / 1e5, 5)
+    assert np.abs(got - np.arccos(np.round(k / 1e5, 5))).max() < 4e-15 * np.pi
+    odd = _probe(np.array([1.5, -1.00002, np.nan, 1.0 + 1e-9, -1.0 - 1e-9]), 5)
+    assert np.isnan(odd[:3]).all() and odd[3] == 0.0 and abs(odd[4] - np.pi) < 1e-15
