@@ -8,7 +8,8 @@ GPU box, gloo in the CPU tests.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import os
+from typing import Optional, Set, Tuple
 
 import torch
 import torch.distributed as dist
@@ -37,6 +38,46 @@ def make_sharded_env(total_envs: int, rank: Optional[int] = None, world_size: Op
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     return BatchedRendezvousEnv(hi - lo, device=device, seed=seed, env_offset=lo, **kwargs)
+
+
+def gpu_cpu_affinity(device_index: int) -> Set[int]:
+    """The host cores NVML reports as local to a GPU (same socket / PCIe root), intersected with the cores this
+    process may run on.  Empty when NVML cannot say (no driver, no permission)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(device_index)
+        if visible:
+            ids = [x.strip() for x in visible.split(",") if x.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                index = int(ids[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+    except Exception:
+        return set()
+    return cores & set(os.sched_getaffinity(0))
+
+
+def bind_to_gpu_cpus(device_index: int, local_rank: int = 0, local_world: int = 1) -> Optional[Set[int]]:
+    """One process per GPU: keep this process (the Python thread that stages actions and builds the per-episode
+    objects of a VecEnv step, and the pinned buffers it first touches) on host cores local to its GPU.  The GPU's
+    local cores are dealt out among the ranks whose GPUs share them, so that ranks do not sit on each other's cores or
+    on the sibling hyper-threads of a busy neighbour more than the box forces them to.  Returns the cores it bound to,
+    or None when NVML gave no answer (nothing is changed then)."""
+    mine = gpu_cpu_affinity(device_index)
+    if not mine:
+        return None
+    # ranks with the same local core set share it: rank r takes every k-th core starting at its position among them
+    sharers = [r for r in range(int(local_world)) if gpu_cpu_affinity(r) == mine] or [int(local_rank)]
+    pos = sharers.index(int(local_rank)) if int(local_rank) in sharers else 0
+    ordered = sorted(mine)
+    per = max(1, len(ordered) // len(sharers))
+    cores = set(ordered[pos * per:(pos + 1) * per]) or mine
+    os.sched_setaffinity(0, cores)
+    return cores
 
 
 def all_reduce_stats(stats: torch.Tensor, group=None, async_op: bool = False):
