@@ -27,6 +27,7 @@ import argparse
 import json
 import math
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -162,30 +163,42 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------------------------
+def cpu_baseline_leg(args):
+    """The oracle timed on the host cores (SubprocVecEnv protocol, single process, plain-C port): bench.py's
+    `cpu_baseline` object.  Runs in a child interpreter of the CUDA arm (`--cpu-baseline-only`)."""
+    from oracle.subproc_vec_env import time_c_port, time_single_process, time_subproc_baseline
+    cores = os.cpu_count() or 1
+    res = time_subproc_baseline(steps=100000, warmup=2, n_procs=cores, seed=0, max_seconds=args.cpu_seconds)
+    single = time_single_process(seconds=min(3.0, args.cpu_seconds))
+    cport = time_c_port(n_envs=4096, steps=10, threads=cores)
+    return {
+        "value": res["value"], "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{res['steps']} VecEnv steps x {cores} envs (one per process, SubprocVecEnv protocol), "
+                  f"random fp64 actions, numpy restatement of the reference env (bit-exact), "
+                  f"{res['seconds']:.1f} s",
+        "single_process_value": single["value"],
+        "single_process_sample": f"one env in-process (DummyVecEnv style, main.py:33-34), {single['steps']} steps",
+        "c_port_value": cport["value"],
+        "c_port_sample": f"plain-C oracle, {cport['envs']} envs x {cport['steps']} steps on {cores} threads",
+    }
+
+
 def run_cuda(args):
     import numpy as np
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    # CPU baseline first (rank 0, N = 1 only), before CUDA is initialised in this process
+    # CPU baseline first (rank 0, N = 1 only), in a child interpreter: the 16 worker processes, the numpy oracle's
+    # object churn and the C oracle's threads leave this process untouched.  (Run in-process, the leg left the heap
+    # fragmented enough to slow the end-to-end leg's per-episode dict building by 18 %: 1.14 against 0.96 ms per step.)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.subproc_vec_env import time_c_port, time_single_process, time_subproc_baseline
-        cores = os.cpu_count() or 1
-        res = time_subproc_baseline(steps=100000, warmup=2, n_procs=cores, seed=0, max_seconds=args.cpu_seconds)
-        single = time_single_process(seconds=min(3.0, args.cpu_seconds))
-        cport = time_c_port(n_envs=4096, steps=10, threads=cores)
-        cpu_baseline = {
-            "value": res["value"], "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{res['steps']} VecEnv steps x {cores} envs (one per process, SubprocVecEnv protocol), "
-                      f"random fp64 actions, numpy restatement of the reference env (bit-exact), "
-                      f"{res['seconds']:.1f} s",
-            "single_process_value": single["value"],
-            "single_process_sample": f"one env in-process (DummyVecEnv style, main.py:33-34), {single['steps']} steps",
-            "c_port_value": cport["value"],
-            "c_port_sample": f"plain-C oracle, {cport['envs']} envs x {cport['steps']} steps on {cores} threads",
-        }
+        child = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only",
+                                "--cpu-seconds", str(args.cpu_seconds)], capture_output=True, text=True)
+        if child.returncode != 0:
+            raise SystemExit("cpu baseline leg failed:\n" + child.stderr[-2000:])
+        cpu_baseline = json.loads(child.stdout.strip().splitlines()[-1])
 
     import torch
     import torch.distributed as dist
@@ -544,6 +557,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=250, help="env steps fused into one rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-only", action="store_true", help="(internal) print the cpu_baseline object and exit")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-envs", type=int, default=0, help="(ignored; kept for compatibility)")
     ap.add_argument("--ref-max-seconds", type=float, default=150.0)
@@ -553,6 +567,9 @@ def main():
     out = _json_only_stdout()
     sys.stdout = out
     try:
+        if args.cpu_baseline_only:
+            print(json.dumps(cpu_baseline_leg(args)))
+            return 0
         if args.impl == "reference":
             return run_reference(args)
         return run_cuda(args)

@@ -175,8 +175,9 @@ def build_host(force=False):
     global _host
     if force or not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < os.path.getmtime(HOST_SRC):
         cc = shutil.which("gcc") or shutil.which("cc") or "gcc"
-        subprocess.run([cc, "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"], "-o", HOST_LIB,
-                        HOST_SRC], check=True)
+        import numpy                                            # row views are made through the numpy C API
+        subprocess.run([cc, "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"],
+                        "-I", numpy.get_include(), "-o", HOST_LIB, HOST_SRC], check=True)
         _host = None
     return HOST_LIB
 

@@ -4,14 +4,19 @@
  * env and step, and for every env whose episode ended {"terminal_observation": ndarray, "episode": {"r", "l", "t"}}.
  * At 65,536 envs and ~3,300 episode ends per step the interpreter spends more time creating those objects than the
  * GPU spends stepping the envs; this module builds them from the finished rows (RdvFinishedRow, include/rdv_b200.h)
- * with direct C-API calls.  Built by _native.build() with gcc against Python.h; no numpy C API is needed (row views
- * come from the sequence protocol of the [m,17] array the caller passes).
+ * with direct C-API calls.  Built by _native.build() with gcc against Python.h and numpy's headers (the row views of
+ * the [m,17] terminal-observation array are made with PyArray_NewFromDescr).
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#define NPY_NO_DEPRECATED_API NPY_1_7_API_VERSION
+#include <numpy/arrayobject.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+
+#define PF_FAR 16          /* iterations ahead: the slot's dict object ... */
+#define PF_NEAR 8          /* ... and its key table */
 
 typedef struct {
     int32_t env, end_reason;
@@ -22,24 +27,52 @@ typedef struct {
 
 static PyObject *k_term, *k_episode, *k_r, *k_l, *k_t, *k_success, *k_collided, *k_dv, *k_dw, *k_reason;
 
-/* build_infos(infos: list, dirty: list[int], rows: buffer of m 128-byte rows, term: [m,17] array, elapsed: float,
- *             rich: bool, reasons: tuple[str]) -> list[int]
+/* build_infos(infos: list, dirty: buffer of int32, rows: buffer of m 128-byte rows, term: [m,17] array, elapsed: float,
+ *             rich: bool, reasons: tuple[str]) -> bytes (int32[m])
  * Slots named by `dirty` (last step's episode-end dicts) become empty dicts; slot rows[j].env gets the
  * episode-end dict of row j.  A slot's dict is reused when the list holds the only reference to it and replaced by a
- * new one otherwise, so a dict the caller kept is never changed behind its back.  Returns the env indices of this step's rows (the next call's `dirty`). */
+ * new one otherwise, so a dict the caller kept is never changed behind its back.  Returns the env indices of this
+ * step's rows as packed int32 (the next call's `dirty`; one object instead of a list of m Python ints). */
 static PyObject *build_infos(PyObject *self, PyObject *args)
 {
-    PyObject *infos, *dirty, *rows_obj, *term, *reasons;
+    PyObject *infos, *dirty_obj, *rows_obj, *term, *reasons;
     double elapsed;
     int rich;
-    if (!PyArg_ParseTuple(args, "O!O!OOdpO!", &PyList_Type, &infos, &PyList_Type, &dirty, &rows_obj, &term, &elapsed,
+    if (!PyArg_ParseTuple(args, "O!OOOdpO!", &PyList_Type, &infos, &dirty_obj, &rows_obj, &term, &elapsed,
                           &rich, &PyTuple_Type, &reasons))
         return NULL;
+    Py_buffer dview;
+    if (PyObject_GetBuffer(dirty_obj, &dview, PyBUF_SIMPLE) < 0) return NULL;
+    if (dview.len % (Py_ssize_t)sizeof(int32_t)) {
+        PyBuffer_Release(&dview);
+        PyErr_SetString(PyExc_ValueError, "dirty must hold packed int32 env indices");
+        return NULL;
+    }
+    const int32_t *dirty = (const int32_t *)dview.buf;
+    const Py_ssize_t nd = dview.len / (Py_ssize_t)sizeof(int32_t);
     const Py_ssize_t n = PyList_GET_SIZE(infos);
-    for (Py_ssize_t k = 0; k < PyList_GET_SIZE(dirty); ++k) {
-        const Py_ssize_t i = PyLong_AsSsize_t(PyList_GET_ITEM(dirty, k));
+    /* The 65,536 per-env dicts are spread over ~20 MB of heap and the finished envs are a random subset of them: left
+     * alone, every slot costs two or three cache misses (the dict, its key table).  The slots a few iterations ahead
+     * are prefetched -- first the dict object, then, once that has arrived, its key table. */
+    for (Py_ssize_t k = 0; k < nd; ++k) {
+        if (k + PF_FAR < nd) {
+            const Py_ssize_t f = dirty[k + PF_FAR];
+            if (f >= 0 && f < n) __builtin_prefetch(PyList_GET_ITEM(infos, f));
+        }
+        if (k + PF_NEAR < nd) {
+            const Py_ssize_t f = dirty[k + PF_NEAR];
+            if (f >= 0 && f < n) {
+                PyObject *o = PyList_GET_ITEM(infos, f);
+                if (PyDict_CheckExact(o)) {
+                    const char *kp = (const char *)((PyDictObject *)o)->ma_keys;
+                    __builtin_prefetch(kp); __builtin_prefetch(kp + 64); __builtin_prefetch(kp + 128);
+                }
+            }
+        }
+        const Py_ssize_t i = dirty[k];
         if (i < 0 || i >= n) {
-            if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "dirty index out of range");
+            PyBuffer_Release(&dview);
+            PyErr_SetString(PyExc_IndexError, "dirty index out of range");
             return NULL;
         }
         /* a dict nobody else holds is emptied in place (no one can tell it from a fresh one); one the caller kept a
@@ -49,10 +82,11 @@ static PyObject *build_infos(PyObject *self, PyObject *args)
             PyDict_Clear(old);
         } else {
             PyObject *d = PyDict_New();
-            if (!d) return NULL;
+            if (!d) { PyBuffer_Release(&dview); return NULL; }
             PyList_SetItem(infos, i, d);                             /* steals d, releases the old dict */
         }
     }
+    PyBuffer_Release(&dview);
     Py_buffer view;
     if (PyObject_GetBuffer(rows_obj, &view, PyBUF_SIMPLE) < 0) return NULL;
     if (view.len % (Py_ssize_t)sizeof(FinishedRow)) {
@@ -62,26 +96,54 @@ static PyObject *build_infos(PyObject *self, PyObject *args)
     }
     const Py_ssize_t m = view.len / (Py_ssize_t)sizeof(FinishedRow);
     const FinishedRow *rows = (const FinishedRow *)view.buf;
-    PyObject *out = PyList_New(m);
+    if (!PyArray_Check(term) || PyArray_TYPE((PyArrayObject *)term) != NPY_FLOAT32 || PyArray_NDIM((PyArrayObject *)term) != 2 ||
+        PyArray_DIM((PyArrayObject *)term, 1) != 17 || PyArray_DIM((PyArrayObject *)term, 0) < m ||
+        !PyArray_IS_C_CONTIGUOUS((PyArrayObject *)term)) {
+        PyBuffer_Release(&view);
+        PyErr_SetString(PyExc_TypeError, "term must be a C-contiguous float32 [m,17] array");
+        return NULL;
+    }
+    char *term_data = PyArray_BYTES((PyArrayObject *)term);
+    PyArray_Descr *f32_descr = PyArray_DESCR((PyArrayObject *)term);
+    PyObject *out = PyBytes_FromStringAndSize(NULL, m * (Py_ssize_t)sizeof(int32_t));
     PyObject *t_obj = PyFloat_FromDouble(elapsed);
-    if (!out || !t_obj) goto fail;
+    /* this step's episode dicts are clones of one template {"r", "l", "t": elapsed}: a clone copies the key table in
+     * one piece, and writing "r" / "l" replaces values in place (no insertion, no resize) */
+    PyObject *ep_tmpl = PyDict_New();
+    if (!out || !t_obj || !ep_tmpl) goto fail;
+    int32_t *out_idx = (int32_t *)PyBytes_AS_STRING(out);
+    if (PyDict_SetItem(ep_tmpl, k_r, Py_None) < 0 || PyDict_SetItem(ep_tmpl, k_l, Py_None) < 0 ||
+        PyDict_SetItem(ep_tmpl, k_t, t_obj) < 0)
+        goto fail;
     for (Py_ssize_t j = 0; j < m; ++j) {
+        if (j + PF_FAR < m) {
+            const int32_t f = rows[j + PF_FAR].env;
+            if (f >= 0 && f < n) __builtin_prefetch(PyList_GET_ITEM(infos, f));
+        }
         FinishedRow row;
         memcpy(&row, rows + j, sizeof(row));
         if (row.env < 0 || row.env >= n) {
             PyErr_SetString(PyExc_IndexError, "finished row names an env outside the batch");
             goto fail;
         }
-        PyObject *obs = PySequence_GetItem(term, j);                 /* row view of the caller's own [m,17] array */
+        /* row view of the caller's own [m,17] array (what term[j] returns, without the generic indexing path) */
+        npy_intp dim = 17;
+        Py_INCREF(f32_descr);
+        PyObject *obs = PyArray_NewFromDescr(&PyArray_Type, f32_descr, 1, &dim, NULL,
+                                             term_data + (size_t)j * 17 * sizeof(float), NPY_ARRAY_CARRAY, NULL);
+        if (obs) {
+            Py_INCREF(term);
+            if (PyArray_SetBaseObject((PyArrayObject *)obs, term) < 0) { Py_DECREF(obs); obs = NULL; }   /* steals term */
+        }
         PyObject *slot = PyList_GET_ITEM(infos, row.env);
         const int reuse = PyDict_CheckExact(slot) && Py_REFCNT(slot) == 1;   /* the env's own dict, held by nobody else */
-        PyObject *ep = PyDict_New(), *d = reuse ? slot : PyDict_New();
+        PyObject *ep = PyDict_Copy(ep_tmpl), *d = reuse ? slot : PyDict_New();
         if (reuse && PyDict_GET_SIZE(d)) PyDict_Clear(d);
         PyObject *r = PyFloat_FromDouble(rint(row.record[0] * 1e6) / 1e6);     /* Monitor rounds the return to 6 places */
         PyObject *l = PyLong_FromLong((long)row.record[1]);
         int bad = !obs || !ep || !d || !r || !l;
         if (!bad) {
-            bad |= PyDict_SetItem(ep, k_r, r) < 0 || PyDict_SetItem(ep, k_l, l) < 0 || PyDict_SetItem(ep, k_t, t_obj) < 0;
+            bad |= PyDict_SetItem(ep, k_r, r) < 0 || PyDict_SetItem(ep, k_l, l) < 0;
             bad |= PyDict_SetItem(d, k_term, obs) < 0 || PyDict_SetItem(d, k_episode, ep) < 0;
         }
         if (!bad && rich) {
@@ -100,15 +162,15 @@ static PyObject *build_infos(PyObject *self, PyObject *args)
         Py_XDECREF(obs); Py_XDECREF(ep); Py_XDECREF(r); Py_XDECREF(l);
         if (bad) { if (!reuse) Py_XDECREF(d); goto fail; }
         if (!reuse) PyList_SetItem(infos, row.env, d);               /* steals d */
-        PyObject *idx = PyLong_FromLong(row.env);
-        if (!idx) goto fail;
-        PyList_SET_ITEM(out, j, idx);
+        out_idx[j] = row.env;
     }
     Py_DECREF(t_obj);
+    Py_DECREF(ep_tmpl);
     PyBuffer_Release(&view);
     return out;
 fail:
     Py_XDECREF(t_obj);
+    Py_XDECREF(ep_tmpl);
     Py_XDECREF(out);
     PyBuffer_Release(&view);
     return NULL;
@@ -122,6 +184,7 @@ static struct PyModuleDef module = {PyModuleDef_HEAD_INIT, "_rdv_host", "host-si
 
 PyMODINIT_FUNC PyInit__rdv_host(void)
 {
+    import_array();
     k_term = PyUnicode_InternFromString("terminal_observation");
     k_episode = PyUnicode_InternFromString("episode");
     k_r = PyUnicode_InternFromString("r");

@@ -137,7 +137,7 @@ class RendezvousVecEnv(_Base):
         self._t_start = time.time()
         # one independent dict per env (DummyVecEnv semantics); finished envs get a fresh one per episode end
         self._infos: List[dict] = [{} for _ in range(n)]
-        self._dirty: List[int] = []                     # envs whose slot holds last step's episode-end dict
+        self._dirty = b""                               # packed int32: envs whose slot holds last step's episode-end dict
         self._rows_guess = max(64, n // 8)              # finished rows fetched with the fixed part of the block
         self.h2d_bytes_per_step = n * N.ACT_DIM * 4
         # device -> host per step: count, obs, reward, done of every env, plus the rows of the finished ones

@@ -219,8 +219,9 @@ def test_info_dict_builder_cpu():
     infos = [{} for _ in range(n)]
     keep = list(infos)
     term = np.ascontiguousarray(rows["terminal_obs"])
-    dirty = h.build_infos(infos, [], rows, term, 12.5, True, N.END_REASONS)
-    assert sorted(dirty) == sorted(rows["env"].tolist())
+    dirty_b = h.build_infos(infos, b"", rows, term, 12.5, True, N.END_REASONS)
+    dirty = np.frombuffer(dirty_b, dtype=np.int32).tolist()            # packed int32, in the order of the rows
+    assert isinstance(dirty_b, bytes) and dirty == rows["env"].tolist()
     for j in range(m):
         d = infos[int(rows["env"][j])]
         np.testing.assert_array_equal(d["terminal_observation"], rows["terminal_obs"][j])
@@ -231,22 +232,48 @@ def test_info_dict_builder_cpu():
     untouched = set(range(n)) - set(rows["env"].tolist())
     assert all(infos[i] is keep[i] for i in untouched)                 # running envs keep their own dict
     # next step: nothing finished -> last step's slots get fresh empty dicts
-    dirty2 = h.build_infos(infos, dirty, rows[:0], term[:0], 13.0, False, N.END_REASONS)
-    assert dirty2 == [] and all(infos[i] == {} for i in dirty) and len({id(d) for d in infos}) == n
+    dirty2 = h.build_infos(infos, dirty_b, rows[:0], term[:0], 13.0, False, N.END_REASONS)
+    assert dirty2 == b"" and all(infos[i] == {} for i in dirty) and len({id(d) for d in infos}) == n
     # dicts the caller kept a reference to are never changed behind its back: they are replaced in the list ...
     assert all(keep[i] == {} for i in range(n)) and all(infos[i] is not keep[i] for i in dirty)
     # ... while a dict only the list holds is reused in place (finished -> filled, next step -> emptied)
     del keep
     ids = [id(d) for d in infos]
-    dirty3 = h.build_infos(infos, [], rows, term, 14.0, False, N.END_REASONS)
+    dirty3_b = h.build_infos(infos, b"", rows, term, 14.0, False, N.END_REASONS)
+    dirty3 = np.frombuffer(dirty3_b, dtype=np.int32).tolist()
     assert [id(d) for d in infos] == ids and set(infos[int(rows["env"][0])]) == {"terminal_observation", "episode"}
     held = infos[int(rows["env"][0])]                                  # the caller keeps one episode-end dict
-    h.build_infos(infos, dirty3, rows[:0], term[:0], 15.0, False, N.END_REASONS)
+    h.build_infos(infos, np.asarray(dirty3, dtype=np.int32), rows[:0], term[:0], 15.0, False, N.END_REASONS)   # any int32 buffer
     assert held["episode"]["t"] == 14.0 and infos[int(rows["env"][0])] == {} and infos[int(rows["env"][0])] is not held
     assert all(infos[i] == {} for i in dirty3) and len({id(d) for d in infos}) == n
     bad = rows[:1].copy()
     bad["env"] = n + 5
     with pytest.raises(IndexError):
-        h.build_infos(infos, [], bad, term[:1], 0.0, False, N.END_REASONS)
+        h.build_infos(infos, b"", bad, term[:1], 0.0, False, N.END_REASONS)
     with pytest.raises(ValueError):
-        h.build_infos(infos, [], np.zeros(100, dtype=np.uint8), term[:0], 0.0, False, N.END_REASONS)
+        h.build_infos(infos, b"", np.zeros(100, dtype=np.uint8), term[:0], 0.0, False, N.END_REASONS)
+    # the terminal observations are row views of the caller's array, made through the numpy C API: float32 [17] with
+    # the array as base, and nothing else is accepted (wrong dtype, wrong width, too few rows, a non-contiguous view)
+    import sys
+    term2 = term.copy()
+    base_refs = sys.getrefcount(term2)
+    dirty4 = h.build_infos(infos, b"", rows, term2, 16.0, False, N.END_REASONS)
+    v = infos[int(rows["env"][3])]["terminal_observation"]
+    assert v.dtype == np.float32 and v.shape == (17,) and v.base is term2 and v.flags.c_contiguous and v.flags.writeable
+    assert sys.getrefcount(term2) == base_refs + m                     # one reference per view ...
+    del v
+    h.build_infos(infos, dirty4, rows[:0], term2[:0], 17.0, False, N.END_REASONS)
+    assert sys.getrefcount(term2) == base_refs                         # ... and all of them released with the dicts
+    for wrong in (term.astype(np.float64), np.zeros((m, 16), np.float32), term[:m - 1], np.zeros((m, 34), np.float32)[:, ::2],
+                  [[0.0] * 17] * m):
+        with pytest.raises(TypeError):
+            h.build_infos(infos, b"", rows, wrong, 0.0, False, N.END_REASONS)
+    # `dirty` is a buffer of int32 indices (the prefetches look ahead in it): anything else fails cleanly
+    with pytest.raises(TypeError):
+        h.build_infos(infos, [0, 1, 2], rows[:0], term[:0], 0.0, False, N.END_REASONS)
+    with pytest.raises(ValueError):
+        h.build_infos(infos, b"\x00" * 7, rows[:0], term[:0], 0.0, False, N.END_REASONS)
+    with pytest.raises(IndexError):
+        h.build_infos(infos, np.array([2] * 30 + [n + 7], dtype=np.int32), rows[:0], term[:0], 0.0, False, N.END_REASONS)
+    with pytest.raises(IndexError):
+        h.build_infos(infos, np.array([5, -1], dtype=np.int32), rows[:0], term[:0], 0.0, False, N.END_REASONS)
