@@ -190,8 +190,9 @@ def run_cuda(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     # CPU baseline first (rank 0, N = 1 only), in a child interpreter: the 16 worker processes, the numpy oracle's
-    # object churn and the C oracle's threads leave this process untouched.  (Run in-process, the leg left the heap
-    # fragmented enough to slow the end-to-end leg's per-episode dict building by 18 %: 1.14 against 0.96 ms per step.)
+    # object churn and the C oracle's threads leave this process untouched.  (Run in-process, whatever the leg left
+    # behind -- most likely a fragmented small-object heap -- made the end-to-end leg's host side 18 % slower:
+    # 1.14 against 0.96 ms per step, measured with and without --no-cpu-baseline.)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         child = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only",
