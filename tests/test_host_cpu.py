@@ -277,3 +277,18 @@ def test_info_dict_builder_cpu():
         h.build_infos(infos, np.array([2] * 30 + [n + 7], dtype=np.int32), rows[:0], term[:0], 0.0, False, N.END_REASONS)
     with pytest.raises(IndexError):
         h.build_infos(infos, np.array([5, -1], dtype=np.int32), rows[:0], term[:0], 0.0, False, N.END_REASONS)
+
+
+def test_cpu_binding_helper_without_nvml():
+    """distributed.bind_to_gpu_cpus: without a driver NVML has no answer -> nothing is changed and None comes back."""
+    import os
+    from reinforcement_learning_rendezvous_b200.distributed import bind_to_gpu_cpus, gpu_cpu_affinity
+    before = os.sched_getaffinity(0)
+    cores = gpu_cpu_affinity(0)
+    assert isinstance(cores, set) and cores <= before
+    got = bind_to_gpu_cpus(0, 0, 1)
+    if not cores:
+        assert got is None and os.sched_getaffinity(0) == before
+    else:                                              # a box with a driver: bound to a non-empty subset, then restored
+        assert got and got <= cores
+        os.sched_setaffinity(0, before)
