@@ -60,7 +60,8 @@ class ActorCritic(nn.Module):
         return mean, value
 
     def distribution(self, mean):
-        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean))
+        # validate_args=False: the argument checks of torch.distributions synchronise with the device on every call
+        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean), validate_args=False)
 
     def to_mlp_policy(self, device) -> MlpPolicy:
         sd = {k: v.detach().float().cpu().numpy() for k, v in self.state_dict().items()}
@@ -104,6 +105,7 @@ class PPOConfig:
     normalize_advantage: bool = True
     n_evals: int = 50                 # custom_callbacks.py: n_evals
     fused: bool = True                # collect with the policy-fused rollout kernel (device env only)
+    cuda_graph: bool = True           # replay one captured minibatch step (forward, loss, backward, clip, Adam)
     seed: int = 0
     log: list = field(default_factory=list)
 
@@ -124,7 +126,10 @@ class PPO:
         self.device = env.device
         torch.manual_seed(self.cfg.seed)
         self.policy = (policy or ActorCritic()).to(self.device)
-        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5)
+        # capturable: the step counters live on the device, so an optimiser step can be part of a CUDA graph
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate, eps=1e-5,
+                                          capturable=bool(self.cfg.cuda_graph))
+        self._graph = None                # (CUDAGraph, static minibatch tensors, static loss tensors)
         n, T = env.num_envs, self.cfg.n_steps
         dev = self.device
         self.buf_obs = torch.empty((T, n, 17), dtype=torch.float32, device=dev)
@@ -215,34 +220,83 @@ class PPO:
         return self._gae(last_value)
 
     # -- clipped-surrogate update (PPO.train) --------------------------------------------------------------------
+    def _minibatch_step(self, obs, act, old_logp, adv, ret):
+        """One optimiser step of SB3's ``PPO.train`` on one minibatch; returns (pg_loss, value_loss, entropy)."""
+        cfg = self.cfg
+        mean, value = self.policy(obs)
+        dist = self.policy.distribution(mean)
+        logp = dist.log_prob(act).sum(-1)
+        a = adv
+        if cfg.normalize_advantage and a.numel() > 1:
+            a = (a - a.mean()) / (a.std() + 1e-8)
+        ratio = (logp - old_logp).exp()
+        pg_loss = -torch.min(a * ratio, a * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+        v_loss = nn.functional.mse_loss(ret, value)
+        ent_loss = -dist.entropy().sum(-1).mean()
+        loss = pg_loss + cfg.ent_coef * ent_loss + cfg.vf_coef * v_loss
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+        self.optimizer.step()
+        return pg_loss.detach(), v_loss.detach(), -ent_loss.detach()
+
+    def _captured_step(self, B):
+        """The minibatch step as a CUDA graph over static [B, ...] input tensors: the ~90 small kernels of forward,
+        loss, backward, gradient clipping and Adam are launch-bound at these sizes, so replaying them as one graph is
+        what sets the update rate.  Captured once per batch size, after three eager steps on a side stream (PyTorch's
+        whole-network capture recipe); those warm-up steps run on a copy of the parameters and optimiser state."""
+        if self._graph is not None and self._graph[1][0].shape[0] == B:
+            return self._graph
+        dev = self.device
+        static = (torch.zeros((B, 17), device=dev), torch.zeros((B, 6), device=dev), torch.zeros(B, device=dev),
+                  torch.linspace(-1.0, 1.0, B, device=dev), torch.zeros(B, device=dev))   # (no draw from the RNG)
+        params = list(self.policy.parameters())
+        saved_p = {k: v.detach().clone() for k, v in self.policy.state_dict().items()}
+        saved_o = {q: {k: v.clone() for k, v in self.optimizer.state[q].items() if torch.is_tensor(v)}
+                   for q in params if q in self.optimizer.state}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._minibatch_step(*static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            losses = self._minibatch_step(*static)
+        # the warm-up and the capture pass must not count as training: parameters and optimiser state go back -- IN
+        # PLACE, the graph refers to these very tensors (moments and step counters that did not exist before are zeroed)
+        self.policy.load_state_dict(saved_p)
+        with torch.no_grad():
+            for q in params:
+                for k, v in self.optimizer.state[q].items():
+                    if torch.is_tensor(v):
+                        v.copy_(saved_o[q][k]) if q in saved_o else v.zero_()
+        self._graph = (graph, static, losses)
+        return self._graph
+
     def update(self, adv, ret):
         cfg = self.cfg
         N = adv.numel()
         obs, act = self.buf_obs.reshape(N, 17), self.buf_act.reshape(N, 6)
         old_logp, adv, ret = self.buf_logp.reshape(N), adv.reshape(N), ret.reshape(N)
-        stats = {}
+        B = min(cfg.batch_size, N)
+        use_graph = bool(cfg.cuda_graph) and self.device.type == "cuda"
+        stats = ()
         for _ in range(cfg.n_epochs):
             perm = torch.randperm(N, device=self.device)
-            for s in range(0, N, cfg.batch_size):
-                idx = perm[s:s + cfg.batch_size]
-                mean, value = self.policy(obs[idx])
-                dist = self.policy.distribution(mean)
-                logp = dist.log_prob(act[idx]).sum(-1)
-                a = adv[idx]
-                if cfg.normalize_advantage and a.numel() > 1:
-                    a = (a - a.mean()) / (a.std() + 1e-8)
-                ratio = (logp - old_logp[idx]).exp()
-                pg_loss = -torch.min(a * ratio, a * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
-                v_loss = nn.functional.mse_loss(ret[idx], value)
-                ent_loss = -dist.entropy().sum(-1).mean()
-                loss = pg_loss + cfg.ent_coef * ent_loss + cfg.vf_coef * v_loss
-                self.optimizer.zero_grad(set_to_none=True)
-                loss.backward()
-                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
-                self.optimizer.step()
-                stats = {"pg_loss": float(pg_loss.detach()), "value_loss": float(v_loss.detach()),
-                         "entropy": float(-ent_loss.detach())}
-        return stats
+            for s in range(0, N, B):
+                idx = perm[s:s + B]
+                if use_graph and idx.numel() == B:
+                    graph, static, losses = self._captured_step(B)
+                    for dst, src in zip(static, (obs, act, old_logp, adv, ret)):
+                        torch.index_select(src, 0, idx, out=dst)
+                    graph.replay()
+                    stats = losses
+                else:                                       # a ragged last minibatch, or graphs switched off
+                    stats = self._minibatch_step(obs[idx], act[idx], old_logp[idx], adv[idx], ret[idx])
+        # the losses of the last minibatch, read back once (a read-back per minibatch would serialise host and device)
+        return {k: float(v) for k, v in zip(("pg_loss", "value_loss", "entropy"), stats)} if stats else {}
 
     # -- deterministic evaluation (CustomCallback._on_rollout_start / evaluate_policy) --------------------------
     @torch.no_grad()

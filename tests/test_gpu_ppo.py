@@ -52,3 +52,33 @@ def test_ppo_through_the_vecenv_drop_in():
     assert last > first + 0.01, (first, last)
     st = venv.read_stats()
     assert st["steps"] == 10 * 16 * 2048 and st["episodes"] > 0
+
+
+def test_captured_update_equals_eager_update():
+    """PPO.update with the minibatch step replayed as a CUDA graph == the same update run eagerly: same buffer, same
+    permutations -> the same parameters (the capture's warm-up steps leave no trace), also with a ragged last
+    minibatch and across two consecutive updates (Adam state carried by the graph)."""
+    import torch
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    from reinforcement_learning_rendezvous_b200.ppo import PPO, PPOConfig
+    algos = []
+    for graph in (True, False):
+        env = BatchedRendezvousEnv(1000, seed=3)
+        cfg = PPOConfig(n_steps=8, batch_size=3000, n_epochs=3, n_evals=8, seed=1, fused=True, cuda_graph=graph)
+        algos.append(PPO(env, cfg))
+    a, b = algos
+    b.policy.load_state_dict(a.policy.state_dict())
+    init = [v.clone() for v in a.policy.state_dict().values()]
+    for it in range(2):
+        adv, ret = a.collect()
+        for name in ("buf_obs", "buf_act", "buf_logp", "buf_val", "buf_rew", "buf_done"):
+            getattr(b, name).copy_(getattr(a, name))
+        torch.manual_seed(100 + it)
+        sa = a.update(adv, ret)
+        torch.manual_seed(100 + it)
+        sb = b.update(adv.clone(), ret.clone())
+        assert a._graph is not None and b._graph is None
+        for (k, pa), (_, pb) in zip(a.policy.state_dict().items(), b.policy.state_dict().items()):
+            assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-6), (it, k, (pa - pb).abs().max().item())
+        assert abs(sa["value_loss"] - sb["value_loss"]) <= 1e-4 * max(1.0, abs(sb["value_loss"]))
+    assert any((pa - pi).abs().max().item() > 1e-4 for pa, pi in zip(a.policy.state_dict().values(), init))
