@@ -197,9 +197,13 @@ def run_cuda(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         child = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only",
                                 "--cpu-seconds", str(args.cpu_seconds)], capture_output=True, text=True)
-        if child.returncode != 0:
-            raise SystemExit("cpu baseline leg failed:\n" + child.stderr[-2000:])
-        cpu_baseline = json.loads(child.stdout.strip().splitlines()[-1])
+        try:
+            if child.returncode != 0:
+                raise RuntimeError(child.stderr[-2000:])
+            cpu_baseline = json.loads(child.stdout.strip().splitlines()[-1])
+        except Exception as exc:                      # no child interpreter to be had: time the leg in this process
+            print("cpu baseline leg: child failed, running in-process:", exc, file=sys.stderr)
+            cpu_baseline = cpu_baseline_leg(args)
 
     import torch
     import torch.distributed as dist
