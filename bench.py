@@ -324,7 +324,7 @@ def run_cuda(args):
     b_step = (386.0 + 2 * 8.0 * N.RESET_ROWS + 68.0) / KL
     ach_tf = f_step * n / (t_step * 1e-3) / 1e12
     ach_gbs = b_step * n / (t_step * 1e-3) / 1e9
-    traffic, f_exec, ncu_pipe, ncu_src = None, None, None, None
+    traffic, f_exec, ncu_pipe, ncu_issue, ncu_src, ncu_steady = None, None, None, None, None, None
     try:                                # per-launch facts of the committed ncu capture of this kernel
         with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:
             tr = json.load(f)
@@ -332,7 +332,16 @@ def run_cuda(args):
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             f_exec = tr.get("fp64_flop_per_env_step_executed")
             ncu_pipe = tr.get("fp64_pipe_pct")
+            ncu_issue = tr.get("issue_active_pct")
             ncu_src = tr.get("source")
+        with open(os.path.join(ROOT, "profiles", "rollout_traffic_250steps.json")) as f:
+            ts = json.load(f)
+        if ts.get("envs") == n:         # the same kernel in one 250-step launch (steady state)
+            ncu_steady = {"steps_per_launch": ts["steps_per_launch"], "fp64_pipe_pct": ts["fp64_pipe_pct"],
+                          "issue_slots_pct": ts["issue_active_pct"], "xu_pipe_pct": ts["xu_pipe_pct"],
+                          "warp_instructions_per_warp_step": ts["warp_instructions_per_warp_step"],
+                          "fp64_instructions_per_warp_step": ts["fp64_instructions_per_warp_step"],
+                          "source": ts["source"]}
     except Exception:
         pass
     roofline = {
@@ -353,6 +362,9 @@ def run_cuda(args):
                      {"flop_per_env_step": f_exec, "achieved": f_exec * n / (t_step * 1e-3) / 1e12, "unit": "TFLOP/s",
                       "frac": f_exec * n / (t_step * 1e-3) / 1e12 / fp64_peak, "source": ncu_src}),
         "ncu_fp64_pipe_pct": ncu_pipe,
+        # the busiest unit of the SM in the same capture: the warp schedulers' issue slots (smsp__issue_active)
+        "ncu_issue_slots_pct": ncu_issue,
+        "ncu_steady_state": ncu_steady,
         "launch_ms": t_launch, "launch_ms_min": min(full), "launch_ms_max": max(full), "launches_timed": len(full),
         "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                 "bytes_per_env_step": b_step, "peak_source": peak_src},
