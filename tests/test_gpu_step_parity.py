@@ -210,6 +210,47 @@ def test_plane_solver_edge_states_vs_c_oracle():
         assert env.read_stats()["failures"] == 0
 
 
+@pytest.mark.parametrize("dt", [0.25, 1.0, 4.0])
+def test_fast_spins_take_the_general_controller_paths(dt):
+    """select_initial_step and the last attempt of a solve are shortened by bounds that hold for every body the
+    reference's ranges produce (csrc/rdv_math.cuh: RDV_INIT_LAZY_D0, RDV_INIT_NOSQRT, RDV_LAST_SHORTCUT).  Bodies that
+    spin at up to several rad/s break those bounds -- 100 h0 becomes the smallest candidate, d2 exceeds d1, steps are
+    rejected, the clipped last attempt is not trivially acceptable -- and must then follow the C oracle through the
+    general path, at every dt of the sensitivity grid, through both kernels."""
+    import torch
+    from oracle import c_oracle as CO
+    from reinforcement_learning_rendezvous_b200 import BatchedRendezvousEnv
+    n = 768
+    rng = np.random.default_rng(23)
+    st = np.zeros((n, 20))
+    st[:, 0:3] = [0.0, -10.0, 0.0] + rng.normal(0, 0.5, (n, 3))
+    st[:, 3:6] = rng.normal(0, 0.05, (n, 3))
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    qt = rng.normal(size=(n, 4)); qt /= np.linalg.norm(qt, axis=1, keepdims=True)
+    st[:, 6:10], st[:, 13:17] = q, qt
+    scale = np.repeat([0.02, 0.3, 1.0, 3.0, 6.0, 12.0], n // 6)[:, None]        # rad/s, slow to absurd
+    st[:, 10:13] = rng.uniform(-1, 1, (n, 3)) * scale
+    st[:, 17:20] = rng.uniform(-1, 1, (n, 3)) * scale[::-1]
+    a = rng.uniform(-1, 1, (2, n, 6))
+    kw = dict(dt=dt, t_max=100 * dt)
+    for fused in (False, True):
+        env = BatchedRendezvousEnv(n, seed=1, auto_reset=False, **kw)
+        env.reset()
+        env.set_state(st)
+        orc = CO.COracleBatch(CO.make_params(**kw), n)
+        orc.set_state(st, recompute_flags=True)
+        env.refresh_flags()
+        for k in range(2):
+            if fused:
+                env.rollout(1, actions=torch.as_tensor(a[k:k + 1], device=env.device))
+            else:
+                env.step(torch.as_tensor(a[k], device=env.device))
+            orc.step(a[k], threads=4)
+            assert rel_err(env.get_state().cpu().numpy(), orc.state) <= REL_TOL, (fused, k, dt)
+        stats = env.read_stats()
+        assert stats["failures"] == 0 and stats["rk_rejected"] > 0, stats      # the rejection path was exercised
+
+
 def test_closed_form_fast_path_within_tolerance():
     """The opt-in closed-form attitude propagation (exact for the env's isotropic, torque-free bodies) stays
     within the parity tolerance of the reference's RK45 at the default dt = 1 s."""
