@@ -100,6 +100,23 @@ RDV_DEV void rot_apply_T(const Rot &R, const double v[3], double o[3])          
     for (int i = 0; i < 3; ++i) o[i] = fma(R.m[6 + i], v[2], fma(R.m[3 + i], v[1], R.m[i] * v[0]));
 }
 
+// R(q / |q|) v for ONE vector without forming the matrix: v + 2 w (u x v) + 2 u x (u x v) with q / |q| = (w, u) --
+// 32 fp64 operations against 48 for quat2mat (including its re-normalisation) plus one matrix-vector product.
+// Same rotation as rot_apply(rot_from_quat(q), v) to rounding.
+#ifndef RDV_QUAT_ROTATE
+#define RDV_QUAT_ROTATE 0
+#endif
+RDV_DEV void quat_rotate(const double q[4], const double v[3], double o[3])
+{
+    const double r = fast_rsqrt(dot4(q, q));
+    const double w = q[0] * r, u[3] = {q[1] * r, q[2] * r, q[3] * r};
+    double c[3], d[3];
+    cross3(u, v, c);
+    cross3(u, c, d);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = fma(2.0, fma(w, c[i], d[i]), v[i]);
+}
+
 // sqrt(x) for x >= 0 (<= 1 ulp): x * rsqrt(x)
 RDV_DEV double fast_sqrt(double x) { return x > 0.0 ? x * fast_rsqrt(x) : 0.0; }
 

@@ -52,9 +52,13 @@ RDV_DEV void ingest_action_f32(const RdvParams &P, const float (&a)[6], EnvCount
 // first half of env_advance: the impulse rotated by the OLD chaser attitude, then the CW transition
 RDV_DEV void env_translate(const RdvParams &P, EnvRegs &e, const ActionTerms &t)
 {
-    const Rot Rc_old = rot_from_quat(e.qc);
     double dv[3];
+#if RDV_QUAT_ROTATE
+    quat_rotate(e.qc, t.dvb, dv);                  // one vector: no matrix
+#else
+    const Rot Rc_old = rot_from_quat(e.qc);
     rot_apply(Rc_old, t.dvb, dv);
+#endif
     const double r0 = e.rc[0], r1 = e.rc[1], r2 = e.rc[2];
     const double v0 = e.vc[0] + dv[0], v1 = e.vc[1] + dv[1], v2 = e.vc[2] + dv[2];
     const double *c = P.cw;
@@ -143,9 +147,25 @@ template <bool WANT_OBS = true, bool DETAIL = false>
 RDV_DEV StepResult env_evaluate(const RdvParams &P, const EnvRegs &e, const double fuel, EnvCounters &c,
                                 float (&ov)[RDV_OBS_DIM], EvalDetail *detail = nullptr)
 {
-    const Rot Rc = rot_from_quat(e.qc);
     const double rc_sq = dot3(e.rc, e.rc);
+#if RDV_QUAT_ROTATE
+    // far from the target only the capture axis is rotated by the chaser's attitude (one vector: no matrix)
+    const bool near = DETAIL || rc_sq < P.near_sq;
+    Rot Rc;
+    double att;
+    if (near) {
+        Rc = rot_from_quat(e.qc);
+        att = attitude_error(P, e, Rc, rc_sq);
+    } else {
+        double cap[3];
+        quat_rotate(e.qc, P.capture_axis, cap);
+        att = rounded_angle_from(-dot3(e.rc, cap), rc_sq, dot3(cap, cap));
+    }
+#else
+    const bool near = DETAIL || rc_sq < P.near_sq;
+    const Rot Rc = rot_from_quat(e.qc);
     const double att = attitude_error(P, e, Rc, rc_sq);
+#endif
     // The target-relative quantities (corridor angle, position / velocity / rate errors) only matter near the
     // target: a collision needs |rc| < koz, and success (:406-422) or the reward bonus (:348-351) need a position
     // error <= max_rd_error, impossible unless | |rc| - |rd| | <= max_rd_error (|R(qt) rd| = |rd|).  Far away
@@ -153,7 +173,7 @@ RDV_DEV StepResult env_evaluate(const RdvParams &P, const EnvRegs &e, const doub
     bool col_now = false;
     ErrSq es;
     es.pos = es.vel = es.rot = 1.0e300;
-    if (DETAIL || rc_sq < P.near_sq) {
+    if (near) {
         const Rot Rt = rot_from_quat(e.qt);
         if (DETAIL) {
             // the evaluator's own forms (errors_kernel): IEEE square roots, the corridor angle at any distance
