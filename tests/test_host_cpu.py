@@ -292,3 +292,17 @@ def test_cpu_binding_helper_without_nvml():
     else:                                              # a box with a driver: bound to a non-empty subset, then restored
         assert got and got <= cores
         os.sched_setaffinity(0, before)
+
+
+def test_bench_cpu_baseline_leg_runs_in_a_child():
+    """bench.py times its cpu_baseline object in a child interpreter (`--cpu-baseline-only`): one JSON line with the
+    keys the contract asks for, no CUDA needed."""
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--cpu-baseline-only", "--cpu-seconds", "1.0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    c = json.loads(lines[0])
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "env-steps/s"
+    assert "sample" in c and c["single_process_value"] > 0 and c["c_port_value"] > 0
