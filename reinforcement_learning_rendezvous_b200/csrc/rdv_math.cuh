@@ -89,6 +89,17 @@ RDV_DEV Rot rot_from_quat(const double q_in[4])
     R.m[6] = 2.0 * fma(x, z, -(w * y)); R.m[7] = 2.0 * fma(y, z, w * x); R.m[8] = fma(2.0, fma(z, z, ww), -1.0);
     return R;
 }
+// the same matrix for a quaternion that is already a unit vector (no re-normalisation)
+RDV_DEV Rot rot_from_unit_quat(const double q[4])
+{
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double ww = w * w;
+    Rot R;
+    R.m[0] = fma(2.0, fma(x, x, ww), -1.0); R.m[1] = 2.0 * fma(x, y, -(w * z)); R.m[2] = 2.0 * fma(x, z, w * y);
+    R.m[3] = 2.0 * fma(x, y, w * z); R.m[4] = fma(2.0, fma(y, y, ww), -1.0); R.m[5] = 2.0 * fma(y, z, -(w * x));
+    R.m[6] = 2.0 * fma(x, z, -(w * y)); R.m[7] = 2.0 * fma(y, z, w * x); R.m[8] = fma(2.0, fma(z, z, ww), -1.0);
+    return R;
+}
 RDV_DEV void rot_apply(const Rot &R, const double v[3], double o[3])            // body -> LVLH (:490-508)
 {
 #pragma unroll
