@@ -84,7 +84,7 @@ def test_last_attempt_bound_implies_scipy_accepts():
             for h in (1e-3, 0.03, 0.1, 0.3, 0.9, 2.0):
                 y_new, f_new = rk_step(_fun, 0.0, y0, f0, h, RK45.A, RK45.B, RK45.C, K := np.empty((7, 7)))
                 e = np.dot(K.T, RK45.E) * h
-                assert np.all(np.abs(e[4:]) < 1e-30)                           # the rates carry no error (w' = 0 to rounding)
+                assert np.all(np.abs(e[4:]) < 1e-15)           # the rates carry no error (w' = w x I w / I: rounding noise)
                 # the kernel's bound, from the plane coordinates of the error estimate (q0 is orthogonal to p)
                 ea = np.dot(e[:4], q0) / np.dot(q0, q0)
                 eb = np.dot(e[:4], p) / np.dot(p, p) if np.dot(p, p) > 0 else 0.0
@@ -95,6 +95,6 @@ def test_last_attempt_bound_implies_scipy_accepts():
                 if ub < 0.99:
                     accepted_by_bound += 1
                     assert err2 < 1.0, (rate, h, ub, err2)
-                    assert err2 <= ub + 1e-20          # an upper bound (SciPy's 4-component rounding noise lies off the plane)
+                    assert err2 <= ub + 1e-16          # an upper bound (SciPy's 7-component rounding noise lies off the plane)
     # the bound decides a good share of these attempts (the clipped last step of a solve is a short one)
     assert accepted_by_bound > 0.3 * total, (accepted_by_bound, total)
